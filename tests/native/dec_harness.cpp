@@ -1,0 +1,81 @@
+// TEST-ONLY host build of the decimal / fixed-point headers (phanotate_b200/csrc/*.cuh are
+// __host__ __device__).  Lets tests/test_dec_host.py compare every arithmetic primitive with
+// Python's decimal (libmpdec) on the CPU box.  Not part of the product, never loaded by it.
+#include "../../phanotate_b200/csrc/fxpow.cuh"
+#include "../../phanotate_b200/csrc/frepr.cuh"
+
+struct TDec {
+    u64 lo, hi;
+    i32 e, neg;
+};
+static Dec in(const TDec& t) {
+    Dec d;
+    d.c.w[0] = (u32)t.lo;
+    d.c.w[1] = (u32)(t.lo >> 32);
+    d.c.w[2] = (u32)t.hi;
+    d.c.w[3] = (u32)(t.hi >> 32);
+    d.e = t.e;
+    d.neg = t.neg;
+    return d;
+}
+static TDec out(const Dec& d) {
+    TDec t;
+    t.lo = d.c.w[0] | ((u64)d.c.w[1] << 32);
+    t.hi = d.c.w[2] | ((u64)d.c.w[3] << 32);
+    t.e = d.e;
+    t.neg = d.neg;
+    return t;
+}
+extern "C" {
+void t_binop(int op, int n, const TDec* a, const TDec* b, int prec, TDec* o) {
+    for (int i = 0; i < n; i++) {
+        Dec x = in(a[i]), y = in(b[i]), r;
+        switch (op) {
+            case 0: r = dec_add(x, y, prec); break;
+            case 1: r = dec_sub(x, y, prec); break;
+            case 2: r = dec_mul(x, y, prec); break;
+            default: r = dec_div(x, y, prec); break;
+        }
+        o[i] = out(r);
+    }
+}
+void t_powi(int n, const TDec* a, const u32* nn, int prec, TDec* o) {
+    for (int i = 0; i < n; i++) o[i] = out(dec_powi(in(a[i]), nn[i], prec));
+}
+// y given as Decimal
+void t_powr(int n, const TDec* a, const TDec* y, int prec, TDec* o, int* okv) {
+    for (int i = 0; i < n; i++) {
+        bool ok1, ok2;
+        Dec yy = in(y[i]);
+        int yneg = yy.neg;
+        yy.neg = 0;
+        Fx Y = fx_from_dec(yy, &ok1);
+        o[i] = out(dec_pow_fx(in(a[i]), Y, yneg, prec, &ok2));
+        okv[i] = ok1 && ok2;
+    }
+}
+// y given as a double (exact binary value, like Decimal(length/3))
+void t_powd(int n, const TDec* a, const double* y, int prec, TDec* o, int* okv) {
+    for (int i = 0; i < n; i++) {
+        bool ok2;
+        Fx Y = fx_from_double(fabs(y[i]));
+        o[i] = out(dec_pow_fx(in(a[i]), Y, y[i] < 0, prec, &ok2));
+        okv[i] = ok2;
+    }
+}
+void t_repr(int n, const double* v, TDec* o, int* okv) {
+    for (int i = 0; i < n; i++) {
+        bool ok;
+        o[i] = out(dec_from_double_repr(v[i], &ok));
+        okv[i] = ok;
+    }
+}
+void t_milli(int n, const TDec* a, u32* mag /* n x 8 */, int* okv) {
+    for (int i = 0; i < n; i++) {
+        Wide<8> m;
+        w_zero(m);
+        okv[i] = dec_to_milli_int<8>(in(a[i]), m);
+        for (int j = 0; j < 8; j++) mag[i * 8 + j] = m.w[j];
+    }
+}
+}

@@ -1,0 +1,202 @@
+"""Host-side unit tests of the decimal / fixed-point headers against Python's decimal (libmpdec).
+
+The headers under phanotate_b200/csrc are __host__ __device__; tests/native/dec_harness.cpp compiles
+them with g++ so that the arithmetic the CUDA kernels run can be checked digit for digit here, on the
+CPU box.  The harness is test infrastructure: the product never loads it.
+"""
+import ctypes
+import os
+import random
+import subprocess
+from decimal import Decimal, getcontext, localcontext
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "native", "dec_harness.cpp")
+SO = os.path.join(HERE, "native", "dec_harness.so")
+
+TDEC = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("e", "<i4"), ("neg", "<i4")])
+
+
+@pytest.fixture(scope="module")
+def lib():
+    deps = [SRC] + [os.path.join(HERE, "..", "phanotate_b200", "csrc", f)
+                    for f in ("wide.cuh", "dec.cuh", "fxpow.cuh", "frepr.cuh", "tables.inc")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+def pack(vals):
+    a = np.zeros(len(vals), dtype=TDEC)
+    for i, d in enumerate(vals):
+        s, digits, e = Decimal(d).as_tuple()
+        c = int("".join(map(str, digits)))
+        a[i] = (c & (2 ** 64 - 1), c >> 64, e, s)
+    return a
+
+
+def unpack(a):
+    out = []
+    for r in a:
+        c = int(r["lo"]) | (int(r["hi"]) << 64)
+        out.append(Decimal((int(r["neg"]), tuple(map(int, str(c))), int(r["e"]))))
+    return out
+
+
+def same(a: Decimal, b: Decimal):
+    return a.as_tuple() == b.as_tuple()
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def rand_dec(rng, maxd=28):
+    nd = rng.choice([1, 2, 3, 5, 14, 27, 28, maxd])
+    c = rng.randrange(0, 10 ** nd)
+    if rng.random() < 0.15:
+        c = c - c % (10 ** rng.randrange(0, nd + 1))     # trailing zeros
+    if rng.random() < 0.05:
+        c = 10 ** rng.randrange(0, nd + 1)               # powers of ten / rounding-carry cases
+    if rng.random() < 0.05:
+        c = 10 ** nd - 1
+    e = rng.choice([0, 0, -1, -5, -27, -28, -29, -30, -40, -56, -84, 3, 12, 25])
+    return Decimal((rng.random() < 0.3, tuple(map(int, str(c))), e))
+
+
+def binop(lib, op, xs, ys, prec=28):
+    a, b = pack(xs), pack(ys)
+    o = np.zeros(len(xs), dtype=TDEC)
+    lib.t_binop(op, len(xs), P(a), P(b), prec, P(o))
+    return unpack(o)
+
+
+@pytest.mark.parametrize("op,fn", [(0, lambda x, y: x + y), (1, lambda x, y: x - y),
+                                    (2, lambda x, y: x * y), (3, lambda x, y: x / y)])
+def test_binops_match_decimal(lib, op, fn):
+    rng = random.Random(1234 + op)
+    xs = [rand_dec(rng) for _ in range(40000)]
+    ys = [rand_dec(rng) for _ in range(40000)]
+    if op == 3:
+        ys = [y if y != 0 else Decimal(7) for y in ys]
+    got = binop(lib, op, xs, ys)
+    getcontext().prec = 28
+    for x, y, g in zip(xs, ys, got):
+        assert same(fn(x, y), g), (op, x, y, fn(x, y), g)
+
+
+def test_path_specific_identities(lib):
+    # the mixed int/Decimal forms the reference uses (functions.py:26-46,140,174-178; orfs.py:168-173)
+    p = Decimal("0.05520932534679849777229484991")
+    cases = [(1, Decimal(1), p), (1, Decimal(1), Decimal("0E-84")), (3, Decimal(1), Decimal("0.05")),
+             (0, Decimal(0), p), (3, Decimal(3), Decimal(6)), (3, Decimal(24), Decimal(96)),
+             (0, Decimal("1.000000000000000000000000000"), Decimal(20)), (3, Decimal(0), Decimal(93)),
+             (2, Decimal("0E-28"), p), (0, Decimal("0E-56"), Decimal("0E-57"))]
+    for op, x, y in cases:
+        want = [lambda: x + y, lambda: x - y, lambda: x * y, lambda: x / y][op]()
+        assert same(want, binop(lib, op, [x], [y])[0]), (op, x, y)
+
+
+def test_integer_power_follows_libmpdec(lib):
+    rng = random.Random(99)
+    xs, ns = [], []
+    for _ in range(20000):
+        p = Decimal(rng.randrange(1, 15 * 10 ** 26)) / Decimal(10 ** 28)
+        xs.append(1 - p)
+        ns.append(rng.choice([1, 2, 3, 4, 7, 33, 99, 100, 101, 255, 256, 333, 499, 502]))
+    xs += [Decimal(1), Decimal("1.000"), Decimal("1.000000000000000000000000000"), Decimal("0.953125"), Decimal("0.5")]
+    ns += [5, 3, 100, 0, 10]
+    a = pack(xs)
+    nn = np.array(ns, dtype=np.uint32)
+    o = np.zeros(len(xs), dtype=TDEC)
+    lib.t_powi(len(xs), P(a), P(nn), 28, P(o))
+    for x, n, g in zip(xs, ns, unpack(o)):
+        assert same(x ** Decimal(n), g), (x, n, x ** Decimal(n), g)
+
+
+def test_real_power_decimal_exponent(lib):
+    # stage E: ((1-pstop)**pos_max[i])**pos_min[j]  (functions.py:293,298)
+    rng = random.Random(5)
+    xs, ys = [], []
+    for _ in range(30000):
+        kind = rng.random()
+        if kind < 0.6:
+            x = 1 - Decimal(rng.randrange(1, 15 * 10 ** 26)) / Decimal(10 ** 28)
+        elif kind < 0.8:
+            x = 1 - Decimal(rng.randrange(1, 10 ** 12)) / Decimal(10 ** rng.choice([13, 18, 24, 28]))
+        else:
+            x = Decimal(rng.randrange(10 ** 27, 10 ** 28)) / Decimal(10 ** 28)   # any value in (0.1, 1)
+        cnt = rng.randrange(2, 200000)
+        y = Decimal(rng.randrange(1, cnt)) / Decimal(cnt)
+        xs.append(+x)
+        ys.append(y)
+    xs += [Decimal(1), Decimal("1.000000000000000000000000000"), Decimal("0.9999999999999999999999999999")]
+    ys += [Decimal("0.5"), Decimal("0.3333333333333333333333333333"), Decimal("0.0001531628120692295910552917752")]
+    a, b = pack(xs), pack(ys)
+    o = np.zeros(len(xs), dtype=TDEC)
+    ok = np.zeros(len(xs), dtype=np.int32)
+    lib.t_powr(len(xs), P(a), P(b), 28, P(o), P(ok))
+    assert ok.all()
+    for x, y, g in zip(xs, ys, unpack(o)):
+        assert same(x ** y, g), (x, y, x ** y, g)
+
+
+def test_real_power_float_exponent(lib):
+    # score_gap: g ** Decimal(length/3) with length/3 a Python float (functions.py:41-43)
+    rng = random.Random(6)
+    xs, ys = [], []
+    for _ in range(300):
+        g = 1 - Decimal(rng.randrange(10 ** 26, 15 * 10 ** 26)) / Decimal(10 ** 28)
+        for length in range(-2, 301):
+            if length % 3 == 0:
+                continue
+            xs.append(g)
+            ys.append(length / 3)
+    a = pack(xs)
+    yv = np.array(ys, dtype=np.float64)
+    o = np.zeros(len(xs), dtype=TDEC)
+    ok = np.zeros(len(xs), dtype=np.int32)
+    lib.t_powd(len(xs), P(a), P(yv), 28, P(o), P(ok))
+    assert ok.all()
+    for x, y, g in zip(xs, ys, unpack(o)):
+        assert same(x ** Decimal(y), g), (x, y)
+
+
+def test_decimal_of_float_repr(lib):
+    # Orf.score: Decimal(str(weight_rbs)) (orfs.py:126)
+    rng = random.Random(7)
+    vals = [1.0, 100.0, 1e15, 1e16, 1e-4, 1e-5, 0.1, 123456.75, 5e-324 * 0 + 2.5, 1 / 3, 2 / 3, 1e22, 9.999999999999999e22]
+    for _ in range(100000):
+        n1, n2 = rng.randrange(1, 5000), rng.randrange(28, 10 ** 7)
+        m1, m2 = rng.randrange(1, 10 ** 6), rng.randrange(28, 2 * 10 ** 7)
+        vals.append((n1 / n2) / (m1 / m2))
+    for _ in range(20000):
+        vals.append(rng.random() * 10 ** rng.randrange(-9, 12))
+    v = np.array(vals, dtype=np.float64)
+    o = np.zeros(len(v), dtype=TDEC)
+    ok = np.zeros(len(v), dtype=np.int32)
+    lib.t_repr(len(v), P(v), P(o), P(ok))
+    assert ok.all()
+    for x, g in zip(vals, unpack(o)):
+        assert same(Decimal(str(x)), g), (x, str(x), g)
+
+
+def test_milli_integer(lib):
+    rng = random.Random(8)
+    xs = [rand_dec(rng) for _ in range(5000)] + [Decimal("-6.1E+28"), Decimal("1.2345E+50"), Decimal("-0.0004")]
+    a = pack(xs)
+    mag = np.zeros((len(xs), 8), dtype=np.uint32)
+    ok = np.zeros(len(xs), dtype=np.int32)
+    lib.t_milli(len(xs), P(a), P(mag), P(ok))
+    for x, m, k in zip(xs, mag, ok):
+        want = abs(int((x * 1000).to_integral_value(rounding="ROUND_DOWN")))
+        if want < 2 ** 255 and want < 10 ** 72:
+            assert k
+            got = sum(int(v) << (32 * i) for i, v in enumerate(m))
+            with localcontext() as ctx:
+                ctx.prec = 100
+                want = abs(int((x * 1000).to_integral_value(rounding="ROUND_DOWN")))
+            assert got == want, (x, got, want)
