@@ -1,0 +1,143 @@
+/* phanotate_b200 -- C ABI of the B200-native PHANOTATE hot path.
+ *
+ * One call processes a BATCH of contigs: six-frame ORF scan + RBS / start-codon / GC-frame
+ * scoring, ORF/gap/overlap graph, exact shortest path, CDS call table.  This is what a
+ * maintainer of the reference binds (ctypes) in place of the per-contig
+ * Python calls in /root/reference/phanotate.py:40-76:
+ *
+ *   functions.get_orfs(locus)          phanotate_modules/functions.py:143-303   -> pb200_run + pb200_get_orfs
+ *   functions.get_graph(orfs)          phanotate_modules/functions.py:307-454   -> pb200_build_edges + pb200_get_nodes/edges
+ *   fz.empty_graph / add_edge / get_path   phanotate.py:56-64 (third-party fastpathz)
+ *                                                                              -> inside pb200_run; pb200_bellman_ford for
+ *                                                                                 an arbitrary edge list
+ *   path -> CDS features               phanotate.py:65-76, locus.py:29-37       -> pb200_get_calls
+ *
+ * Plain pointers and sizes only.  Input buffers are caller-owned; result tables are owned by the
+ * context and valid until the next pb200_run / pb200_destroy.  Every function returns 0 on
+ * success or a negative code; pb200_last_error() gives the text.  A context is bound to one CUDA
+ * device and one stream and must not be used from two threads at once (the reference is
+ * single-threaded; its solver keeps module-global state, phanotate.py:56).
+ */
+#ifndef PHANOTATE_B200_H
+#define PHANOTATE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* decimal number sign * c * 10^e, c < 10^38 as four little-endian 32-bit limbs: the reference's
+ * Decimal values (prec 28) cross the boundary digit for digit */
+typedef struct pb200_dec {
+    uint32_t c[4];
+    int32_t e;
+    int32_t neg;
+} pb200_dec;
+
+/* the five scoring parameters of file_handling.get_args (file_handling.py:46-66) */
+typedef struct pb200_params {
+    int32_t n_start;            /* <= 8 */
+    char start_codon[8][4];     /* lower-case acgt, NUL padded */
+    pb200_dec start_weight[8];  /* already divided by the max weight (file_handling.py:58-62) */
+    int32_t n_stop;             /* <= 8 */
+    char stop_codon[8][4];
+    int32_t min_orf_len;        /* -l/--minlen, default 90; must be >= 9 */
+    int32_t reserved;
+} pb200_params;
+
+typedef struct pb200_call {     /* one CDS row of Locus.tabular (locus.py:39-56) */
+    int32_t contig;
+    int32_t left;               /* entry node position              (phanotate.py:72-74) */
+    int32_t right;              /* exit node position + 2           (locus.py:30)        */
+    int32_t strand;             /* +1 / -1 = sign(left.frame)                             */
+    pb200_dec weight;           /* graph.weight(Edge(left,right)) = Orf.weight           */
+    double score;               /* float(weight), what '%E' prints  (phanotate.py:75-76) */
+} pb200_call;
+
+typedef struct pb200_orf {      /* Orf (orfs.py:71-95) */
+    int32_t contig, start, stop, frame;   /* start/stop = leftmost base of the codon, frame = +-1..3 */
+    int32_t rbs_score;
+    int32_t trigger;            /* scan position at which the reference emits the ORF (insertion order) */
+    int32_t start_weight;       /* index into start_codon[] or -1 */
+    int32_t node;               /* start node id */
+    pb200_dec pstop, weight;
+} pb200_orf;
+
+typedef struct pb200_node {     /* Node (nodes.py:2-21); ids are global over the batch, sorted by contig, position */
+    int32_t contig, position;
+    int32_t kind;               /* 0 (start,+f) entry, 1 (stop,+f) exit, 2 (stop,-f) entry, 3 (start,-f) exit */
+    int32_t frame;              /* 1..3 */
+    int32_t mate;               /* start node: its stop-key node; stop-key node: farthest start node */
+    int32_t orf;                /* start node: its ORF; stop-key node: the family's longest ORF */
+    int32_t other_end;          /* Orfs.other_end[position] (orfs.py:22-30) */
+    int32_t trigger;
+} pb200_node;
+
+enum { PB200_EDGE_ORF = 0, PB200_EDGE_GAP = 1, PB200_EDGE_OVERLAP = 2, PB200_EDGE_BRIDGE = 3,
+       PB200_EDGE_SOURCE = 4, PB200_EDGE_TARGET = 5 };
+#define PB200_NODE_SOURCE (-2)
+#define PB200_NODE_TARGET (-3)
+typedef struct pb200_edge {     /* Edge (edges.py:3-23) */
+    int32_t contig, src, dst, kind;
+    pb200_dec weight;
+} pb200_edge;
+
+typedef struct pb200_contig {
+    int32_t length;
+    uint32_t err;               /* PB200_ERR_* bits */
+    int32_t node_off, n_nodes, orf_off, n_orfs, call_off, n_calls;
+    int32_t n_ties;             /* relaxations that found an equal distance (tie-break diagnostics) */
+    int32_t reserved;
+    pb200_dec pstop;            /* contig-level P(stop) = pgap (functions.py:178,309) */
+    pb200_dec pos_max[4], pos_min[4];   /* GC-frame exponents (functions.py:281-284) */
+    double background_rbs[28], training_rbs[28];
+} pb200_contig;
+
+enum {
+    PB200_ERR_CHAR = 1,      /* letter outside the IUPAC alphabet: the reference raises KeyError */
+    PB200_ERR_RANGE = 2,
+    PB200_ERR_PARALLEL = 4,  /* the reference raises ValueError("parallel edges are forbidden") */
+    PB200_ERR_OVERFLOW = 8,
+    PB200_ERR_NOPATH = 16,
+    PB200_ERR_INTERNAL = 32,
+    PB200_ERR_LOOKUP = 64
+};
+
+enum { PB200_INPUT_DEVICE = 1 };   /* flags of pb200_run: bases/offsets are device pointers */
+
+typedef struct pb200_ctx pb200_ctx;
+
+int pb200_create(int device, pb200_ctx** out);
+void pb200_destroy(pb200_ctx* ctx);
+const char* pb200_last_error(pb200_ctx* ctx);
+
+/* bases: concatenated contig letters (any case, 15 IUPAC codes); offsets[n_contigs+1]. */
+int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs,
+              const pb200_params* params, uint32_t flags);
+
+/* out[0..7] = n_contigs, n_bases, n_nodes, n_orfs, n_overlap_edges, n_bridge_edges, n_calls, n_edges */
+int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
+int pb200_get_calls(pb200_ctx* ctx, pb200_call* out);
+int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out);
+int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out);
+int pb200_get_nodes(pb200_ctx* ctx, pb200_node* out);
+/* materialise every edge of get_graph (gap edges included) for the last batch */
+int pb200_build_edges(pb200_ctx* ctx);
+int pb200_get_edges(pb200_ctx* ctx, pb200_edge* out);
+
+/* fastpathz-compatible solve of an arbitrary graph: exact integers (8 little-endian 32-bit limbs,
+ * two's complement, per edge), edges relaxed in the given order with strict '<' until a pass
+ * changes nothing.  path_out receives node ids source..target; *path_len = 0 if unreachable. */
+int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const int32_t* src,
+                       const int32_t* dst, const uint32_t* weight_limbs, int32_t source, int32_t target,
+                       int32_t* path_out, int32_t* path_len);
+
+/* device time of the stages of the last pb200_run in milliseconds (CUDA events on the context's
+ * stream); names[i] are static strings.  Returns the number of stages written (<= cap). */
+int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);
+/* number of kernels launched by the last pb200_run */
+int pb200_launch_count(pb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,582 @@
+// Graph stages (functions.py:307-454) and the exact shortest path (phanotate.py:53-65 + the
+// fastpathz contract, CHANGELOG.md:11-13,54,57).
+//
+// Nodes are sorted by (contig, position).  entry = forward start / reverse stop-key, exit =
+// forward stop-key / reverse start; every connector goes exit -> entry, every ORF edge entry ->
+// exit.  Gap edges (exit l -> entry r, 0 < r-l < 500) are never materialised for the
+// solve: their weight is a table lookup on r-l.  Overlap edges (exit r -> entry l, backwards) need
+// a 33-digit integer power each and are stored in CSR by source node.  Bridges over >500-bp
+// uncovered runs are rare and stored per contig.
+#pragma once
+#include "score.cuh"
+#include "dec2double.cuh"
+
+PB_HD bool kind_is_entry(int k) { return k == K_FSTART || k == K_RSTOP; }
+PB_HD int contig_of_node(const Batch& B, i32 ni) {
+    int lo = 0, hi = B.nc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.cnode[mid] <= ni) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Stage 8: other_end[] and the pstop used for overlap averaging, per node, with the reference's
+// bare-position dict semantics at the six positions where two roles share a key (orfs.py:17-32,
+// functions.py:362-385).  item = node
+PB_HDN void st_node_attrs(const Batch& B, i64 ni64) {
+    if (ni64 >= B.nn) return;
+    const i32 ni = (i32)ni64;
+    const int c = contig_of_node(B, ni);
+    const int kind = B.n_kind[ni] & 3;
+    const int p = B.n_pos[ni];
+    i32 oth, oidx;
+    if (kind == K_FSTART || kind == K_RSTART) {
+        oth = B.o_stop[B.n_orf[ni]];
+        oidx = -1;
+    } else {
+        oth = B.n_pos[B.n_mate[ni]];
+        oidx = B.n_orf[ni];
+    }
+    i32 twin = -1;
+    if (ni > B.cnode[c] && B.n_pos[ni - 1] == p) twin = ni - 1;
+    else if (ni + 1 < B.cnode[c + 1] && B.n_pos[ni + 1] == p) twin = ni + 1;
+    if (twin >= 0) {
+        const int tk = B.n_kind[twin] & 3;
+        i32 F = -1, R = -1, C = -1, V = -1;
+        if (kind == K_FSTART) F = ni; else if (kind == K_RSTOP) R = ni; else if (kind == K_FSTOP) C = ni; else V = ni;
+        if (tk == K_FSTART) F = twin; else if (tk == K_RSTOP) R = twin; else if (tk == K_FSTOP) C = twin; else V = twin;
+        if (F >= 0 && R >= 0) {
+            // left end: forward ORF starting at p and reverse family keyed at p share other_end[p]
+            i32 trigF = B.n_trig[B.n_mate[F]], trigR = B.n_trig[R];
+            if (trigF < trigR) {         // family R is inserted later and overwrites
+                oth = B.n_pos[B.n_mate[R]];
+                oidx = B.n_orf[R];
+            } else {                     // the forward ORF is inserted later: other_end[p] = its stop
+                oth = B.o_stop[B.n_orf[F]];
+                oidx = B.n_orf[F];       // p is a stop key but other_end[p] is not in its family -> get_orf(p, other_end[p])
+            }
+        } else if (C >= 0 && V >= 0) {
+            // right end: forward family keyed at p is inserted first, the reverse ORF starting at p last
+            oth = B.o_stop[B.n_orf[V]];
+            if (B.n_pos[B.n_mate[C]] == oth) oidx = B.n_orf[C];
+            else oidx = B.n_orf[V];
+        } else {
+            PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_INTERNAL);
+        }
+    }
+    B.n_oth[ni] = oth;
+    B.n_oidx[ni] = oidx;
+}
+
+// overlap predicate for (left entry e at l, right exit x at r), functions.py:400-438
+PB_HD int overlap_kind(const Batch& B, i32 e, i32 x) {     // 0 none, 1 'same', 2 'diff'
+    const int ke = B.n_kind[e] & 3, kx = B.n_kind[x] & 3;
+    const int fe = B.n_kind[e] >> 2, fx = B.n_kind[x] >> 2;
+    const int l = B.n_pos[e], r = B.n_pos[x];
+    const int lo = B.n_oth[e], ro = B.n_oth[x];
+    if (ke == K_FSTART && kx == K_FSTOP) return (fe != fx && r < lo && ro < l) ? 1 : 0;
+    if (ke == K_RSTOP && kx == K_RSTART) return (fe != fx && r < lo && ro < l) ? 1 : 0;
+    if (ke == K_RSTOP && kx == K_FSTOP) return (ro + 3 < l && r < lo) ? 2 : 0;
+    if (ke == K_FSTART && kx == K_RSTART) return (ro < l && r < lo) ? 2 : 0;
+    return 0;
+}
+PB_HD Dec node_o(const Batch& B, int c, i32 n) { return B.n_oidx[n] < 0 ? B.cs[c].pstop : B.o_pstop[B.n_oidx[n]]; }
+// score_overlap(r-l+3, dir, ave([o1,o2]))  (functions.py:26-34,140-141,386)
+PB_HDN Dec overlap_score(const Batch& B, int c, i32 e, i32 x, bool diff) {
+    Dec t = dec_add(dec_from_u64(0), node_o(B, c, e));
+    t = dec_add(t, node_o(B, c, x));
+    Dec pbar = dec_div(t, dec_from_u64(2));
+    Dec o = dec_sub(dec_one(), pbar);
+    Dec sc = dec_powi(o, (u32)(B.n_pos[x] - B.n_pos[e] + 3));
+    sc = dec_div(dec_one(), sc);
+    if (diff) sc = dec_add(sc, dec_twenty());
+    return sc;
+}
+// Stage 9/10: overlap edges out of exit node ni.  fill=false counts, fill=true writes.
+PB_HDN void overlaps_of(const Batch& B, i32 ni, bool fill) {
+    const int kind = B.n_kind[ni] & 3;
+    u32 cnt = 0;
+    if (!kind_is_entry(kind)) {
+        const int c = contig_of_node(B, ni);
+        const int r = B.n_pos[ni];
+        u32 k = fill ? B.ov_cnt[ni] : 0;
+        for (i32 j = ni - 1; j >= B.cnode[c] && r - B.n_pos[j] < 500; j--) {
+            if (B.n_pos[j] >= r) continue;
+            int ok = overlap_kind(B, j, ni);
+            if (!ok) continue;
+            if (fill) {
+                Dec w = overlap_score(B, c, j, ni, ok == 2);
+                B.ov_dst[k] = j;
+                B.ov_w[k] = w;
+                WInt wi;
+                if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+                B.ov_wint[k] = wi;
+                k++;
+            }
+            cnt++;
+        }
+    }
+    if (!fill) B.ov_cnt[ni] = cnt;
+}
+PB_HDN void st_ov_count(const Batch& B, i64 ni) {
+    if (ni < B.nn) overlaps_of(B, (i32)ni, false);
+}
+PB_HDN void st_ov_fill(const Batch& B, i64 ni) {
+    if (ni < B.nn) overlaps_of(B, (i32)ni, true);
+}
+
+// Stage 11: bridges over uncovered runs longer than 500 bp (functions.py:320-354).  item = contig
+PB_HDN void bridges_of(const Batch& B, int c, bool fill) {
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    const int L = B.cs[c].L;
+    u32 cnt = 0;
+    u32 k = fill ? B.br_cnt[c] : 0;
+    int last = 0;
+    for (i32 i = nb; i < ne; i++) {
+        const int kind = B.n_kind[i] & 3;
+        int mi, ma;
+        if (kind == K_RSTOP) {
+            mi = B.n_pos[i];
+            ma = B.n_pos[B.n_mate[i]];
+        } else if (kind == K_FSTART && B.n_mate[B.n_mate[i]] == i) {   // the longest ORF of its family
+            mi = B.n_pos[i];
+            ma = B.n_pos[B.n_mate[i]];
+        } else continue;
+        int me = ma < L - 1 ? ma : L - 1;       // covered: mi .. me-1
+        if (me <= mi) continue;
+        if (mi > last && mi - last > 500) {
+            const int base = mi;
+            // left: exits with last-500 < l <= last+1 ; right: entries with base-1 <= r < base+500
+            for (i32 r = i; r < ne && B.n_pos[r] < base + 500; r++) {
+                if (B.n_pos[r] < base - 1 || !kind_is_entry(B.n_kind[r] & 3)) continue;
+                for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
+                    if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
+                    int len = B.n_pos[r] - B.n_pos[l] - 3;
+                    if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
+                    if (fill) {
+                        Dec w = gap_score(B, c, len, false);
+                        B.br_src[k] = l;
+                        B.br_dst[k] = r;
+                        B.br_w[k] = w;
+                        WInt wi;
+                        if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+                        B.br_wint[k] = wi;
+                        k++;
+                    }
+                    cnt++;
+                }
+            }
+            // entries to the right may sit before index i (same position twins): scan back over equal positions
+            for (i32 r = i - 1; r >= nb && B.n_pos[r] >= base - 1; r--) {
+                if (!kind_is_entry(B.n_kind[r] & 3)) continue;
+                for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
+                    if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
+                    int len = B.n_pos[r] - B.n_pos[l] - 3;
+                    if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
+                    if (fill) {
+                        Dec w = gap_score(B, c, len, false);
+                        B.br_src[k] = l;
+                        B.br_dst[k] = r;
+                        B.br_w[k] = w;
+                        WInt wi;
+                        if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+                        B.br_wint[k] = wi;
+                        k++;
+                    }
+                    cnt++;
+                }
+            }
+        }
+        if (me - 1 > last) last = me - 1;
+    }
+    if (!fill) B.br_cnt[c] = cnt;
+}
+PB_HDN void st_br_count(const Batch& B, i64 c) {
+    if (c < B.nc) bridges_of(B, (int)c, false);
+}
+PB_HDN void st_br_fill(const Batch& B, i64 c) {
+    if (c < B.nc) bridges_of(B, (int)c, true);
+}
+
+// integer weight of score_gap(len,'same'|'diff') as the solver sees it
+PB_HDN WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok) {
+    *ok = true;
+    if (len <= 300) {
+        i64 k = (i64)c * GAPN + (len + 2);
+        return wint_from_i64(diff ? B.gapi_diff[k] : B.gapi_same[k]);
+    }
+    if (len <= 999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi3);
+    if (len <= 9999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi4);
+    WInt w;
+    *ok = dec_to_wint(gap_score(B, c, len, diff), w);
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 12: exact single-source shortest path source -> target.  One warp per contig: nodes are
+// visited in position order, each visit pushes the node's out-edges (lanes over edges); an
+// improvement through a backward (overlap) edge rewinds the sweep to the improved node, so the
+// result is the Bellman-Ford fixpoint with strict '<' relaxation.
+#ifdef __CUDA_ARCH__
+#define PB_SYNCWARP() __syncwarp()
+#else
+#define PB_SYNCWARP()
+#endif
+
+struct SolveCtx {
+    const Batch* B;
+    int c;
+    u32 ties;
+};
+PB_HD bool relax(const Batch& B, SolveCtx& S, i32 v, const WInt& cand, i32 from) {
+    WInt cur = B.dist[v];
+    if (wint_less(cand, cur)) {
+        B.dist[v] = cand;
+        B.parent[v] = from;
+        B.dirty[v] = 1;
+        return true;
+    }
+    if (!wint_is_inf(cur) && w_cmp(cand, cur) == 0 && B.parent[v] != from) S.ties++;
+    return false;
+}
+
+PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    CStat* cs = B.cs + c;
+    const int L = cs->L;
+    SolveCtx S;
+    S.B = &B;
+    S.c = c;
+    S.ties = 0;
+    bool okw = true;
+    for (i32 i = nb + lane; i < ne; i += NL) {
+        B.dist[i] = wint_inf();
+        B.parent[i] = -1;
+        B.dirty[i] = 0;
+    }
+    WInt tdist = wint_inf();
+    i32 tpar = -1;
+    PB_SYNCWARP();
+    // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
+    for (i32 i = nb + lane; i < ne && B.n_pos[i] <= 2000; i += NL) {
+        if (kind_is_entry(B.n_kind[i] & 3)) {
+            bool o;
+            B.dist[i] = gap_wint(B, c, B.n_pos[i], false, &o);
+            okw = okw && o;
+            B.parent[i] = -2;
+            B.dirty[i] = 1;
+        }
+    }
+    PB_SYNCWARP();
+    const u32 brb = B.br_cnt[c], bre = B.br_cnt[c + 1];
+    i32 i = nb;
+    i64 budget = 64 * (i64)(ne - nb) + 1024;
+    while (i < ne) {
+        // next dirty node at or after i
+#ifdef __CUDA_ARCH__
+        {
+            bool found = false;
+            while (i < ne) {
+                i32 j = i + lane;
+                unsigned m = __ballot_sync(0xFFFFFFFFu, j < ne && B.dirty[j]);
+                if (m) {
+                    i += __ffs(m) - 1;
+                    found = true;
+                    break;
+                }
+                i += 32;
+            }
+            if (!found) break;
+        }
+#else
+        while (i < ne && !B.dirty[i]) i++;
+        if (i >= ne) break;
+#endif
+        if (--budget < 0) {
+            if (lane == 0) PB_ATOMIC_OR(&cs->err, (u32)ERR_INTERNAL);
+            break;
+        }
+        const i32 u = i;
+        const WInt Du = B.dist[u];
+        const int kind = B.n_kind[u] & 3;
+        const int pu = B.n_pos[u];
+        PB_SYNCWARP();
+        if (lane == 0) B.dirty[u] = 0;
+        i32 rewind = 0x7FFFFFFF;
+        if (kind == K_FSTART) {
+            if (lane == 0) {
+                WInt cand = Du;
+                w_add(cand, B.o_wint[B.n_orf[u]]);
+                relax(B, S, B.n_mate[u], cand, u);
+            }
+        } else if (kind == K_RSTOP) {
+            const int farpos = B.n_pos[B.n_mate[u]];
+            for (i32 j = u + 1 + lane; j < ne && B.n_pos[j] <= farpos; j += NL) {
+                if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == u) {
+                    WInt cand = Du;
+                    w_add(cand, B.o_wint[B.n_orf[j]]);
+                    relax(B, S, j, cand, u);
+                }
+            }
+        } else {
+            // gap edges to entries within 500 bp downstream (functions.py:360-438)
+            for (i32 j = u + 1 + lane; j < ne && B.n_pos[j] - pu < 500; j += NL) {
+                const int kj = B.n_kind[j] & 3;
+                const int d = B.n_pos[j] - pu;
+                if (d <= 0 || !kind_is_entry(kj)) continue;
+                bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+                if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
+                bool o;
+                WInt cand = Du;
+                w_add(cand, gap_wint(B, c, d - 3, diff, &o));
+                relax(B, S, j, cand, u);
+            }
+            // overlap edges (backwards)
+            for (u32 k = B.ov_cnt[u] + lane; k < B.ov_cnt[u + 1]; k += NL) {
+                WInt cand = Du;
+                w_add(cand, B.ov_wint[k]);
+                i32 v = B.ov_dst[k];
+                if (relax(B, S, v, cand, u) && v < rewind) rewind = v;
+            }
+            // bridges
+            for (u32 k = brb + lane; k < bre; k += NL) {
+                if (B.br_src[k] != u) continue;
+                WInt cand = Du;
+                w_add(cand, B.br_wint[k]);
+                relax(B, S, B.br_dst[k], cand, u);
+            }
+            // exit -> target within 2000 bp of the right end (functions.py:448-451)
+            if (L - pu <= 2000) {
+                bool o;
+                WInt cand = Du;
+                w_add(cand, gap_wint(B, c, L - pu, false, &o));
+                okw = okw && o;
+                if (wint_less(cand, tdist)) {
+                    tdist = cand;
+                    tpar = u;
+                } else if (!wint_is_inf(tdist) && w_cmp(cand, tdist) == 0 && tpar != u) S.ties++;
+            }
+        }
+#ifdef __CUDA_ARCH__
+        for (int o = 16; o > 0; o >>= 1) {
+            i32 other = __shfl_xor_sync(0xFFFFFFFFu, rewind, o);
+            rewind = other < rewind ? other : rewind;
+        }
+#endif
+        PB_SYNCWARP();
+        i = (rewind < u) ? rewind : u + 1;
+    }
+    if (S.ties) PB_ATOMIC_ADD(&cs->n_ties, S.ties);
+    if (!okw && lane == 0) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+    if (lane == 0) {
+        B.tdist[c] = tdist;
+        B.tparent[c] = tpar;
+    }
+}
+
+// Stage 13: walk the parent pointers back from the target; the ORF edges on the path are the calls
+// (phanotate.py:65-76: source dropped, then consecutive non-overlapping pairs).  item = contig
+PB_HDN void st_backtrack(const Batch& B, i64 c64) {
+    if (c64 >= B.nc) return;
+    const int c = (int)c64;
+    CStat* cs = B.cs + c;
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    i32* out = B.call_tmp + B.corf[c];
+    const i32 cap = B.corf[c + 1] - B.corf[c];
+    i32 n = 0;
+    i32 x = B.tparent[c];
+    if (x < 0) {
+        if (ne > nb) cs->err |= ERR_NOPATH;       // a graph with CDS nodes but no source->target path
+        B.call_cnt[c] = 0;
+        cs->n_calls = 0;
+        return;
+    }
+    while (x >= 0 && n < cap) {
+        i32 e = B.parent[x];                       // entry node of the ORF edge e -> x
+        if (e < 0) {
+            cs->err |= ERR_INTERNAL;
+            break;
+        }
+        i32 orf = ((B.n_kind[x] & 3) == K_RSTART) ? B.n_orf[x] : B.n_orf[e];
+        out[n++] = orf;
+        x = B.parent[e];                           // exit node of the connector into e, or -2 = source
+    }
+    for (i32 a = 0, b = n - 1; a < b; a++, b--) {
+        i32 t = out[a];
+        out[a] = out[b];
+        out[b] = t;
+    }
+    B.call_cnt[c] = (u32)n;
+    cs->n_calls = n;
+}
+// call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them
+PB_HDN void st_gather_calls(const Batch& B, i64 c) {
+    if (c >= B.nc) return;
+    const i32* src = B.call_tmp + B.corf[c];
+    u32 o = B.call_cnt[c], n = B.call_cnt[c + 1] - o;
+    for (u32 k = 0; k < n; k++) {
+        const i32 orf = src[k];
+        B.call_orf[o + k] = orf;
+        CallRec r;
+        const bool rev = B.o_frame[orf] < 0;
+        r.contig = (i32)c;
+        r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
+        r.right = (rev ? B.o_start[orf] : B.o_stop[orf]) + 2;     // right = exit node position + 2
+        r.strand = rev ? -1 : 1;
+        r.weight = B.o_weight[orf];
+        bool ok;
+        r.score = dec_to_double(r.weight, &ok);
+        if (!ok) B.cs[c].err |= ERR_RANGE;
+        B.calls[o + k] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge list of get_graph for the API mirror / --dump (functions.py:307-454): every edge including
+// the implicit gap edges, grouped by the node that emits it.  fill=false counts.  item = node
+PB_HDN void edges_of(const Batch& B, i32 u, bool fill) {
+    const int c = contig_of_node(B, u);
+    const int kind = B.n_kind[u] & 3;
+    const int pu = B.n_pos[u];
+    const int L = B.cs[c].L;
+    const i32 ne = B.cnode[c + 1];
+    u32 cnt = 0;
+    EdgeRec* out = fill ? B.edges + B.ed_cnt[u] : (EdgeRec*)0;
+#define EMIT(S, D, K, W)                 \
+    do {                                 \
+        if (fill) {                      \
+            EdgeRec r;                   \
+            r.contig = c;                \
+            r.src = (S);                 \
+            r.dst = (D);                 \
+            r.kind = (K);                \
+            r.weight = (W);              \
+            out[cnt] = r;                \
+        }                                \
+        cnt++;                           \
+    } while (0)
+    if (kind_is_entry(kind)) {
+        if (pu <= 2000) EMIT(-2, u, EK_SOURCE, gap_score(B, c, pu, false));
+        if (kind == K_FSTART) {
+            EMIT(u, B.n_mate[u], EK_ORF, B.o_weight[B.n_orf[u]]);
+        } else {
+            const int farpos = B.n_pos[B.n_mate[u]];
+            for (i32 j = u + 1; j < ne && B.n_pos[j] <= farpos; j++)
+                if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == u) EMIT(u, j, EK_ORF, B.o_weight[B.n_orf[j]]);
+        }
+    } else {
+        for (i32 j = u + 1; j < ne && B.n_pos[j] - pu < 500; j++) {
+            const int kj = B.n_kind[j] & 3;
+            const int d = B.n_pos[j] - pu;
+            if (d <= 0 || !kind_is_entry(kj)) continue;
+            bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+            if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;
+            EMIT(u, j, EK_GAP, gap_score(B, c, d - 3, diff));
+        }
+        for (u32 k = B.ov_cnt[u]; k < B.ov_cnt[u + 1]; k++) EMIT(u, B.ov_dst[k], EK_OVERLAP, B.ov_w[k]);
+        for (u32 k = B.br_cnt[c]; k < B.br_cnt[c + 1]; k++)
+            if (B.br_src[k] == u) EMIT(u, B.br_dst[k], EK_BRIDGE, B.br_w[k]);
+        if (L - pu <= 2000) EMIT(u, -3, EK_TARGET, gap_score(B, c, L - pu, false));
+    }
+#undef EMIT
+    if (!fill) B.ed_cnt[u] = cnt;
+}
+PB_HDN void st_edge_count(const Batch& B, i64 u) {
+    if (u < B.nn) edges_of(B, (i32)u, false);
+}
+PB_HDN void st_edge_fill(const Batch& B, i64 u) {
+    if (u < B.nn) edges_of(B, (i32)u, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fastpathz-compatible solver for an arbitrary edge list (phanotate.py:56-64): literal Bellman-Ford,
+// edges in the given order, strict '<', passes until nothing changes.  Sequential by definition of
+// its tie-breaking; used only by the API mirror, never on the batch path.
+struct BFArgs {
+    i32 n_nodes, n_edges, source, target;
+    const i32* src;
+    const i32* dst;
+    const WInt* w;
+    WInt* dist;
+    i32* parent;
+    i32* path;      // [n_nodes]
+    i32* path_len;
+};
+PB_HDN void bf_literal(const BFArgs& a) {
+    for (i32 i = 0; i < a.n_nodes; i++) {
+        a.dist[i] = wint_inf();
+        a.parent[i] = -1;
+    }
+    *a.path_len = 0;
+    if (a.source < 0 || a.source >= a.n_nodes || a.target < 0 || a.target >= a.n_nodes) return;
+    w_zero(a.dist[a.source]);
+    for (i32 pass = 0; pass <= a.n_nodes; pass++) {
+        bool changed = false;
+        for (i32 k = 0; k < a.n_edges; k++) {
+            const WInt du = a.dist[a.src[k]];
+            if (wint_is_inf(du)) continue;
+            WInt cand = du;
+            w_add(cand, a.w[k]);
+            if (wint_less(cand, a.dist[a.dst[k]])) {
+                a.dist[a.dst[k]] = cand;
+                a.parent[a.dst[k]] = a.src[k];
+                changed = true;
+            }
+        }
+        if (!changed) break;
+    }
+    if (wint_is_inf(a.dist[a.target])) return;
+    i32 n = 0;
+    for (i32 v = a.target; v != -1 && n < a.n_nodes; v = a.parent[v]) a.path[n++] = v;
+    for (i32 x = 0, y = n - 1; x < y; x++, y--) {
+        i32 t = a.path[x];
+        a.path[x] = a.path[y];
+        a.path[y] = t;
+    }
+    *a.path_len = n;
+}
+
+// pack the ABI views
+struct OrfRec {
+    i32 contig, start, stop, frame, rbs_score, trigger, start_weight, node;
+    Dec pstop, weight;
+};
+struct NodeRec {
+    i32 contig, position, kind, frame, mate, orf, other_end, trigger;
+};
+PB_HDN void pack_orf(const Batch& B, i64 oi, OrfRec* out) {
+    if (oi >= B.no) return;
+    int lo = 0, hi = B.nc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.corf[mid] <= oi) lo = mid;
+        else hi = mid;
+    }
+    OrfRec r;
+    r.contig = lo;
+    r.start = B.o_start[oi];
+    r.stop = B.o_stop[oi];
+    r.frame = B.o_frame[oi];
+    r.rbs_score = B.o_rbs[oi];
+    r.trigger = B.n_trig[B.n_mate[B.o_node[oi]]];
+    r.start_weight = B.o_sw[oi];
+    r.node = B.o_node[oi];
+    r.pstop = B.o_pstop[oi];
+    r.weight = B.o_weight[oi];
+    out[oi] = r;
+}
+PB_HDN void pack_node(const Batch& B, i64 ni, NodeRec* out) {
+    if (ni >= B.nn) return;
+    NodeRec r;
+    r.contig = contig_of_node(B, (i32)ni);
+    r.position = B.n_pos[ni];
+    r.kind = B.n_kind[ni] & 3;
+    r.frame = B.n_kind[ni] >> 2;
+    r.mate = B.n_mate[ni];
+    r.orf = B.n_orf[ni];
+    r.other_end = B.n_oth[ni];
+    r.trigger = (r.kind == K_FSTOP || r.kind == K_RSTOP) ? B.n_trig[ni] : B.n_trig[B.n_mate[ni]];
+    out[ni] = r;
+}

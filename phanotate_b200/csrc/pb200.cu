@@ -1,0 +1,698 @@
+// C-ABI library of the B200-native PHANOTATE hot path (include/phanotate_b200.h).
+//
+// Product build:   nvcc -gencode arch=compute_100a,code=sm_100a  ->  libpb200.so  (needs a GPU)
+// Test-only build: g++ -x c++ -DPB_HOSTSIM  ->  tests/native/pb200_hostsim.so : the same stage
+//                  functions run as host loops so the stage logic can be unit-tested on a box
+//                  without a GPU.  The Python package never loads that build.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/phanotate_b200.h"
+#include "graph.cuh"
+
+static_assert(sizeof(pb200_dec) == sizeof(Dec), "Dec layout");
+static_assert(sizeof(pb200_call) == sizeof(CallRec), "CallRec layout");
+static_assert(sizeof(pb200_edge) == sizeof(EdgeRec), "EdgeRec layout");
+static_assert(sizeof(pb200_orf) == sizeof(OrfRec), "OrfRec layout");
+static_assert(sizeof(pb200_node) == sizeof(NodeRec), "NodeRec layout");
+
+#define NPHASE 8
+
+#ifndef PB_HOSTSIM
+// ================================================================================================
+//                                         CUDA backend
+// ================================================================================================
+#include <cuda_runtime.h>
+#define PB_BLOCK 128
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_);                         \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define PB_KERNEL(stage)                                                                        \
+    __global__ void __launch_bounds__(PB_BLOCK) k_##stage(const Batch B, i64 n) {               \
+        for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) stage(B, i); \
+    }
+PB_KERNEL(st_scan)
+PB_KERNEL(st_mark)
+PB_KERNEL(st_count64)
+PB_KERNEL(st_contig_offsets)
+PB_KERNEL(st_fill)
+PB_KERNEL(st_contig_stats)
+PB_KERNEL(st_gap_lut)
+PB_KERNEL(st_score_orf)
+PB_KERNEL(st_node_attrs)
+PB_KERNEL(st_ov_count)
+PB_KERNEL(st_ov_fill)
+PB_KERNEL(st_br_count)
+PB_KERNEL(st_br_fill)
+PB_KERNEL(st_backtrack)
+PB_KERNEL(st_gather_calls)
+PB_KERNEL(st_edge_count)
+PB_KERNEL(st_edge_fill)
+
+// one warp per contig
+__global__ void __launch_bounds__(PB_BLOCK) k_solve(const Batch B, i32 nc) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 c = warp; c < nc; c += nwarps) solve_contig(B, (int)c, lane, 32);
+}
+__global__ void k_pack_orfs(const Batch B, OrfRec* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.no; i += (i64)gridDim.x * blockDim.x) pack_orf(B, i, out);
+}
+__global__ void k_pack_nodes(const Batch B, NodeRec* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.nn; i += (i64)gridDim.x * blockDim.x) pack_node(B, i, out);
+}
+__global__ void k_bf_literal(const BFArgs a) { bf_literal(a); }
+
+// ---- exclusive prefix sums (three passes; T = u32 or u64 with two packed 32-bit counters)
+#define SCAN_TILE 2048
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const T* in, i64 n, T* sums) {
+    __shared__ T sh[256];
+    i64 base = (i64)blockIdx.x * SCAN_TILE;
+    T s = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
+        i64 i = base + k;
+        if (i < n) s += in[i];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = sh[0];
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_sums(T* sums, i64 nt, T* total) {
+    __shared__ T sh[1024];
+    __shared__ T carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 base = 0; base < nt; base += 1024) {
+        i64 i = base + threadIdx.x;
+        T v = (i < nt) ? sums[i] : (T)0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            T t = ((int)threadIdx.x >= o) ? sh[threadIdx.x - o] : (T)0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        T incl = sh[threadIdx.x];
+        if (i < nt) sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_apply(T* data, i64 n, const T* sums) {
+    __shared__ T sh[256];
+    i64 base = (i64)blockIdx.x * SCAN_TILE;
+    const int per = SCAN_TILE / 256;
+    T loc[SCAN_TILE / 256];
+    T s = 0;
+    i64 i0 = base + (i64)threadIdx.x * per;
+    for (int k = 0; k < per; k++) {
+        i64 i = i0 + k;
+        T v = (i < n) ? data[i] : (T)0;
+        loc[k] = s;
+        s += v;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        T t = ((int)threadIdx.x >= o) ? sh[threadIdx.x - o] : (T)0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    T off = sums[blockIdx.x] + sh[threadIdx.x] - s;
+    for (int k = 0; k < per; k++) {
+        i64 i = i0 + k;
+        if (i < n) data[i] = off + loc[k];
+    }
+}
+
+struct DevBuf {
+    char* p = nullptr;
+    size_t cap = 0, used = 0;
+};
+struct StageTime {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct pb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevBuf ph[NPHASE];
+    DevBuf in_seq, in_off, scratch;
+    Batch B;
+    bool have = false;
+    std::vector<StageTime> times;
+    std::vector<cudaEvent_t> evpool;
+    size_t evused = 0;
+    int launches = 0;
+    int sm_count = 148;
+};
+static int buf_ensure(pb200_ctx* ctx, DevBuf& b, size_t bytes) {
+    b.used = 0;
+    if (bytes <= b.cap) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    CK(cudaMalloc((void**)&b.p, want));
+    b.cap = want;
+    return 0;
+}
+static void* buf_take(DevBuf& b, size_t bytes) {
+    size_t a = (b.used + 255) & ~(size_t)255;
+    if (a + bytes > b.cap) return nullptr;
+    b.used = a + bytes;
+    return b.p + a;
+}
+static cudaEvent_t ev_get(pb200_ctx* ctx) {
+    if (ctx->evused == ctx->evpool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->evpool.push_back(e);
+    }
+    return ctx->evpool[ctx->evused++];
+}
+static int grid_for(pb200_ctx* ctx, i64 n, int block) {
+    i64 g = (n + block - 1) / block;
+    i64 cap = (i64)ctx->sm_count * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+template <typename T>
+static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> data[n]
+    i64 nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nt < 1) nt = 1;
+    if (buf_ensure(ctx, ctx->scratch, (size_t)(nt + 1) * sizeof(T))) return -1;
+    T* sums = (T*)buf_take(ctx->scratch, (size_t)(nt + 1) * sizeof(T));
+    k_scan_tile_sums<T><<<(int)nt, 256, 0, ctx->stream>>>(data, n, sums);
+    k_scan_sums<T><<<1, 1024, 0, ctx->stream>>>(sums, nt, data + n);
+    k_scan_apply<T><<<(int)nt, 256, 0, ctx->stream>>>(data, n, sums);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+#define PB_PHASE(k, bytes)                                             \
+    do {                                                               \
+        if (buf_ensure(ctx, ctx->ph[k], (size_t)(bytes))) return -1;   \
+    } while (0)
+#define PB_ALLOC(k, T, count) ((T*)buf_take(ctx->ph[k], (size_t)(count) * sizeof(T)))
+#define PB_ZERO(ptr, bytes) CK(cudaMemsetAsync((ptr), 0, (bytes), ctx->stream))
+#define PB_FETCH(dst, src, bytes)                                                                \
+    do {                                                                                         \
+        CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream));         \
+        CK(cudaStreamSynchronize(ctx->stream));                                                  \
+    } while (0)
+#define PB_RUN(stage, n)                                                                         \
+    do {                                                                                         \
+        i64 n_ = (i64)(n);                                                                       \
+        if (n_ > 0) {                                                                            \
+            StageTime t_;                                                                        \
+            t_.name = #stage;                                                                    \
+            t_.a = ev_get(ctx);                                                                  \
+            t_.b = ev_get(ctx);                                                                  \
+            cudaEventRecord(t_.a, ctx->stream);                                                  \
+            k_##stage<<<grid_for(ctx, n_, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, n_);         \
+            cudaEventRecord(t_.b, ctx->stream);                                                  \
+            ctx->times.push_back(t_);                                                            \
+            ctx->launches++;                                                                     \
+            CK(cudaGetLastError());                                                              \
+        }                                                                                        \
+    } while (0)
+#define PB_RUN_SOLVE(nc_)                                                                        \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = "solve";                                                                       \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        k_solve<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        cudaEventRecord(t_.b, ctx->stream);                                                      \
+        ctx->times.push_back(t_);                                                                \
+        ctx->launches++;                                                                         \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
+#define PB_SCAN64(ptr, n)                          \
+    do {                                           \
+        if (dev_scan<u64>(ctx, (ptr), (n))) return -1; \
+    } while (0)
+#define PB_SCAN32(ptr, n)                          \
+    do {                                           \
+        if (dev_scan<u32>(ctx, (ptr), (n))) return -1; \
+    } while (0)
+#define PB_TO_HOST(dst, src, bytes)                                                              \
+    do {                                                                                         \
+        CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream));         \
+        CK(cudaStreamSynchronize(ctx->stream));                                                  \
+    } while (0)
+
+#else
+// ================================================================================================
+//                              host-sim backend (unit tests only)
+// ================================================================================================
+#define CK(x) (x)
+struct DevBuf {
+    char* p = nullptr;
+    size_t cap = 0, used = 0;
+};
+struct pb200_ctx {
+    int device = 0;
+    std::string err;
+    DevBuf ph[NPHASE];
+    DevBuf in_seq, in_off, scratch;
+    Batch B;
+    bool have = false;
+    int launches = 0;
+};
+static int buf_ensure(pb200_ctx*, DevBuf& b, size_t bytes) {
+    b.used = 0;
+    if (bytes <= b.cap) return 0;
+    free(b.p);
+    b.cap = bytes + bytes / 8 + 4096;
+    b.p = (char*)malloc(b.cap);
+    return b.p ? 0 : -1;
+}
+static void* buf_take(DevBuf& b, size_t bytes) {
+    size_t a = (b.used + 255) & ~(size_t)255;
+    if (a + bytes > b.cap) return nullptr;
+    b.used = a + bytes;
+    return b.p + a;
+}
+template <typename T>
+static int dev_scan(pb200_ctx*, T* data, i64 n) {
+    T s = 0;
+    for (i64 i = 0; i < n; i++) {
+        T v = data[i];
+        data[i] = s;
+        s += v;
+    }
+    data[n] = s;
+    return 0;
+}
+#define PB_PHASE(k, bytes)                                             \
+    do {                                                               \
+        if (buf_ensure(ctx, ctx->ph[k], (size_t)(bytes))) return -1;   \
+    } while (0)
+#define PB_ALLOC(k, T, count) ((T*)buf_take(ctx->ph[k], (size_t)(count) * sizeof(T)))
+#define PB_ZERO(ptr, bytes) memset((ptr), 0, (bytes))
+#define PB_FETCH(dst, src, bytes) memcpy((dst), (src), (bytes))
+#define PB_TO_HOST(dst, src, bytes) memcpy((dst), (src), (bytes))
+#define PB_RUN(stage, n)                                  \
+    do {                                                  \
+        i64 n_ = (i64)(n);                                \
+        for (i64 i_ = 0; i_ < n_; i_++) stage(B, i_);     \
+        ctx->launches++;                                  \
+    } while (0)
+#define PB_RUN_SOLVE(nc_)                                              \
+    do {                                                               \
+        for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
+        ctx->launches++;                                               \
+    } while (0)
+#define PB_SCAN64(ptr, n) dev_scan<u64>(ctx, (ptr), (n))
+#define PB_SCAN32(ptr, n) dev_scan<u32>(ctx, (ptr), (n))
+#endif
+
+// ================================================================================================
+//                                   backend-independent host code
+// ================================================================================================
+static int codon_code(const char* s) {        // 'acgt' codon -> 0..63, -1 if not plain acgt
+    int v = 0;
+    for (int i = 0; i < 3; i++) {
+        int c;
+        switch (s[i] | 0x20) {
+            case 'a': c = 0; break;
+            case 'c': c = 1; break;
+            case 'g': c = 2; break;
+            case 't': c = 3; break;
+            default: return -1;
+        }
+        v = v * 4 + c;
+    }
+    return s[3] == 0 ? v : -1;
+}
+static int revcomp_code(int v) {
+    int a = v >> 4, b = (v >> 2) & 3, c = v & 3;
+    return (3 - c) * 16 + (3 - b) * 4 + (3 - a);
+}
+// codon classes with the reference's elif priority (functions.py:198-215)
+static int make_params(pb200_ctx* ctx, const pb200_params* in, Params* P) {
+    memset(P, 0, sizeof(*P));
+    if (in->n_start < 1 || in->n_start > 8 || in->n_stop < 0 || in->n_stop > 8) {
+        ctx->err = "between 1 and 8 start codons and at most 8 stop codons are supported";
+        return -2;
+    }
+    if (in->min_orf_len < 9) {
+        ctx->err = "min_orf_len must be >= 9";
+        return -2;
+    }
+    bool is_start[64] = {false}, is_stop[64] = {false};
+    int sw[64];
+    for (int i = 0; i < 64; i++) sw[i] = -1;
+    for (int k = 0; k < in->n_start; k++) {
+        int v = codon_code(in->start_codon[k]);
+        if (v < 0) {
+            ctx->err = "start codons must be three letters of acgt";
+            return -2;
+        }
+        is_start[v] = true;
+        sw[v] = k;                           // a repeated key keeps the last weight, like the dict in file_handling.py:58-60
+        memcpy(&P->startw[k], &in->start_weight[k], sizeof(Dec));
+    }
+    for (int k = 0; k < in->n_stop; k++) {
+        int v = codon_code(in->stop_codon[k]);
+        if (v < 0) {
+            ctx->err = "stop codons must be three letters of acgt";
+            return -2;
+        }
+        is_stop[v] = true;
+    }
+    for (int v = 0; v < 64; v++) {
+        int rc = revcomp_code(v);
+        int cls = CLS_NONE;
+        if (is_start[v]) cls = CLS_S;
+        else if (is_start[rc]) cls = CLS_s;
+        else if (is_stop[v]) cls = CLS_T;
+        else if (is_stop[rc]) cls = CLS_t;
+        P->codon_cls[v] = (u8)cls;
+        P->rev_start[v] = is_start[rc] ? 1 : 0;
+        P->sw_fwd[v] = (signed char)sw[v];
+        P->sw_rev[v] = (signed char)sw[rc];
+    }
+    P->min_orf_len = in->min_orf_len;
+    return 0;
+}
+
+static int run_pipeline(pb200_ctx* ctx) {
+    Batch& B = ctx->B;
+#include "driver.inc"
+    return 0;
+}
+
+extern "C" {
+
+int pb200_create(int device, pb200_ctx** out) {
+    if (!out) return -2;
+    pb200_ctx* ctx = new pb200_ctx();
+    ctx->device = device;
+#ifndef PB_HOSTSIM
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreate(&ctx->stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "phanotate_b200: no usable CUDA device %d: %s\n", device, cudaGetErrorString(e));
+        delete ctx;
+        *out = nullptr;
+        return -1;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+#endif
+    *out = ctx;
+    return 0;
+}
+
+void pb200_destroy(pb200_ctx* ctx) {
+    if (!ctx) return;
+#ifndef PB_HOSTSIM
+    cudaSetDevice(ctx->device);
+    for (int k = 0; k < NPHASE; k++) cudaFree(ctx->ph[k].p);
+    cudaFree(ctx->in_seq.p);
+    cudaFree(ctx->in_off.p);
+    cudaFree(ctx->scratch.p);
+    for (auto e : ctx->evpool) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+#else
+    for (int k = 0; k < NPHASE; k++) free(ctx->ph[k].p);
+    free(ctx->in_seq.p);
+    free(ctx->in_off.p);
+    free(ctx->scratch.p);
+#endif
+    delete ctx;
+}
+
+const char* pb200_last_error(pb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs,
+              const pb200_params* params, uint32_t flags) {
+    if (!ctx || !offsets || !params || n_contigs < 1) {
+        if (ctx) ctx->err = "bad arguments";
+        return -2;
+    }
+    ctx->have = false;
+    Batch& B = ctx->B;
+    memset(&B, 0, sizeof(B));
+    int rc = make_params(ctx, params, &B.P);
+    if (rc) return rc;
+    B.nc = n_contigs;
+#ifndef PB_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    ctx->times.clear();
+    ctx->evused = 0;
+    ctx->launches = 0;
+    if (flags & PB200_INPUT_DEVICE) {
+        i64 last;
+        CK(cudaMemcpyAsync(&last, offsets + n_contigs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        B.nb = last;
+        B.seq = bases;
+        B.coff = offsets;
+    } else {
+        B.nb = offsets[n_contigs];
+        if (B.nb < 1 || !bases) {
+            ctx->err = "empty batch";
+            return -2;
+        }
+        if (buf_ensure(ctx, ctx->in_seq, (size_t)B.nb + 64)) return -1;
+        if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
+        CK(cudaMemcpyAsync(ctx->in_seq.p, bases, (size_t)B.nb, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        B.seq = (const u8*)ctx->in_seq.p;
+        B.coff = (const i64*)ctx->in_off.p;
+    }
+#else
+    (void)flags;
+    ctx->launches = 0;
+    B.nb = offsets[n_contigs];
+    B.seq = bases;
+    B.coff = offsets;
+#endif
+    if (B.nb < 1) {
+        ctx->err = "empty batch";
+        return -2;
+    }
+    if (B.nb >= ((i64)1 << 32)) {
+        ctx->err = "batch larger than 2^32 bases";
+        return -2;
+    }
+    rc = run_pipeline(ctx);
+    if (rc) return rc;
+#ifndef PB_HOSTSIM
+    CK(cudaStreamSynchronize(ctx->stream));
+#endif
+    ctx->have = true;
+    return 0;
+}
+
+int pb200_sizes(pb200_ctx* ctx, int64_t out[8]) {
+    if (!ctx || !ctx->have) return -2;
+    const Batch& B = ctx->B;
+    out[0] = B.nc;
+    out[1] = B.nb;
+    out[2] = B.nn;
+    out[3] = B.no;
+    out[4] = B.nov;
+    out[5] = B.nbr;
+    out[6] = B.ncalls;
+    out[7] = B.nedges;
+    return 0;
+}
+
+int pb200_get_calls(pb200_ctx* ctx, pb200_call* out) {
+    if (!ctx || !ctx->have) return -2;
+    if (ctx->B.ncalls > 0) PB_TO_HOST(out, ctx->B.calls, (size_t)ctx->B.ncalls * sizeof(CallRec));
+    return 0;
+}
+
+int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out) {
+    if (!ctx || !ctx->have) return -2;
+    const Batch& B = ctx->B;
+    std::vector<CStat> cs(B.nc);
+    std::vector<i32> cnode(B.nc + 1), corf(B.nc + 1);
+    std::vector<u32> ccall(B.nc + 1);
+    PB_TO_HOST(cs.data(), B.cs, (size_t)B.nc * sizeof(CStat));
+    PB_TO_HOST(cnode.data(), B.cnode, (size_t)(B.nc + 1) * 4);
+    PB_TO_HOST(corf.data(), B.corf, (size_t)(B.nc + 1) * 4);
+    PB_TO_HOST(ccall.data(), B.call_cnt, (size_t)(B.nc + 1) * 4);
+    for (int c = 0; c < B.nc; c++) {
+        pb200_contig& o = out[c];
+        memset(&o, 0, sizeof(o));
+        o.length = cs[c].L;
+        o.err = cs[c].err;
+        o.node_off = cnode[c];
+        o.n_nodes = cnode[c + 1] - cnode[c];
+        o.orf_off = corf[c];
+        o.n_orfs = corf[c + 1] - corf[c];
+        o.call_off = (i32)ccall[c];
+        o.n_calls = (i32)(ccall[c + 1] - ccall[c]);
+        o.n_ties = (i32)cs[c].n_ties;
+        memcpy(&o.pstop, &cs[c].pstop, sizeof(Dec));
+        memcpy(o.pos_max, cs[c].pos_max, sizeof(Dec) * 4);
+        memcpy(o.pos_min, cs[c].pos_min, sizeof(Dec) * 4);
+        double ybg = 28.0 + 2.0 * (double)cs[c].L, ytr = 28.0 + (double)o.n_orfs;
+        for (int r = 0; r < 28; r++) {
+            o.background_rbs[r] = (1.0 + (double)cs[c].hist_bg[r]) / ybg;
+            o.training_rbs[r] = (1.0 + (double)cs[c].hist_tr[r]) / ytr;
+        }
+    }
+    return 0;
+}
+
+int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out) {
+    if (!ctx || !ctx->have) return -2;
+    Batch& B = ctx->B;
+    if (B.no < 1) return 0;
+    PB_PHASE(6, (size_t)B.no * sizeof(OrfRec) + 1024);
+    OrfRec* tmp = PB_ALLOC(6, OrfRec, B.no);
+#ifndef PB_HOSTSIM
+    k_pack_orfs<<<grid_for(ctx, B.no, 128), 128, 0, ctx->stream>>>(B, tmp);
+    CK(cudaGetLastError());
+#else
+    for (i64 i = 0; i < B.no; i++) pack_orf(B, i, tmp);
+#endif
+    PB_TO_HOST(out, tmp, (size_t)B.no * sizeof(OrfRec));
+    return 0;
+}
+
+int pb200_get_nodes(pb200_ctx* ctx, pb200_node* out) {
+    if (!ctx || !ctx->have) return -2;
+    Batch& B = ctx->B;
+    if (B.nn < 1) return 0;
+    PB_PHASE(6, (size_t)B.nn * sizeof(NodeRec) + 1024);
+    NodeRec* tmp = PB_ALLOC(6, NodeRec, B.nn);
+#ifndef PB_HOSTSIM
+    k_pack_nodes<<<grid_for(ctx, B.nn, 128), 128, 0, ctx->stream>>>(B, tmp);
+    CK(cudaGetLastError());
+#else
+    for (i64 i = 0; i < B.nn; i++) pack_node(B, i, tmp);
+#endif
+    PB_TO_HOST(out, tmp, (size_t)B.nn * sizeof(NodeRec));
+    return 0;
+}
+
+int pb200_build_edges(pb200_ctx* ctx) {
+    if (!ctx || !ctx->have) return -2;
+    Batch& B = ctx->B;
+    B.nedges = 0;
+    if (B.nn < 1) return 0;
+    PB_PHASE(7, ((size_t)B.nn + 2) * 4 + 1024);
+    B.ed_cnt = PB_ALLOC(7, u32, (size_t)B.nn + 1);
+    PB_RUN(st_edge_count, B.nn);
+    PB_SCAN32(B.ed_cnt, B.nn);
+    u32 tot;
+    PB_FETCH(&tot, B.ed_cnt + B.nn, 4);
+    // the counts live in phase 7's buffer; the records go to phase 6 (shared with the pack views)
+    PB_PHASE(6, ((size_t)tot + 1) * sizeof(EdgeRec) + 1024);
+    B.edges = PB_ALLOC(6, EdgeRec, (size_t)tot + 1);
+    PB_RUN(st_edge_fill, B.nn);
+    B.nedges = (i32)tot;
+#ifndef PB_HOSTSIM
+    CK(cudaStreamSynchronize(ctx->stream));
+#endif
+    return 0;
+}
+
+int pb200_get_edges(pb200_ctx* ctx, pb200_edge* out) {
+    if (!ctx || !ctx->have) return -2;
+    if (ctx->B.nedges > 0) PB_TO_HOST(out, ctx->B.edges, (size_t)ctx->B.nedges * sizeof(EdgeRec));
+    return 0;
+}
+
+int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const int32_t* src, const int32_t* dst,
+                       const uint32_t* weight_limbs, int32_t source, int32_t target, int32_t* path_out,
+                       int32_t* path_len) {
+    if (!ctx || n_nodes < 1 || n_edges < 0) return -2;
+    DevBuf& b = ctx->scratch;
+    size_t need = (size_t)n_edges * (8 + sizeof(WInt)) + (size_t)n_nodes * (sizeof(WInt) + 8) + 8192;
+    if (buf_ensure(ctx, b, need)) return -1;
+    BFArgs a;
+    a.n_nodes = n_nodes;
+    a.n_edges = n_edges;
+    a.source = source;
+    a.target = target;
+    i32* dsrc = (i32*)buf_take(b, (size_t)n_edges * 4 + 4);
+    i32* ddst = (i32*)buf_take(b, (size_t)n_edges * 4 + 4);
+    WInt* dw = (WInt*)buf_take(b, (size_t)n_edges * sizeof(WInt) + 32);
+    a.dist = (WInt*)buf_take(b, (size_t)n_nodes * sizeof(WInt));
+    a.parent = (i32*)buf_take(b, (size_t)n_nodes * 4);
+    a.path = (i32*)buf_take(b, (size_t)n_nodes * 4);
+    a.path_len = (i32*)buf_take(b, 8);
+    a.src = dsrc;
+    a.dst = ddst;
+    a.w = dw;
+#ifndef PB_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    if (n_edges > 0) {
+        CK(cudaMemcpyAsync(dsrc, src, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ddst, dst, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dw, weight_limbs, (size_t)n_edges * sizeof(WInt), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_bf_literal<<<1, 1, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+#else
+    if (n_edges > 0) {
+        memcpy(dsrc, src, (size_t)n_edges * 4);
+        memcpy(ddst, dst, (size_t)n_edges * 4);
+        memcpy(dw, weight_limbs, (size_t)n_edges * sizeof(WInt));
+    }
+    bf_literal(a);
+#endif
+    PB_TO_HOST(path_len, a.path_len, 4);
+    if (*path_len > 0) PB_TO_HOST(path_out, a.path, (size_t)(*path_len) * 4);
+    return 0;
+}
+
+int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap) {
+    if (!ctx) return -2;
+#ifndef PB_HOSTSIM
+    int n = 0;
+    for (auto& t : ctx->times) {
+        if (n >= cap) break;
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, t.a, t.b) != cudaSuccess) v = -1.f;
+        names[n] = t.name;
+        ms[n] = v;
+        n++;
+    }
+    return n;
+#else
+    (void)names;
+    (void)ms;
+    (void)cap;
+    return 0;
+#endif
+}
+
+int pb200_launch_count(pb200_ctx* ctx) { return ctx ? ctx->launches : -2; }
+
+}  // extern "C"

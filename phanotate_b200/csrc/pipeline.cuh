@@ -1,0 +1,635 @@
+// The PHANOTATE hot path as data-parallel stages over a batch of contigs.
+//
+// Every stage is a per-item function (item = strip of bases, base position, node, ORF, contig ...)
+// marked __host__ __device__: kernels.cu wraps each in a grid-stride __global__ kernel; the unit
+// tests compile the very same functions for the host (tests/native/hostsim.cpp) so that the stage
+// logic can be checked against the oracle on a CPU-only box.  The product only ever runs the CUDA
+// build.  Coordinates are 1-based inside a contig, as in the reference; file:line citations are
+// into /root/reference.
+//
+// HBM layout (structure of arrays, contigs concatenated):
+//   per base   : seq (input, 1 B), meta (1 B: codon class | GC-frame ordering), nflag (1 B)
+//   per 64 bp  : rank_nodes / rank_orfs (exclusive prefix counts -> node / ORF index of a position)
+//   per node   : position, kind, mate, ORF id, trigger, other_end, pstop index (sorted by contig, position)
+//   per ORF    : start, stop, frame, rbs score, start-codon weight id, pstop, weight (Dec), integer weight
+//   per contig : CStat (counts, histograms, pstop, RBS weights, GC-frame exponents, ln g), gap tables
+#pragma once
+#include "fxpow.cuh"
+#include "frepr.cuh"
+
+// ------------------------------------------------------------------------------------------------
+enum { CLS_NONE = 0, CLS_S = 1, CLS_s = 2, CLS_T = 3, CLS_t = 4 };
+enum { K_FSTART = 0, K_FSTOP = 1, K_RSTOP = 2, K_RSTART = 3 };   // entry: FSTART,RSTOP  exit: FSTOP,RSTART
+enum {
+    ERR_CHAR = 1,        // letter outside the 15 IUPAC codes -> KeyError (functions.py:20-24,169)
+    ERR_RANGE = 2,       // arithmetic outside the supported range
+    ERR_PARALLEL = 4,    // ValueError("parallel edges are forbidden") (graphs.py:73-74)
+    ERR_OVERFLOW = 8,    // integer distance does not fit the wide type
+    ERR_NOPATH = 16,     // target not reachable (behaviour of the absent fastpathz is undefined)
+    ERR_INTERNAL = 32,
+    ERR_LOOKUP = 64      // ValueError from Orfs.get_orf (orfs.py:62-69)
+};
+#define GAPN 303          // gap lengths -2..300 (functions.py:36-46)
+#define WN 8              // limbs of the exact distances (256 bit)
+typedef Wide<WN> WInt;    // two's complement
+
+struct Params {
+    u8 codon_cls[64];     // CLS_* with the reference's elif priority applied (functions.py:198-215)
+    u8 rev_start[64];     // rev_comp(codon) in start_codons
+    signed char sw_fwd[64];   // index into startw for codon / -1
+    signed char sw_rev[64];   // index into startw for rev_comp(codon) / -1
+    Dec startw[8];
+    i32 min_orf_len;
+    i32 pad;
+};
+
+struct CStat {
+    i32 L;
+    u32 err;
+    u32 nAT, nGC;
+    u32 hist_bg[28], hist_tr[28];
+    u32 cmax[4], cmin[4];
+    u32 n_ties, n_relax;
+    Dec pstop, g, g100;
+    SFx ln_g;
+    Dec wrbs[28];
+    Dec pos_max[4], pos_min[4];
+    Fx fmax[4], fmin[4];
+    u8 max_one[4], min_one[4];
+    i32 n_calls;
+    i32 pad;
+    i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
+};
+
+struct CallRec {          // one CDS call (contig, left, right, strand, weight, float score)
+    i32 contig, left, right, strand;
+    Dec weight;
+    double score;
+};
+
+struct EdgeRec {          // = pb200_edge
+    i32 contig, src, dst, kind;
+    Dec weight;
+};
+enum { EK_ORF = 0, EK_GAP = 1, EK_OVERLAP = 2, EK_BRIDGE = 3, EK_SOURCE = 4, EK_TARGET = 5 };
+
+struct Batch {
+    Params P;
+    i32 nc;
+    i32 flags;
+    i64 nb;
+    const u8* seq;
+    const i64* coff;
+    u8* meta;
+    u8* nflag;
+    u64* rank;            // per 64-base block: low 32 = nodes before, high 32 = ORFs before
+    CStat* cs;
+    Dec* gap_same;
+    Dec* gap_diff;
+    i64* gapi_same;
+    i64* gapi_diff;
+    // nodes
+    i32 nn;
+    i32 no;
+    i32* cnode;           // [nc+1]
+    i32* corf;            // [nc+1]
+    i32* n_pos;
+    u8* n_kind;           // K_* | frame<<2
+    i32* n_mate;
+    i32* n_orf;
+    i32* n_trig;
+    i32* n_oth;
+    i32* n_oidx;
+    // ORFs
+    i32* o_start;
+    i32* o_stop;
+    signed char* o_frame;
+    u8* o_rbs;
+    signed char* o_sw;
+    i32* o_node;
+    Dec* o_pstop;
+    Dec* o_weight;
+    WInt* o_wint;
+    // explicit connectors (overlaps) in CSR by source exit node, and bridges by contig
+    u32* ov_cnt;          // [nn+1] counts then exclusive offsets
+    i32 nov;
+    i32 nbr;
+    i32* ov_dst;
+    Dec* ov_w;
+    WInt* ov_wint;
+    u32* br_cnt;          // [nc+1]
+    i32* br_src;
+    i32* br_dst;
+    Dec* br_w;
+    WInt* br_wint;
+    // solve
+    WInt* dist;
+    i32* parent;
+    u8* dirty;
+    WInt* tdist;          // [nc] distance of the target
+    i32* tparent;         // [nc]
+    // calls
+    i32* call_tmp;        // [no] ORF ids on the path, per contig region
+    u32* call_cnt;        // [nc+1]
+    i32* call_orf;        // compacted
+    CallRec* calls;
+    i32 ncalls;
+    i32 nedges;
+    u32* ed_cnt;          // [nn+1] out-degree (all edge kinds) then exclusive offsets
+    EdgeRec* edges;
+};
+
+#ifdef __CUDA_ARCH__
+#define PB_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define PB_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PB_ATOMIC_OR(p, v) (*(p) |= (v))
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// alphabet (functions.py:19-24,159-163)
+PB_HD u8 lower(u8 ch) { return (ch >= 'A' && ch <= 'Z') ? (u8)(ch | 0x20) : ch; }
+// 0..3 = a,c,g,t ; 4 = other IUPAC ; 5 = invalid
+PB_HD int base_code(u8 ch) {
+    switch (ch) {
+        case 'a': return 0;
+        case 'c': return 1;
+        case 'g': return 2;
+        case 't': return 3;
+        case 'n': case 'r': case 'y': case 's': case 'w': case 'k': case 'm': case 'b': case 'v': case 'd': case 'h':
+            return 4;
+        default: return 5;
+    }
+}
+PB_HD int gc_flag(u8 ch) { return (ch == 'g' || ch == 'c' || ch == 's' || ch == 'b' || ch == 'v') ? 1 : 0; }
+
+PB_HD int contig_of(const Batch& B, i64 g) {
+    int lo = 0, hi = B.nc;             // coff[lo] <= g < coff[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.coff[mid] <= g) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RBS motif score of one window, scalar form (functions.py:48-138).  s = contig bases, window =
+// s[i : i+21] clipped at L.  rev: score_rbs(rev_comp(window)).  Handles truncated windows and
+// ambiguity codes (a motif only ever matches plain acgt letters).
+PB_HDN int rbs_score_scalar(const u8* s, int L, int i, bool rev) {
+    if (i < 0 || i >= L) return 0;
+    int W = L - i;
+    if (W > 21) W = 21;
+    u8 code[21];
+    for (int k = 0; k < W; k++) code[k] = (u8)base_code(lower(s[i + k]));
+    int best = 0;
+    for (int m = 0; m < PB_NMOTIF; m++) {
+        int cls = TBL(rbs_motif)[m][0], len = TBL(rbs_motif)[m][1], mc = TBL(rbs_motif)[m][2];
+        for (int a = 3; a <= 15; a++) {
+            if (a + len > W) break;
+            int grp = (a <= 4) ? 1 : (a <= 10) ? 0 : (a <= 12) ? 2 : 3;
+            int sc = TBL(rbs_group_score)[grp][cls];
+            if (sc <= best) continue;
+            bool hit = true;
+            for (int t = 0; t < len && hit; t++) {
+                int want = (mc >> (2 * (len - 1 - t))) & 3;          // motif letter t
+                int have = rev ? code[a + t] : code[W - 1 - a - t];   // s[a+t] of the reversed / complemented window
+                if (have > 3) hit = false;
+                else if (rev) hit = (3 - have) == want;
+                else hit = have == want;
+            }
+            if (hit) best = sc;
+        }
+    }
+    return best;
+}
+PB_HD int rbs_group_max(int g, u32 mask) {
+    int lo, hi;
+    switch (g) {
+        case 0: lo = TBL(rbs_g0_lo)[mask & 31]; hi = TBL(rbs_g0_hi)[mask >> 5]; break;
+        case 1: lo = TBL(rbs_g1_lo)[mask & 31]; hi = TBL(rbs_g1_hi)[mask >> 5]; break;
+        case 2: lo = TBL(rbs_g2_lo)[mask & 31]; hi = TBL(rbs_g2_hi)[mask >> 5]; break;
+        default: lo = TBL(rbs_g3_lo)[mask & 31]; hi = TBL(rbs_g3_hi)[mask >> 5]; break;
+    }
+    return lo > hi ? lo : hi;
+}
+
+// GC-frame ordering code of the triple (a,b,c) = (T(p),T(p+1),T(p+2)): three trits
+PB_HD int gc_trits(int a, int b, int c) {
+    int ab = (a > b) ? 2 : (a == b) ? 1 : 0;
+    int ac = (a > c) ? 2 : (a == c) ? 1 : 0;
+    int bc = (b > c) ? 2 : (b == c) ? 1 : 0;
+    return ab * 9 + ac * 3 + bc;
+}
+// (imax,imin) from the trit code; rev = triple reversed (functions.py:272-278,291-297; gc_frame_plot.py:7-28)
+PB_HD void gc_class(int code, bool rev, int& imax, int& imin) {
+    int ab = code / 9, ac = (code / 3) % 3, bc = code % 3;
+    if (!rev) {
+        bool agb = ab == 2, agc = ac == 2, bgc = bc == 2;
+        imax = agb ? (agc ? 1 : 3) : (bgc ? 2 : 3);
+        imin = agb ? (bgc ? 3 : 2) : (agc ? 3 : 1);
+    } else {   // x=c, y=b, z=a
+        bool xgy = bc == 0, xgz = ac == 0, ygz = ab == 0;   // c>b, c>a, b>a
+        imax = xgy ? (xgz ? 1 : 3) : (ygz ? 2 : 3);
+        imin = xgy ? (ygz ? 3 : 2) : (xgz ? 3 : 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: per-base scan (functions.py:158-171 + codon classes of :196-215 + gc_frame_plot.py)
+// item = strip of SCAN_STRIP consecutive bases of the concatenated batch
+#define SCAN_STRIP 32
+PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1, u8* meta) {
+    CStat* cs = B.cs + c;
+    const int n = i1 - i0;
+    // ---- window sums Tz(j) = sum_{k=-19..20} gc0(j+3k), j = i0 .. i1+1
+    int tz[SCAN_STRIP + 2];
+    for (int r = 0; r < 3; r++) {
+        int j = i0 + r;
+        if (j > i1 + 1) break;
+        int sum = 0;
+        for (int k = -19; k <= 20; k++) {
+            int q = j + 3 * k;
+            if (q >= 0 && q < L) sum += gc_flag(lower(s[q]));
+        }
+        tz[r] = sum;
+        for (int jj = j + 3; jj <= i1 + 1; jj += 3) {
+            int qa = jj + 60, qs = jj - 60;
+            if (qa >= 0 && qa < L) sum += gc_flag(lower(s[qa]));
+            if (qs >= 0 && qs < L) sum -= gc_flag(lower(s[qs]));
+            tz[jj - i0] = sum;
+        }
+    }
+    // ---- base codes of [i0, i1+20]
+    u8 code[SCAN_STRIP + 21];
+    int ncode = n + 20;
+    bool bad = false;
+    for (int k = 0; k < ncode; k++) {
+        int q = i0 + k;
+        int cd = 5;
+        if (q < L) {
+            cd = base_code(lower(s[q]));
+            if (cd == 5 && k < n) bad = true;
+            if (cd == 5) cd = 4;
+        }
+        code[k] = (u8)cd;
+    }
+    if (bad) PB_ATOMIC_OR(&cs->err, (u32)ERR_CHAR);
+    // ---- 6-mer motif masks for 6-mers starting at i0+k (valid only when all six bases are acgt)
+    unsigned short em[SCAN_STRIP + 16], sm[SCAN_STRIP + 16];
+    for (int k = 0; k < n + 15; k++) {
+        int idx = 0, ok = 1;
+        for (int t = 0; t < 6; t++) {
+            int cd = (k + t < ncode) ? code[k + t] : 5;
+            if (cd > 3) ok = 0;
+            idx = (idx << 2) | (cd & 3);
+        }
+        em[k] = ok ? TBL(rbs_end_mask)[idx] : 0;
+        sm[k] = ok ? TBL(rbs_start_mask)[idx] : 0;
+    }
+    u32 nAT = 0, nGC = 0;
+    for (int k = 0; k < n; k++) {
+        int i = i0 + k;
+        u8 ch = lower(s[i]);
+        if (gc_flag(ch)) nGC++;
+        else nAT++;
+        int cls = CLS_NONE;
+        if (i + 2 < L && code[k] < 4 && code[k + 1] < 4 && code[k + 2] < 4)
+            cls = B.P.codon_cls[code[k] * 16 + code[k + 1] * 4 + code[k + 2]];
+        int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
+        meta[i] = (u8)(cls | (tr << 3));
+        // RBS background, both strands
+        int sf, sr;
+        bool clean = (i + 21 <= L);
+        if (clean)
+            for (int t = 0; t < 21; t++)
+                if (code[k + t] > 3) {
+                    clean = false;
+                    break;
+                }
+        if (clean) {
+            u32 gm = em[k + 5] | em[k + 6] | em[k + 7] | em[k + 8] | em[k + 9] | em[k + 10];
+            u32 gl = em[k + 11] | em[k + 12];
+            u32 gh = em[k + 3] | em[k + 4];
+            u32 gf = em[k] | em[k + 1] | em[k + 2];
+            int a = rbs_group_max(0, gm), b = rbs_group_max(1, gl), cc = rbs_group_max(2, gh), d = rbs_group_max(3, gf);
+            sf = a > b ? a : b;
+            if (cc > sf) sf = cc;
+            if (d > sf) sf = d;
+            gm = sm[k + 5] | sm[k + 6] | sm[k + 7] | sm[k + 8] | sm[k + 9] | sm[k + 10];
+            gl = sm[k + 3] | sm[k + 4];
+            gh = sm[k + 11] | sm[k + 12];
+            gf = sm[k + 13] | sm[k + 14] | sm[k + 15];
+            a = rbs_group_max(0, gm), b = rbs_group_max(1, gl), cc = rbs_group_max(2, gh), d = rbs_group_max(3, gf);
+            sr = a > b ? a : b;
+            if (cc > sr) sr = cc;
+            if (d > sr) sr = d;
+        } else {
+            sf = rbs_score_scalar(s, L, i, false);
+            sr = rbs_score_scalar(s, L, i, true);
+        }
+        if (sf) PB_ATOMIC_ADD(&cs->hist_bg[sf], 1u);
+        if (sr) PB_ATOMIC_ADD(&cs->hist_bg[sr], 1u);
+    }
+    PB_ATOMIC_ADD(&cs->nAT, nAT);
+    PB_ATOMIC_ADD(&cs->nGC, nGC);
+}
+PB_HDN void st_scan(const Batch& B, i64 strip) {
+    i64 g = strip * SCAN_STRIP;
+    if (g >= B.nb) return;
+    i64 gend = g + SCAN_STRIP;
+    if (gend > B.nb) gend = B.nb;
+    int c = contig_of(B, g);
+    while (g < gend) {
+        while (B.coff[c + 1] <= g) c++;
+        i64 cb = B.coff[c];
+        int L = (int)(B.coff[c + 1] - cb);
+        int i0 = (int)(g - cb);
+        i64 e = gend - cb;
+        int i1 = (e < L) ? (int)e : L;
+        scan_range(B, c, B.seq + cb, L, i0, i1, B.meta + cb);
+        g = cb + i1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Six-frame scan as independent walks (functions.py:184-251).  p is 1-based.
+struct CView {
+    const u8* s;
+    const u8* meta;
+    int L;
+};
+PB_HD int cls_at(const CView& v, int p) { return (p >= 1 && p <= v.L - 2) ? (v.meta[p - 1] & 7) : CLS_NONE; }
+PB_HD int frame_end(int L, int f) { return L - ((L - (f - 1)) % 3); }   // functions.py:231
+PB_HD int codon_index(const CView& v, int p) {                           // -1 if any letter is not acgt
+    if (p < 1 || p > v.L - 2) return -1;
+    int a = base_code(lower(v.s[p - 1])), b = base_code(lower(v.s[p])), c = base_code(lower(v.s[p + 1]));
+    if (a > 3 || b > 3 || c > 3) return -1;
+    return a * 16 + b * 4 + c;
+}
+PB_HD bool is_fwd_start(const CView& v, int p) { return cls_at(v, p) == CLS_S || p <= 3; }
+PB_HD bool is_rev_start(const Batch& B, const CView& v, int p, int f) {
+    if (cls_at(v, p) == CLS_s) return true;
+    if (p == frame_end(v.L, f) - 2) {
+        int ci = codon_index(v, p);
+        return ci < 0 || !B.P.rev_start[ci];
+    }
+    return false;
+}
+// forward ORF starting at p: stop key and length.  limit>0 bounds the walk (validity only).
+PB_HD void fwd_orf_of_start(const CView& v, int p, int f, int& key, int& length, int& trig) {
+    int endf = frame_end(v.L, f);
+    for (int q = p; q <= v.L - 2; q += 3) {
+        if (cls_at(v, q) == CLS_T) {
+            key = q;
+            length = q + 2 - p + 1;
+            trig = q;
+            return;
+        }
+    }
+    key = endf - 2;
+    length = endf - p + 1;
+    trig = v.L + 2 * f;
+}
+// reverse ORF whose start codon begins at p (pushed value p+2): stop key (previous rev stop or f)
+PB_HD void rev_orf_of_start(const CView& v, int p, int f, int& key, int& length) {
+    key = f;
+    for (int q = p; q >= f; q -= 3) {
+        if (cls_at(v, q) == CLS_t) {
+            key = q;
+            break;
+        }
+    }
+    length = p + 2 - key + 1;
+}
+// forward family keyed at p (a T codon, or the frame's last codon): farthest pending start
+PB_HD int fwd_family_farthest(const CView& v, int p, int f) {
+    int far = -1;
+    for (int q = p - 3; q >= f; q -= 3) {
+        int c = cls_at(v, q);
+        if (c == CLS_T) break;
+        if (c == CLS_S || q <= 3) far = q;
+    }
+    return far;
+}
+// reverse family keyed at p (a t codon or the frame's first codon): farthest member and trigger
+PB_HD int rev_family_farthest(const Batch& B, const CView& v, int p, int f, int& trig) {
+    int far = -1;
+    trig = v.L + 2 * f + 1;
+    for (int q = p + 3; q <= v.L - 2; q += 3) {
+        if (cls_at(v, q) == CLS_t) {
+            trig = q;
+            return far;
+        }
+        if (is_rev_start(B, v, q, f)) far = q;
+    }
+    return far;
+}
+
+// Stage 2: mark which positions carry a start node (bit0; bit2 = reverse strand) and / or a
+// stop-key node (bit1; bit3 = reverse strand).  item = base position of the batch.
+PB_HDN void st_mark(const Batch& B, i64 g) {
+    if (g >= B.nb) return;
+    int c = contig_of(B, g);
+    i64 cb = B.coff[c];
+    CView v;
+    v.s = B.seq + cb;
+    v.meta = B.meta + cb;
+    v.L = (int)(B.coff[c + 1] - cb);
+    int p = (int)(g - cb) + 1;
+    u8 flag = 0;
+    if (v.L >= 9 && p <= v.L - 2) {
+        int f = (p - 1) % 3 + 1;
+        int cls = cls_at(v, p);
+        const int minlen = B.P.min_orf_len;
+        int endf = frame_end(v.L, f);
+        int nstart = 0;
+        if (cls == CLS_S || p <= 3) {
+            int key, len, trig;
+            fwd_orf_of_start(v, p, f, key, len, trig);
+            if (len >= minlen) {
+                flag |= 1;
+                nstart++;
+            }
+        }
+        if (is_rev_start(B, v, p, f)) {
+            int key, len;
+            rev_orf_of_start(v, p, f, key, len);
+            if (len >= minlen) {
+                flag |= 1 | 4;
+                nstart++;
+            }
+        }
+        int nstop = 0;
+        if (cls == CLS_T || p == endf - 2) {
+            int far = fwd_family_farthest(v, p, f);
+            if (far > 0 && p + 2 - far + 1 >= minlen) {
+                flag |= 2;
+                nstop++;
+            }
+        }
+        if (cls == CLS_t || p <= 3) {
+            int trig;
+            int far = rev_family_farthest(B, v, p, f, trig);
+            if (far > 0 && far + 2 - p + 1 >= minlen) {
+                flag |= 2 | 8;
+                nstop++;
+            }
+        }
+        if (nstart > 1 || nstop > 1) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_INTERNAL);
+    }
+    B.nflag[g] = flag;
+}
+
+// Stage 3: per 64-base block counts (nodes in the low word, ORFs = start nodes in the high word)
+PB_HDN void st_count64(const Batch& B, i64 blk) {
+    i64 g0 = blk * 64, g1 = g0 + 64;
+    if (g1 > B.nb) g1 = B.nb;
+    u32 nn = 0, no = 0;
+    for (i64 g = g0; g < g1; g++) {
+        u8 f = B.nflag[g];
+        nn += (f & 1) + ((f >> 1) & 1);
+        no += (f & 1);
+    }
+    B.rank[blk] = (u64)nn | ((u64)no << 32);
+}
+// node index of (global position g, bit) after the exclusive scan of rank[]; start node sorts first
+PB_HD i32 node_index(const Batch& B, i64 g, int bit) {
+    i64 blk = g >> 6;
+    u32 n = (u32)B.rank[blk];
+    for (i64 q = blk << 6; q < g; q++) {
+        u8 f = B.nflag[q];
+        n += (f & 1) + ((f >> 1) & 1);
+    }
+    if (bit == 1) n += (B.nflag[g] & 1);
+    return (i32)n;
+}
+PB_HD i32 orf_index(const Batch& B, i64 g) {
+    i64 blk = g >> 6;
+    u32 n = (u32)(B.rank[blk] >> 32);
+    for (i64 q = blk << 6; q < g; q++) n += (B.nflag[q] & 1);
+    return (i32)n;
+}
+PB_HDN void st_contig_offsets(const Batch& B, i64 c) {
+    if (c > B.nc) return;
+    i64 g = B.coff[c];
+    if (g >= B.nb) {
+        B.cnode[c] = B.nn;
+        B.corf[c] = B.no;
+    } else {
+        B.cnode[c] = node_index(B, g, 0);
+        B.corf[c] = orf_index(B, g);
+    }
+}
+
+// Stage 4: fill node and ORF records; RBS training histogram; GC-frame training counts.
+// item = base position of the batch
+PB_HDN void st_fill(const Batch& B, i64 g) {
+    if (g >= B.nb) return;
+    u8 flag = B.nflag[g];
+    if (!flag) return;
+    int c = contig_of(B, g);
+    i64 cb = B.coff[c];
+    CView v;
+    v.s = B.seq + cb;
+    v.meta = B.meta + cb;
+    v.L = (int)(B.coff[c + 1] - cb);
+    CStat* cs = B.cs + c;
+    int p = (int)(g - cb) + 1;
+    int f = (p - 1) % 3 + 1;
+    if (flag & 1) {
+        i32 ni = node_index(B, g, 0);
+        i32 oi = orf_index(B, g);
+        bool rev = (flag & 4) != 0;
+        int key, len, trig = 0, rbs, sw;
+        if (!rev) {
+            fwd_orf_of_start(v, p, f, key, len, trig);
+            rbs = (p >= 21) ? rbs_score_scalar(v.s, v.L, p - 21, false) : 0;      // dna[start-21:start], functions.py:208-209
+            int ci = codon_index(v, p);
+            sw = (ci >= 0) ? B.P.sw_fwd[ci] : -1;
+        } else {
+            rev_orf_of_start(v, p, f, key, len);
+            int P2 = p + 2;                                                       // dna[start:start+21], functions.py:221-222
+            rbs = (P2 < v.L) ? rbs_score_scalar(v.s, v.L, P2, true) : 0;
+            int ci = codon_index(v, p);
+            sw = (ci >= 0) ? B.P.sw_rev[ci] : -1;
+        }
+        PB_ATOMIC_ADD(&cs->hist_tr[rbs], 1u);
+        B.n_pos[ni] = p;
+        B.n_kind[ni] = (u8)((rev ? K_RSTART : K_FSTART) | (f << 2));
+        B.n_orf[ni] = oi;
+        B.n_mate[ni] = node_index(B, cb + key - 1, 1);
+        B.n_trig[ni] = 0;
+        B.o_start[oi] = p;
+        B.o_stop[oi] = key;
+        B.o_frame[oi] = (signed char)(rev ? -f : f);
+        B.o_rbs[oi] = (u8)rbs;
+        B.o_sw[oi] = (signed char)sw;
+        B.o_node[oi] = ni;
+    }
+    if (flag & 2) {
+        i32 ni = node_index(B, g, 1);
+        bool rev = (flag & 8) != 0;
+        const int minlen = B.P.min_orf_len;
+        int far, trig;
+        int atg = -1;                    // farthest valid member whose start codon is literally 'atg' (functions.py:266)
+        if (!rev) {
+            far = -1;
+            trig = (cls_at(v, p) == CLS_T) ? p : v.L + 2 * f;
+            for (int q = p - 3; q >= f; q -= 3) {
+                int cq = cls_at(v, q);
+                if (cq == CLS_T) break;
+                if (cq == CLS_S || q <= 3) {
+                    far = q;
+                    if (p + 2 - q + 1 >= minlen && codon_index(v, q) == 14) atg = q;   // a,t,g = 0*16+3*4+2
+                }
+            }
+        } else {
+            far = -1;
+            trig = v.L + 2 * f + 1;
+            for (int q = p + 3; q <= v.L - 2; q += 3) {
+                if (cls_at(v, q) == CLS_t) {
+                    trig = q;
+                    break;
+                }
+                if (is_rev_start(B, v, q, f)) {
+                    far = q;
+                    if (q + 2 - p + 1 >= minlen && codon_index(v, q) == 19) atg = q;   // 'cat' = 1*16+0*4+3
+                }
+            }
+        }
+        B.n_pos[ni] = p;
+        B.n_kind[ni] = (u8)((rev ? K_RSTOP : K_FSTOP) | (f << 2));
+        B.n_mate[ni] = node_index(B, cb + far - 1, 0);
+        B.n_orf[ni] = orf_index(B, cb + far - 1);
+        B.n_trig[ni] = trig;
+        if (atg > 0) {                   // functions.py:267-279
+            u32 cM[4] = {0, 0, 0, 0}, cm[4] = {0, 0, 0, 0};
+            if (!rev) {
+                int start = atg, stop = p;
+                int n = ((stop - start) / 8) * 3;
+                for (int b = start + n; b < stop - 36; b += 3) {
+                    int im, il;
+                    gc_class(v.meta[b - 1] >> 3, false, im, il);
+                    cM[im]++;
+                    cm[il]++;
+                }
+            } else {
+                int start = atg, stop = p;
+                int n = ((start - stop) / 8) * 3;
+                for (int b = start - n; b > stop + 36; b -= 3) {
+                    int im, il;
+                    gc_class(v.meta[b - 1] >> 3, true, im, il);
+                    cM[im]++;
+                    cm[il]++;
+                }
+            }
+            for (int k = 1; k < 4; k++) {
+                if (cM[k]) PB_ATOMIC_ADD(&cs->cmax[k], cM[k]);
+                if (cm[k]) PB_ATOMIC_ADD(&cs->cmin[k], cm[k]);
+            }
+        }
+    }
+}

@@ -1,0 +1,298 @@
+// Scoring stages: contig statistics, gap-score tables, per-ORF pstop / GC-frame product / weight.
+// (functions.py:153-181, 253-301; orfs.py:122-127,162-173; functions.py:26-46)
+#pragma once
+#include "pipeline.cuh"
+
+PB_HD Dec dec_one() { return dec_from_u64(1); }
+
+// Pt*Pa*Pa + Pt*Pg*Pa + Pt*Pa*Pg, left to right, every operation rounded (functions.py:178, orfs.py:173)
+PB_HDN Dec pstop_formula(const Dec& Pa, const Dec& Pt, const Dec& Pg) {
+    Dec t1 = dec_mul(dec_mul(Pt, Pa), Pa);
+    Dec t2 = dec_mul(dec_mul(Pt, Pg), Pa);
+    Dec t3 = dec_mul(dec_mul(Pt, Pa), Pg);
+    return dec_add(dec_add(t1, t2), t3);
+}
+
+// Stage 5: per-contig statistics.  item = contig
+PB_HDN void st_contig_stats(const Batch& B, i64 c) {
+    if (c >= B.nc) return;
+    CStat* cs = B.cs + c;
+    const int L = (int)(B.coff[c + 1] - B.coff[c]);
+    cs->L = L;
+    if (L < 1) {
+        cs->err |= ERR_RANGE;
+        return;
+    }
+    // base frequencies over both strands: fa = ft = #a+#t, fg = fc = #g+#c (functions.py:159-166,174-178)
+    Dec twoL = dec_from_u64(2ull * (u64)L);
+    Dec Pa = dec_div(dec_from_u64(cs->nAT), twoL);
+    Dec Pg = dec_div(dec_from_u64(cs->nGC), twoL);
+    cs->pstop = pstop_formula(Pa, Pa, Pg);
+    cs->g = dec_sub(dec_one(), cs->pstop);
+    cs->g100 = dec_powi(cs->g, 100);
+    {   // score_gap(len > 300) = g**100 + len: the rounding position only depends on the digit count of len
+        Wide<2> m;
+        bool o3 = dec_to_milli_int<2>(dec_add(cs->g100, dec_from_u64(301)), m);
+        cs->gap_hi3 = (i64)(((u64)m.w[1] << 32) | m.w[0]) - 301000;
+        bool o4 = dec_to_milli_int<2>(dec_add(cs->g100, dec_from_u64(1000)), m);
+        cs->gap_hi4 = (i64)(((u64)m.w[1] << 32) | m.w[0]) - 1000000;
+        if (!o3 || !o4) cs->err |= ERR_OVERFLOW;
+    }
+    bool ok = true, ok2 = true;
+    if (dec_is_one_abs(cs->g)) {
+        w_zero(cs->ln_g.m);
+        cs->ln_g.neg = 0;
+    } else {
+        Fx X = fx_from_dec(cs->g, &ok);
+        cs->ln_g = fx_ln(X, &ok2);
+    }
+    if (!ok || !ok2) cs->err |= ERR_RANGE;
+    // RBS likelihood ratio per score bin, IEEE doubles (functions.py:155-156,180-181,254-257)
+    u32 nz = 0;
+    for (int r = 1; r < 28; r++) nz += cs->hist_bg[r];
+    cs->hist_bg[0] = 2u * (u32)L - nz;
+    double ybg = 28.0 + 2.0 * (double)L;
+    u32 norf = (u32)(B.corf[c + 1] - B.corf[c]);
+    double ytr = 28.0 + (double)norf;
+    for (int r = 0; r < 28; r++) {
+        double bg = (1.0 + (double)cs->hist_bg[r]) / ybg;
+        double tr = (1.0 + (double)cs->hist_tr[r]) / ytr;
+        double wr = tr / bg;
+        bool okr;
+        cs->wrbs[r] = dec_from_double_repr(wr, &okr);
+        if (!okr) cs->err |= ERR_RANGE;
+    }
+    // GC-frame exponents (functions.py:262-263,281-284): counts start at 1, divided by their max
+    u32 mx = 1, mn = 1;
+    for (int k = 1; k < 4; k++) {
+        if (cs->cmax[k] + 1 > mx) mx = cs->cmax[k] + 1;
+        if (cs->cmin[k] + 1 > mn) mn = cs->cmin[k] + 1;
+    }
+    for (int k = 0; k < 4; k++) {
+        u32 a = (k ? cs->cmax[k] : 0) + 1, b = (k ? cs->cmin[k] : 0) + 1;
+        cs->pos_max[k] = dec_div(dec_from_u64(a), dec_from_u64(mx));
+        cs->pos_min[k] = dec_div(dec_from_u64(b), dec_from_u64(mn));
+        cs->max_one[k] = (a == mx);
+        cs->min_one[k] = (b == mn);
+        bool o1, o2;
+        cs->fmax[k] = fx_from_dec(cs->pos_max[k], &o1);
+        cs->fmin[k] = fx_from_dec(cs->pos_min[k], &o2);
+        if (!o1 || !o2) cs->err |= ERR_RANGE;
+    }
+}
+
+// score_gap for length <= 300 (functions.py:36-46): 1/g**Decimal(length/3) (+ 1/0.05 if 'diff')
+PB_HDN Dec gap_score_small(const CStat* cs, int len, bool* ok) {
+    Dec pw;
+    *ok = true;
+    if (len % 3 == 0) {
+        pw = dec_powi(cs->g, (u32)(len / 3));            // len >= 0 here
+    } else {
+        double y = (double)len / 3.0;                     // Python float, then Decimal(float) is exact
+        Fx Y = fx_from_double(fabs(y));
+        if (dec_is_one_abs(cs->g)) {
+            bool o;
+            pw = dec_pow_fx(cs->g, Y, y < 0, PB_PREC, &o);
+        } else {
+            SFx T;
+            T.m = fx_mul(cs->ln_g.m, Y);
+            T.neg = cs->ln_g.neg ^ (y < 0 ? 1 : 0);
+            bool o3, o4;
+            Fx V = fx_exp(T, &o3);
+            pw = fx_to_dec(V, PB_PREC, &o4);
+            *ok = o3 && o4;
+        }
+    }
+    return dec_div(dec_one(), pw);
+}
+PB_HD Dec dec_twenty() {   // 1/Decimal('0.05') == Decimal('2E+1')
+    Dec d = dec_from_u64(2);
+    d.e = 1;
+    return d;
+}
+// Stage 6: gap tables.  item = contig*GAPN + (len+2)
+PB_HDN void st_gap_lut(const Batch& B, i64 item) {
+    i64 c = item / GAPN;
+    if (c >= B.nc) return;
+    int len = (int)(item % GAPN) - 2;
+    CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    bool ok;
+    Dec same = gap_score_small(cs, len, &ok);
+    Dec diff = dec_add(same, dec_twenty());
+    if (!ok) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+    B.gap_same[item] = same;
+    B.gap_diff[item] = diff;
+    Wide<2> m;
+    bool f1 = dec_to_milli_int<2>(same, m);
+    B.gapi_same[item] = (i64)(((u64)m.w[1] << 32) | m.w[0]);
+    bool f2 = dec_to_milli_int<2>(diff, m);
+    B.gapi_diff[item] = (i64)(((u64)m.w[1] << 32) | m.w[0]);
+    if (!f1 || !f2) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+}
+// score_gap for any length as a Dec (used for terminals, bridges and the edge dump)
+PB_HDN Dec gap_score(const Batch& B, int c, int len, bool diff) {
+    if (len > 300) return dec_add(B.cs[c].g100, dec_from_u64((u64)len));   // functions.py:40-41 (no inversion, no +20)
+    i64 k = (i64)c * GAPN + (len + 2);
+    return diff ? B.gap_diff[k] : B.gap_same[k];
+}
+
+PB_HD WInt wint_from_mag(const Wide<WN>& mag, bool neg) {
+    if (!neg) return mag;
+    WInt r;
+    u64 carry = 1;
+#pragma unroll
+    for (int i = 0; i < WN; i++) {
+        carry += (u64)(~mag.w[i]);
+        r.w[i] = (u32)carry;
+        carry >>= 32;
+    }
+    return r;
+}
+PB_HD WInt wint_from_i64(i64 v) {
+    WInt r;
+    u32 ext = v < 0 ? 0xFFFFFFFFu : 0u;
+    r.w[0] = (u32)(u64)v;
+    r.w[1] = (u32)((u64)v >> 32);
+#pragma unroll
+    for (int i = 2; i < WN; i++) r.w[i] = ext;
+    return r;
+}
+PB_HD bool wint_less(const WInt& a, const WInt& b) {   // signed compare
+    u32 sa = a.w[WN - 1] >> 31, sb = b.w[WN - 1] >> 31;
+    if (sa != sb) return sa > sb;
+    return w_cmp(a, b) < 0;
+}
+PB_HD bool wint_is_inf(const WInt& a) { return a.w[WN - 1] == 0x7FFFFFFFu; }
+PB_HD WInt wint_inf() {
+    WInt r;
+#pragma unroll
+    for (int i = 0; i < WN; i++) r.w[i] = 0xFFFFFFFFu;
+    r.w[WN - 1] = 0x7FFFFFFFu;
+    return r;
+}
+PB_HDN bool dec_to_wint(const Dec& d, WInt& out) {
+    Wide<WN> mag;
+    bool ok = dec_to_milli_int<WN>(d, mag);
+    if (ok && (mag.w[WN - 1] >> 16)) ok = false;      // |w| < 2^240: sums of 2^14 weights stay below the INF marker
+    out = wint_from_mag(mag, d.neg && !w_is_zero(mag));
+    return ok;
+}
+
+// Stage 7: score one ORF.  item = ORF id
+PB_HDN void st_score_orf(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    const i32 ni = B.o_node[oi];
+    // contig of this ORF: binary search on corf
+    int lo = 0, hi = B.nc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.corf[mid] <= oi) lo = mid;
+        else hi = mid;
+    }
+    const int c = lo;
+    (void)ni;
+    CStat* cs = B.cs + c;
+    const i64 cb = B.coff[c];
+    const u8* s = B.seq + cb;
+    const u8* meta = B.meta + cb;
+    const int L = cs->L;
+    const int start = B.o_start[oi], stop = B.o_stop[oi];
+    const bool rev = B.o_frame[oi] < 0;
+    // extent of orf.seq in the forward text, 0-based half open (functions.py:206,219,234,246)
+    int x0, x1;
+    if (!rev) {
+        x0 = start - 1;
+        x1 = stop + 2;
+    } else {
+        x0 = stop - 1;
+        x1 = start + 2;
+    }
+    if (x0 < 0) x0 = 0;
+    if (x1 > L) x1 = L;
+    u32 cnt[4] = {0, 0, 0, 0};
+    for (int q = x0; q < x1; q++) {
+        int cd = base_code(lower(s[q]));
+        if (cd < 4) cnt[cd]++;
+    }
+    u32 na = cnt[0], nt = cnt[3], ng = cnt[2];
+    if (rev) {
+        na = cnt[3];
+        nt = cnt[0];
+        ng = cnt[1];
+    }
+    Dec len = dec_from_u64((u64)(x1 - x0));
+    Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);
+    Dec pstop = pstop_formula(Pa, Pt, Pg);
+    B.o_pstop[oi] = pstop;
+    // factors ((1-pstop)**pos_max[i])**pos_min[j] for the six (i,j) classes, computed on first use
+    Dec x = dec_sub(dec_one(), pstop);
+    bool okall = true;
+    const bool xone = dec_is_one_abs(x);
+    SFx lnx;
+    w_zero(lnx.m);
+    lnx.neg = 0;
+    if (!xone) {
+        bool o1, o2;
+        Fx X = fx_from_dec(x, &o1);
+        lnx = fx_ln(X, &o2);
+        okall = okall && o1 && o2;
+    }
+    Dec A[4];
+    SFx lnA[4];
+    u8 haveA = 0, haveL = 0;
+    Dec F[16];
+    u32 haveF = 0;
+    Dec hold = dec_one();
+    const int step = rev ? -3 : 3;
+    for (int b = start; rev ? (b > stop) : (b < stop); b += step) {
+        int im, il;
+        gc_class(meta[b - 1] >> 3, rev, im, il);
+        int key = im * 4 + il;
+        if (!((haveF >> key) & 1u)) {
+            if (!((haveA >> im) & 1)) {
+                if (cs->max_one[im]) A[im] = x;                       // x ** Decimal(1) == x
+                else if (xone) {
+                    bool o;
+                    A[im] = dec_pow_fx(x, cs->fmax[im], 0, PB_PREC, &o);
+                } else {
+                    bool o;
+                    A[im] = dec_pow_ln(lnx, cs->fmax[im], PB_PREC, &o);
+                    okall = okall && o;
+                }
+                haveA |= (u8)(1 << im);
+            }
+            Dec f;
+            if (cs->min_one[il]) f = A[im];
+            else if (dec_is_one_abs(A[im])) {
+                bool o;
+                f = dec_pow_fx(A[im], cs->fmin[il], 0, PB_PREC, &o);
+            } else {
+                if (!((haveL >> im) & 1)) {
+                    bool o1, o2;
+                    Fx XA = fx_from_dec(A[im], &o1);
+                    lnA[im] = fx_ln(XA, &o2);
+                    okall = okall && o1 && o2;
+                    haveL |= (u8)(1 << im);
+                }
+                bool o;
+                f = dec_pow_ln(lnA[im], cs->fmin[il], PB_PREC, &o);
+                okall = okall && o;
+            }
+            F[key] = f;
+            haveF |= 1u << key;
+        }
+        hold = dec_mul(hold, F[key]);                                  // functions.py:293,298
+    }
+    // Orf.score (orfs.py:122-127)
+    Dec sc = dec_div(dec_one(), hold);
+    int sw = B.o_sw[oi];
+    if (sw >= 0) sc = dec_mul(sc, B.P.startw[sw]);
+    sc = dec_mul(sc, cs->wrbs[B.o_rbs[oi]]);
+    sc.neg ^= 1;
+    B.o_weight[oi] = sc;
+    WInt wi;
+    if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+    B.o_wint[oi] = wi;
+    if (!okall) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+}

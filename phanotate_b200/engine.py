@@ -1,0 +1,193 @@
+"""Batch engine: one call = the whole hot path for a batch of contigs on one B200.
+
+    eng = Engine()                       # opens cuda:0 through the C ABI; raises without a GPU
+    res = eng.run([b"acgt...", ...])     # or eng.run_packed(bases_u8, offsets_i64)
+    res.calls                            # numpy structured array, one row per CDS
+    res.call_rows(0)                     # [(left, right, '+', '-4.827981E+02'), ...] like Locus.tabular
+
+Everything numeric happens in the CUDA library; this module only packs inputs, unpacks the
+result tables and formats text.
+"""
+from __future__ import annotations
+
+import ctypes
+from decimal import Decimal
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+DEFAULT_START_CODONS = "atg:0.85,gtg:0.10,ttg:0.05"     # file_handling.py:50
+DEFAULT_STOP_CODONS = "tag,tga,taa"                      # file_handling.py:51
+DEFAULT_MIN_ORF_LEN = 90                                 # file_handling.py:52
+
+
+def parse_start_codons(text: str) -> dict:
+    """file_handling.py:57-62: 'atg:0.85,...' -> {codon: Decimal weight / max weight}."""
+    w = {}
+    for item in text.split(","):
+        codon, weight = item.split(":")
+        w[codon.lower()] = Decimal(weight)
+    m = max(w.values())
+    return {k: v / m for k, v in w.items()}
+
+
+def parse_stop_codons(text: str) -> list:
+    """file_handling.py:63-66"""
+    return [c.lower() for c in text.split(",")]
+
+
+class PhanotateError(RuntimeError):
+    pass
+
+
+def make_params(start_codons=None, stop_codons=None, min_orf_len=DEFAULT_MIN_ORF_LEN) -> np.ndarray:
+    if start_codons is None:
+        start_codons = parse_start_codons(DEFAULT_START_CODONS)
+    if stop_codons is None:
+        stop_codons = parse_stop_codons(DEFAULT_STOP_CODONS)
+    if len(start_codons) > 8 or len(stop_codons) > 8:
+        raise ValueError("at most 8 start and 8 stop codons are supported")
+    p = np.zeros(1, dtype=N.PARAMS)
+    p["n_start"] = len(start_codons)
+    for k, (codon, w) in enumerate(start_codons.items()):
+        p["start_codon"][0][k] = codon.encode()
+        c, e, s = N.decimal_to_dec(Decimal(w))
+        p["start_weight"][0][k]["c"] = c
+        p["start_weight"][0][k]["e"] = e
+        p["start_weight"][0][k]["neg"] = s
+    p["n_stop"] = len(stop_codons)
+    for k, codon in enumerate(stop_codons):
+        p["stop_codon"][0][k] = codon.encode()
+    p["min_orf_len"] = int(min_orf_len)
+    return p
+
+
+class Result:
+    """Tables of one batch (copied out of the context, so they outlive the next run)."""
+
+    def __init__(self, engine, names=None):
+        self._e = engine
+        self.names = names
+        sz = np.zeros(8, dtype=np.int64)
+        engine._ck(engine.lib.pb200_sizes(engine.ctx, sz.ctypes.data))
+        (self.n_contigs, self.n_bases, self.n_nodes, self.n_orfs, self.n_overlaps, self.n_bridges,
+         self.n_calls, _) = (int(v) for v in sz)
+        self.calls = np.zeros(self.n_calls, dtype=N.CALL)
+        engine._ck(engine.lib.pb200_get_calls(engine.ctx, self.calls.ctypes.data))
+        self.contigs = np.zeros(self.n_contigs, dtype=N.CONTIG)
+        engine._ck(engine.lib.pb200_get_contigs(engine.ctx, self.contigs.ctypes.data))
+        self._orfs = self._nodes = self._edges = None
+        self.launches = int(engine.lib.pb200_launch_count(engine.ctx))
+        self.stage_ms = engine._stage_times()
+
+    # lazily fetched tables -- only valid to request before the engine runs the next batch
+    @property
+    def orfs(self):
+        if self._orfs is None:
+            self._orfs = np.zeros(self.n_orfs, dtype=N.ORF)
+            self._e._ck(self._e.lib.pb200_get_orfs(self._e.ctx, self._orfs.ctypes.data))
+        return self._orfs
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            self._nodes = np.zeros(self.n_nodes, dtype=N.NODE)
+            self._e._ck(self._e.lib.pb200_get_nodes(self._e.ctx, self._nodes.ctypes.data))
+        return self._nodes
+
+    @property
+    def edges(self):
+        if self._edges is None:
+            self._e._ck(self._e.lib.pb200_build_edges(self._e.ctx))
+            sz = np.zeros(8, dtype=np.int64)
+            self._e._ck(self._e.lib.pb200_sizes(self._e.ctx, sz.ctypes.data))
+            self._edges = np.zeros(int(sz[7]), dtype=N.EDGE)
+            self._e._ck(self._e.lib.pb200_get_edges(self._e.ctx, self._edges.ctypes.data))
+        return self._edges
+
+    def fetch_all(self):
+        self.orfs, self.nodes, self.edges
+        return self
+
+    def check(self, contig: int | None = None):
+        """Raise what the reference would have raised for a contig (or for any contig)."""
+        cs = self.contigs if contig is None else self.contigs[contig:contig + 1]
+        for i, c in enumerate(cs):
+            err = int(c["err"])
+            if not err:
+                continue
+            k = i if contig is None else contig
+            if err & N.ERR_CHAR:
+                raise KeyError("contig %d: letter outside the IUPAC alphabet (functions.rev_comp)" % k)
+            if err & N.ERR_PARALLEL:
+                raise ValueError("parallel edges are forbidden")
+            if err & N.ERR_NOPATH and not (err & ~N.ERR_NOPATH):
+                continue                        # no source->target path: no calls (undefined in the reference)
+            raise PhanotateError("contig %d: device error bits 0x%x" % (k, err))
+
+    def call_rows(self, contig: int):
+        """[(left, right, strand char, '%E' score)] in path order, the columns Locus.tabular prints."""
+        c = self.contigs[contig]
+        rows = []
+        for r in self.calls[c["call_off"]:c["call_off"] + c["n_calls"]]:
+            rows.append((int(r["left"]), int(r["right"]), "+" if r["strand"] > 0 else "-", "%E" % float(r["score"])))
+        return rows
+
+
+class Engine:
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self.lib = N.load(lib_path)
+        ctx = ctypes.c_void_p()
+        rc = self.lib.pb200_create(int(device), ctypes.byref(ctx))
+        if rc != 0 or not ctx.value:
+            raise RuntimeError("phanotate_b200: cannot open CUDA device %d (no CPU fallback exists)" % device)
+        self.ctx = ctx
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PhanotateError(self.lib.pb200_last_error(self.ctx).decode() or "error %d" % rc)
+
+    def _stage_times(self):
+        names = (ctypes.c_char_p * 64)()
+        ms = (ctypes.c_float * 64)()
+        n = self.lib.pb200_stage_times(self.ctx, names, ms, 64)
+        out = {}
+        for i in range(max(n, 0)):
+            k = names[i].decode()
+            out[k] = out.get(k, 0.0) + float(ms[i])
+        return out
+
+    def run_packed(self, bases, offsets, params=None, names=None, device_pointers=False) -> Result:
+        """bases: uint8 array of concatenated contigs, offsets: int64[n+1] (or device addresses of both)."""
+        if params is None:
+            params = make_params()
+        if device_pointers:
+            bptr, optr, n = int(bases), int(offsets[0]), int(offsets[1])
+            self._ck(self.lib.pb200_run(self.ctx, bptr, optr, n, params.ctypes.data, N.INPUT_DEVICE))
+        else:
+            bases = np.ascontiguousarray(bases, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                        params.ctypes.data, 0))
+        return Result(self, names)
+
+    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None) -> Result:
+        seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+        bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+        return self.run_packed(bases, offs, params, names)
