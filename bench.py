@@ -1,0 +1,298 @@
+#!/usr/bin/env python3
+"""Benchmark of the PHANOTATE hot path (contig Gbp/s through ORF-scan + graph-solve).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contigs C]
+
+A step = one pass of the whole hot path over one batch of synthetic contigs: BASELINE.json
+config 4, `contigs` x 50 kb phage-like windows (SURVEY.md 8d generator), default 10,000 contigs
+= 0.5 Gbp per GPU.  With N > 1 (launched under torchrun, one rank per GPU) every rank runs its own
+batch of that size (weak scaling, contigs are independent) and the per-rank call tables are
+gathered to rank 0 over NCCL inside the timed region.
+
+Prints ONE JSON line (rank 0).  `value` is measured with the batch already resident in HBM;
+`e2e` is the same through the public Python API with pinned HOST buffers, the host->device copy of
+the bases and the device->host copy of the call table inside the timed region.
+`--impl reference` times the CPU oracle port (oracle/phanotate_oracle.py, one process per contig
+on all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from phanotate_b200 import synth  # noqa: E402
+
+METRIC = "contig Gbp/s through ORF-scan+graph-solve"
+UNIT = "Gbp/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores
+def _oracle_one(seq: bytes):
+    from oracle import phanotate_oracle as O
+    rows = O.call_contig(seq.decode())[3]
+    return len(rows)
+
+
+def cpu_sample(n_contigs: int, length: int, first: int = 0):
+    """Time the oracle on n_contigs contigs of the workload with one process per contig on all cores."""
+    from multiprocessing import Pool
+    cores = os.cpu_count() or 1
+    seqs = [synth.synth4_contig(first + k, length) for k in range(n_contigs)]
+    with Pool(cores) as pool:
+        pool.map(_oracle_one, seqs[:min(cores, len(seqs))])      # warm the workers (imports)
+        t = time.perf_counter()
+        ncalls = sum(pool.map(_oracle_one, seqs, chunksize=1))
+        dt = time.perf_counter() - t
+    bp = n_contigs * length
+    return {"value": bp / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d contigs x %d bp of the same synthetic workload (oracle/phanotate_oracle.py, "
+                      "multiprocessing, %.1f s wall, %d calls)" % (n_contigs, length, dt, ncalls)}, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = max(2 * (os.cpu_count() or 1), 8)
+    vals, last = [], None
+    for s in range(args.warmup + args.steps):
+        cb, dt = cpu_sample(n, args.length, first=0)
+        if s >= args.warmup:
+            vals.append((n * args.length, dt))
+        last = cb
+    bp = sum(v[0] for v in vals)
+    sec = sum(v[1] for v in vals)
+    value = bp / sec / 1e9
+    last["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(len(vals), 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+int256",
+            "data": "synthetic", "config": workload_config(args, world), "cpu_baseline": last,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "synthetic %d phage contigs x %d bp per GPU (BASELINE.json config 4: donor lambda|T4|phiX "
+                        "windows, 2%% point mutations, seed 20261017)" % (args.contigs, args.length),
+            "contigs_per_gpu": args.contigs, "contig_bp": args.length, "parallelism": "contig-sharded x%d" % world,
+            "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2" % (args.contigs * args.length / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contigs", type=int, default=10000)
+    ap.add_argument("--length", type=int, default=50000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="contigs in the cpu_baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from phanotate_b200.engine import Engine, make_params
+    from phanotate_b200 import _native as N
+    eng = Engine(local)
+    params = make_params()
+    # this rank's batch: contigs rank*C .. rank*C + C-1 of the generator
+    bases, offs = synth.synth4_batch(args.contigs, args.length, first=rank * args.contigs)
+    total_bp = int(offs[-1])
+    eng.pin(bases)
+    eng.pin(offs)
+
+    def barrier():
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def gather_calls():
+        """cross-contig gather of the call tables to rank 0 over NCCL (only collective of the path)."""
+        if dist is None:
+            return
+        n = eng.sizes()[6]
+        cnt = torch.tensor([n], device="cuda", dtype=torch.int64)
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        mx = int(max(int(c.item()) for c in allc))
+        ptr = eng.lib.pb200_device_calls(eng.ctx)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (max(n, 1) * N.CALL.itemsize,), "typestr": "|u1",
+                                        "data": (int(ptr), True), "version": 2}
+        mine = torch.zeros(max(mx, 1) * N.CALL.itemsize, dtype=torch.uint8, device="cuda")
+        if n:
+            mine[:n * N.CALL.itemsize] = torch.as_tensor(_Arr(), device="cuda")
+        out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, out, dst=0)
+        if rank == 0:
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    eng.run_packed(bases, offs, params, fetch=False)              # uploads the batch once
+    for _ in range(args.warmup):
+        eng.run_packed(bases, offs, params, resident=True, fetch=False)
+        gather_calls()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, stage, launches = 0.0, {}, 0
+    for _ in range(args.steps):
+        eng.run_packed(bases, offs, params, resident=True, fetch=False)
+        dev_ms += eng.last_run_ms()
+        for k, v in eng._stage_times().items():
+            stage[k] = stage.get(k, 0.0) + v
+        launches += int(eng.lib.pb200_launch_count(eng.ctx))
+        gather_calls()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    sizes = eng.sizes()
+    ncalls = sizes[6]
+
+    # ---- end to end through the public API with pinned host buffers (`e2e`)
+    barrier()
+    t1 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        res = eng.run_packed(bases, offs, params)                  # H2D bases+offsets, kernels, D2H calls+contig table
+        d2h = res.calls.nbytes + res.contigs.nbytes
+        gather_calls()
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    errs = int((res.contigs["err"] != 0).sum())
+
+    if dist is not None:
+        tmax = torch.tensor([wall, wall_e2e, dev_ms / 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        wall, wall_e2e, dev_s = (float(x) for x in tmax.tolist())
+        tot = torch.tensor([total_bp, ncalls, errs], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        job_bp, job_calls, errs = (int(x) for x in tot.tolist())
+    else:
+        dev_s = dev_ms / 1e3
+        job_bp, job_calls = total_bp, ncalls
+
+    if rank == 0:
+        # N=1: device time from CUDA events on the library's stream; N>1: max-over-ranks wall incl. the NCCL gather
+        t_value = dev_s if world == 1 else wall
+        value = job_bp * args.steps / t_value / 1e9
+        e2e = job_bp * args.steps / wall_e2e / 1e9
+        # roofline of the dominant kernel (largest share of the step), algorithmic bytes = 1 B/bp + 24 B/CDS
+        peak, peak_src = measured_peak_gbs()
+        dom = max(stage, key=stage.get) if stage else None
+        roof = None
+        if dom:
+            per_launch_s = stage[dom] / args.steps / 1e3
+            alg = total_bp * 1.0 + 24.0 * ncalls
+            ach = alg / per_launch_s / 1e9
+            roof = {"bound": "hbm", "kernel": "k_" + dom if dom != "solve" else "k_solve", "achieved": ach,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_s * 1e3,
+                    "share_of_step": stage[dom] / max(sum(stage.values()), 1e-9),
+                    "note": "integer/decimal-emulation bound, not HBM bound (DESIGN.md): frac is reported for the contract"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+int256", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps},
+                "gpu_launches": launches, "roofline": roof,
+                "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in sorted(stage.items(), key=lambda x: -x[1])},
+                "wall_ms_per_step": 1e3 * wall / args.steps, "calls_per_step": job_calls, "contig_errors": errs,
+                "tables": {"nodes": sizes[2], "orfs": sizes[3], "overlap_edges": sizes[4], "bridge_edges": sizes[5]}}
+        if world == 1 and not args.no_cpu:
+            n = args.cpu_sample or 2 * (os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_sample(n, args.length)[0]
+        print(json.dumps(line), flush=True)
+    eng.unpin(bases)
+    eng.unpin(offs)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@
  */
 #ifndef PHANOTATE_B200_H
 #define PHANOTATE_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -102,7 +103,10 @@ enum {
     PB200_ERR_LOOKUP = 64
 };
 
-enum { PB200_INPUT_DEVICE = 1 };   /* flags of pb200_run: bases/offsets are device pointers */
+enum {
+    PB200_INPUT_DEVICE = 1,   /* flags of pb200_run: bases/offsets are device pointers */
+    PB200_REUSE_INPUT = 2     /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+};
 
 typedef struct pb200_ctx pb200_ctx;
 
@@ -136,6 +140,16 @@ int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const i
 int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);
 /* number of kernels launched by the last pb200_run */
 int pb200_launch_count(pb200_ctx* ctx);
+/* device time of the whole last pb200_run (events at its first and last operation on the stream) */
+float pb200_last_run_ms(pb200_ctx* ctx);
+/* device address of the call table of the last run (n_calls rows), for zero-copy hand-off to a
+ * collective (the multi-GPU gather of call tables) */
+const pb200_call* pb200_device_calls(pb200_ctx* ctx);
+/* page-lock / unlock a caller-owned host buffer so that pb200_run's copies are asynchronous DMA */
+int pb200_pin_host(void* ptr, size_t bytes);
+int pb200_unpin_host(void* ptr);
+/* sizeof() of dec, params, call, orf, node, edge, contig -- lets a binding verify its struct layout */
+int pb200_struct_sizes(int32_t out[8]);
 
 #ifdef __cplusplus
 }

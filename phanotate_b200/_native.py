@@ -35,6 +35,7 @@ assert PARAMS.itemsize == 4 + 32 + 192 + 4 + 32 + 8
 
 ERR_CHAR, ERR_RANGE, ERR_PARALLEL, ERR_OVERFLOW, ERR_NOPATH, ERR_INTERNAL, ERR_LOOKUP = 1, 2, 4, 8, 16, 32, 64
 INPUT_DEVICE = 1
+REUSE_INPUT = 2
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 
@@ -72,4 +73,22 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_bellman_ford.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]
     lib.pb200_stage_times.argtypes = [vp, vp, vp, ctypes.c_int]
     lib.pb200_launch_count.argtypes = [vp]
+    lib.pb200_last_run_ms.argtypes = [vp]
+    lib.pb200_last_run_ms.restype = ctypes.c_float
+    lib.pb200_device_calls.argtypes = [vp]
+    lib.pb200_device_calls.restype = ctypes.c_void_p
+    lib.pb200_pin_host.argtypes = [vp, ctypes.c_size_t]
+    lib.pb200_unpin_host.argtypes = [vp]
+    lib.pb200_struct_sizes.argtypes = [vp]
+    sz = (ctypes.c_int32 * 8)()
+    lib.pb200_struct_sizes(sz)
+    want = [DEC.itemsize, PARAMS.itemsize, CALL.itemsize, ORF.itemsize, NODE.itemsize, EDGE.itemsize, CONTIG.itemsize]
+    if list(sz)[:7] != want:
+        raise RuntimeError("phanotate_b200: struct layout mismatch between %s %s and the binding %s" % (p, list(sz)[:7], want))
     return lib
+
+
+EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_sizes", "pb200_get_calls",
+           "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
+           "pb200_bellman_ford", "pb200_stage_times", "pb200_launch_count", "pb200_last_run_ms",
+           "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes"]

@@ -167,6 +167,7 @@ struct pb200_ctx {
     size_t evused = 0;
     int launches = 0;
     int sm_count = 148;
+    cudaEvent_t run_a = nullptr, run_b = nullptr;
 };
 static int buf_ensure(pb200_ctx* ctx, DevBuf& b, size_t bytes) {
     b.used = 0;
@@ -441,6 +442,8 @@ void pb200_destroy(pb200_ctx* ctx) {
     cudaFree(ctx->in_off.p);
     cudaFree(ctx->scratch.p);
     for (auto e : ctx->evpool) cudaEventDestroy(e);
+    if (ctx->run_a) cudaEventDestroy(ctx->run_a);
+    if (ctx->run_b) cudaEventDestroy(ctx->run_b);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
 #else
     for (int k = 0; k < NPHASE; k++) free(ctx->ph[k].p);
@@ -470,6 +473,11 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     ctx->times.clear();
     ctx->evused = 0;
     ctx->launches = 0;
+    if (!ctx->run_a) {
+        CK(cudaEventCreate(&ctx->run_a));
+        CK(cudaEventCreate(&ctx->run_b));
+    }
+    CK(cudaEventRecord(ctx->run_a, ctx->stream));
     if (flags & PB200_INPUT_DEVICE) {
         i64 last;
         CK(cudaMemcpyAsync(&last, offsets + n_contigs, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -477,6 +485,14 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
         B.nb = last;
         B.seq = bases;
         B.coff = offsets;
+    } else if (flags & PB200_REUSE_INPUT) {
+        B.nb = offsets[n_contigs];
+        if (!ctx->in_seq.p || ctx->in_seq.cap < (size_t)B.nb || !ctx->in_off.p) {
+            ctx->err = "PB200_REUSE_INPUT without a resident batch";
+            return -2;
+        }
+        B.seq = (const u8*)ctx->in_seq.p;
+        B.coff = (const i64*)ctx->in_off.p;
     } else {
         B.nb = offsets[n_contigs];
         if (B.nb < 1 || !bases) {
@@ -508,9 +524,53 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     rc = run_pipeline(ctx);
     if (rc) return rc;
 #ifndef PB_HOSTSIM
+    CK(cudaEventRecord(ctx->run_b, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 #endif
     ctx->have = true;
+    return 0;
+}
+
+float pb200_last_run_ms(pb200_ctx* ctx) {
+#ifndef PB_HOSTSIM
+    float v = -1.f;
+    if (ctx && ctx->have && cudaEventElapsedTime(&v, ctx->run_a, ctx->run_b) == cudaSuccess) return v;
+#else
+    (void)ctx;
+#endif
+    return -1.f;
+}
+
+const pb200_call* pb200_device_calls(pb200_ctx* ctx) {
+    return (ctx && ctx->have) ? (const pb200_call*)ctx->B.calls : nullptr;
+}
+
+int pb200_pin_host(void* ptr, size_t bytes) {
+#ifndef PB_HOSTSIM
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : -1;
+#else
+    (void)ptr;
+    (void)bytes;
+    return 0;
+#endif
+}
+int pb200_unpin_host(void* ptr) {
+#ifndef PB_HOSTSIM
+    return cudaHostUnregister(ptr) == cudaSuccess ? 0 : -1;
+#else
+    (void)ptr;
+    return 0;
+#endif
+}
+int pb200_struct_sizes(int32_t out[8]) {
+    out[0] = (int32_t)sizeof(pb200_dec);
+    out[1] = (int32_t)sizeof(pb200_params);
+    out[2] = (int32_t)sizeof(pb200_call);
+    out[3] = (int32_t)sizeof(pb200_orf);
+    out[4] = (int32_t)sizeof(pb200_node);
+    out[5] = (int32_t)sizeof(pb200_edge);
+    out[6] = (int32_t)sizeof(pb200_contig);
+    out[7] = 0;
     return 0;
 }
 

@@ -171,19 +171,33 @@ class Engine:
             out[k] = out.get(k, 0.0) + float(ms[i])
         return out
 
-    def run_packed(self, bases, offsets, params=None, names=None, device_pointers=False) -> Result:
-        """bases: uint8 array of concatenated contigs, offsets: int64[n+1] (or device addresses of both)."""
+    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True):
+        """bases: uint8 array of concatenated contigs, offsets: int64[n+1].
+
+        resident=True reuses the batch the previous call uploaded (inputs already in HBM).
+        fetch=False skips copying the result tables to the host (returns None).
+        """
         if params is None:
             params = make_params()
-        if device_pointers:
-            bptr, optr, n = int(bases), int(offsets[0]), int(offsets[1])
-            self._ck(self.lib.pb200_run(self.ctx, bptr, optr, n, params.ctypes.data, N.INPUT_DEVICE))
-        else:
-            bases = np.ascontiguousarray(bases, dtype=np.uint8)
-            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-            self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
-                                        params.ctypes.data, 0))
-        return Result(self, names)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                    params.ctypes.data, N.REUSE_INPUT if resident else 0))
+        return Result(self, names) if fetch else None
+
+    def last_run_ms(self) -> float:
+        return float(self.lib.pb200_last_run_ms(self.ctx))
+
+    def sizes(self):
+        sz = np.zeros(8, dtype=np.int64)
+        self._ck(self.lib.pb200_sizes(self.ctx, sz.ctypes.data))
+        return [int(v) for v in sz]
+
+    def pin(self, arr: np.ndarray):
+        return self.lib.pb200_pin_host(arr.ctypes.data, arr.nbytes) == 0
+
+    def unpin(self, arr: np.ndarray):
+        return self.lib.pb200_unpin_host(arr.ctypes.data) == 0
 
     def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None) -> Result:
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]

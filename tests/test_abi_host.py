@@ -1,0 +1,102 @@
+"""CPU-only checks of the boundary: the CUDA library exports every symbol of include/phanotate_b200.h,
+struct layouts agree with the binding, the product refuses to run without a GPU, and the host-side
+logic (parameter parsing, ordering views) behaves like the reference."""
+import ctypes
+import os
+import re
+import subprocess
+from decimal import Decimal
+
+import numpy as np
+import pytest
+
+import conftest
+from phanotate_b200 import _native as N
+from phanotate_b200 import engine, mirror
+from helpers import INDEX, STRESS, golden_text, md5, seq_of
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HOSTSIM = os.path.join(ROOT, "tests", "native", "pb200_hostsim.so")
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "phanotate_b200.h")).read()
+    declared = set(re.findall(r"\b(pb200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(N.EXPORTS)
+    if not os.path.exists(N.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(N.LIB_PATH)                     # loading needs no GPU
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    sz = (ctypes.c_int32 * 8)()
+    lib.pb200_struct_sizes(sz)
+    assert list(sz)[:7] == [N.DEC.itemsize, N.PARAMS.itemsize, N.CALL.itemsize, N.ORF.itemsize, N.NODE.itemsize,
+                            N.EDGE.itemsize, N.CONTIG.itemsize]
+
+
+@pytest.mark.skipif(conftest.HAVE_GPU, reason="only meaningful on a box without a GPU")
+def test_product_fails_loudly_without_gpu():
+    with pytest.raises(RuntimeError):
+        engine.Engine(0)
+
+
+def test_start_codon_weights_match_reference_normalisation():
+    w = engine.parse_start_codons(engine.DEFAULT_START_CODONS)          # file_handling.py:58-62
+    assert w["atg"] == Decimal(1)
+    assert str(w["gtg"]) == "0.1176470588235294117647058824"
+    assert str(w["ttg"]) == "0.05882352941176470588235294118"
+    p = engine.make_params()
+    assert int(p["n_start"][0]) == 3 and int(p["min_orf_len"][0]) == 90
+    assert N.dec_to_decimal(p["start_weight"][0][1]) == w["gtg"]
+
+
+@pytest.fixture(scope="module")
+def sim():
+    """Host build of the SAME stage functions the kernels run (tests only; see pb200.cu header)."""
+    src = os.path.join(ROOT, "phanotate_b200", "csrc")
+    deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "phanotate_b200.h")]
+    if not os.path.exists(HOSTSIM) or any(os.path.getmtime(d) > os.path.getmtime(HOSTSIM) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-DPB_HOSTSIM", "-shared", "-fPIC",
+                               "-o", HOSTSIM, os.path.join(src, "pb200.cu")])
+    e = engine.Engine(0, lib_path=HOSTSIM)
+    yield e
+    e.close()
+
+
+def _texts(res, k):
+    calls = "".join("%d\t%d\t%s\t%s\n" % r for r in res.call_rows(k))
+    return calls, "".join(mirror.orf_table_lines(res, k)), "".join(mirror.ContigGraph(res, k).dump_lines())
+
+
+def test_stage_logic_on_host_matches_reference_goldens(sim):
+    """Stage functions (host build) on the 64 stress contigs in ONE batch: calls, ORF table in
+    Orfs.iter_orfs() order and the --dump edge text in Graph.iteredges() order."""
+    res = sim.run([seq_of(n) for n in STRESS]).fetch_all()
+    for k, name in enumerate(STRESS):
+        assert int(res.contigs[k]["err"]) == 0, name
+        calls, orfs, edges = _texts(res, k)
+        assert calls == golden_text(name, "calls.tsv"), name
+        assert orfs == golden_text(name, "orfs.csv.gz"), name
+        assert edges == golden_text(name, "edges.txt.gz"), name
+
+
+@pytest.mark.parametrize("name", ["phiX174", "lambda", "T4", "synth4_0"])
+def test_stage_logic_on_host_fixtures(sim, name):
+    res = sim.run([seq_of(name)]).fetch_all()
+    calls, orfs, edges = _texts(res, 0)
+    g = INDEX[name]
+    assert (md5(calls), md5(orfs), md5(edges)) == (g["calls_md5"], g["orfs_md5"], g["edges_md5"])
+
+
+def test_literal_bellman_ford_entry_point(sim):
+    # graph with a tie: two equal-cost paths 0->1->3 and 0->2->3; strict '<' keeps the first found
+    src = np.array([0, 0, 1, 2], dtype=np.int32)
+    dst = np.array([1, 2, 3, 3], dtype=np.int32)
+    w = np.zeros((4, 8), dtype=np.uint32)
+    w[:, 0] = [5, 5, 7, 7]
+    path = np.zeros(4, dtype=np.int32)
+    n = ctypes.c_int32(0)
+    rc = sim.lib.pb200_bellman_ford(sim.ctx, 4, 4, src.ctypes.data, dst.ctypes.data, w.ctypes.data, 0, 3,
+                                    path.ctypes.data, ctypes.byref(n))
+    assert rc == 0 and list(path[:n.value]) == [0, 1, 3]

@@ -1,0 +1,74 @@
+"""Parity of the CUDA path (through the C ABI) with the reference goldens and the oracle -- needs a B200."""
+import numpy as np
+import pytest
+
+from helpers import INDEX, STRESS, golden_text, seq_of
+from phanotate_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from phanotate_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def calls_text(res, k):
+    return "".join("%d\t%d\t%s\t%s\n" % r for r in res.call_rows(k))
+
+
+def orf_rows(res, k):
+    c = res.contigs[k]
+    out = {}
+    for o in res.orfs[c["orf_off"]:c["orf_off"] + c["n_orfs"]]:
+        out[(int(o["start"]), int(o["stop"]), int(o["frame"]))] = (
+            int(o["rbs_score"]), str(N.dec_to_decimal(o["pstop"])), str(N.dec_to_decimal(o["weight"])))
+    return out
+
+
+def golden_orf_rows(name):
+    out = {}
+    for line in golden_text(name, "orfs.csv.gz").splitlines():
+        s, e, f, r, p, w = line.split(",")
+        out[(int(s), int(e), int(f))] = (int(r), p, w)
+    return out
+
+
+@pytest.mark.parametrize("name", ["phiX174", "lambda", "T4", "synth4_0", "synth4_1"])
+def test_fixture_calls_and_orf_tables(eng, name):
+    res = eng.run([seq_of(name)])
+    c = res.contigs[0]
+    g = INDEX[name]
+    assert int(c["err"]) == 0
+    assert (int(c["n_orfs"]), int(c["n_nodes"]) + 2, int(c["n_calls"])) == (g["n_orfs"], g["n_nodes"], g["n_calls"])
+    assert str(N.dec_to_decimal(c["pstop"])) == g["pstop"]
+    assert calls_text(res, 0) == golden_text(name, "calls.tsv")          # CDS coordinates, strand, %E score
+    assert orf_rows(res, 0) == golden_orf_rows(name)                      # 28-digit pstop and weight of every ORF
+    assert int(c["n_ties"]) == 0
+
+
+def test_stress_set_in_one_batch(eng):
+    """64 contigs (tiny, IUPAC, N-runs, mixed case) in a single launch sequence: batching + edge cases."""
+    res = eng.run([seq_of(n) for n in STRESS])
+    for k, name in enumerate(STRESS):
+        assert int(res.contigs[k]["err"]) == 0, name
+        assert calls_text(res, k) == golden_text(name, "calls.tsv"), name
+        assert orf_rows(res, k) == golden_orf_rows(name), name
+
+
+def test_batch_equals_single(eng):
+    names = ["phiX174", "stress3", "lambda", "stress17"]
+    res = eng.run([seq_of(n) for n in names])
+    for k, name in enumerate(names):
+        assert calls_text(res, k) == golden_text(name, "calls.tsv"), name
+
+
+def test_invalid_letter_sets_keyerror_bit(eng):
+    res = eng.run([b"acgt" * 40 + b"x" + b"acgt" * 40, seq_of("phiX174").encode()])
+    assert int(res.contigs[0]["err"]) & N.ERR_CHAR
+    with pytest.raises(KeyError):
+        res.check(0)
+    assert calls_text(res, 1) == golden_text("phiX174", "calls.tsv")
