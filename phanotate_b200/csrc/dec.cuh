@@ -54,12 +54,14 @@ PB_HD Dec dec_round(Wide<N> c, i32 e, i32 neg, int prec, bool sticky = false) {
     return r;
 }
 
-PB_HDN Dec dec_mul(const Dec& a, const Dec& b, int prec = PB_PREC) {
+PB_HDNI Dec dec_round8(const Wide<8>& c, i32 e, i32 neg, int prec, bool sticky) { return dec_round<8>(c, e, neg, prec, sticky); }
+
+PB_HDNI Dec dec_mul(const Dec& a, const Dec& b, int prec = PB_PREC) {
     Wide<8> p = w_mul(a.c, b.c);
-    return dec_round(p, a.e + b.e, a.neg ^ b.neg, prec);
+    return dec_round8(p, a.e + b.e, a.neg ^ b.neg, prec, false);
 }
 
-PB_HDN Dec dec_add(const Dec& a_in, const Dec& b_in, int prec = PB_PREC) {
+PB_HDNI Dec dec_add(const Dec& a_in, const Dec& b_in, int prec = PB_PREC) {
     bool az = dec_is_zero(a_in), bz = dec_is_zero(b_in);
     if (az && bz) {
         Dec r;
@@ -82,7 +84,7 @@ PB_HDN Dec dec_add(const Dec& a_in, const Dec& b_in, int prec = PB_PREC) {
                 e -= sh;
             }
         }
-        return dec_round(c, e, x.neg, prec);
+        return dec_round8(c, e, x.neg, prec, false);
     }
     Dec big = a_in, small = b_in;
     if (big.e < small.e) {
@@ -124,11 +126,11 @@ PB_HDN Dec dec_add(const Dec& a_in, const Dec& b_in, int prec = PB_PREC) {
             neg = small.neg;
         }
     }
-    return dec_round(B, small.e, neg, prec);
+    return dec_round8(B, small.e, neg, prec, false);
 }
 PB_HD Dec dec_sub(const Dec& a, const Dec& b, int prec = PB_PREC) { return dec_add(a, dec_neg(b), prec); }
 
-PB_HDN Dec dec_div(const Dec& a, const Dec& b, int prec = PB_PREC) {
+PB_HDNI Dec dec_div(const Dec& a, const Dec& b, int prec = PB_PREC) {
     Dec r;
     if (dec_is_zero(a)) {
         w_zero(r.c);
@@ -159,7 +161,7 @@ PB_HDN Dec dec_div(const Dec& a, const Dec& b, int prec = PB_PREC) {
             sh--;
         }
     }
-    return dec_round(Q, e, a.neg ^ b.neg, prec, inexact);
+    return dec_round8(Q, e, a.neg ^ b.neg, prec, inexact);
 }
 
 // value exactly one?
@@ -170,7 +172,7 @@ PB_HD bool dec_is_one_abs(const Dec& a) {
 }
 
 // x ** n for a non-negative integer n (libmpdec mpd_qpow integer branch)
-PB_HDN Dec dec_powi(const Dec& x, u32 n, int prec = PB_PREC) {
+PB_HDNI Dec dec_powi(const Dec& x, u32 n, int prec = PB_PREC) {
     if (n == 0) return dec_from_u64(1);
     if (dec_is_one_abs(x)) {                   // _qcheck_pow_one: 1.000**3 = 1.000000000, at most prec digits
         i64 sh = (i64)n * (i64)(-x.e);

@@ -26,7 +26,7 @@ PB_HD double wide_to_double_rne(const Wide<N>& v, bool sticky, int exp2) {   // 
     return ldexp((double)mant, exp2 + sh + 1);
 }
 
-PB_HDN double dec_to_double(const Dec& d, bool* ok) {
+PB_HDNI double dec_to_double(const Dec& d, bool* ok) {
     *ok = true;
     if (dec_is_zero(d)) return d.neg ? -0.0 : 0.0;
     double r;

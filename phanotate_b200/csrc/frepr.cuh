@@ -8,7 +8,7 @@
 #include <string.h>
 #include "dec.cuh"
 
-PB_HDN Dec dec_from_double_repr(double v, bool* ok) {
+PB_HDNI Dec dec_from_double_repr(double v, bool* ok) {
     Dec out;
     w_zero(out.c);
     out.e = 0;

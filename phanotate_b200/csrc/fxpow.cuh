@@ -38,7 +38,7 @@ PB_HD Fx fx_one() {
     r.w[6] = 1;
     return r;
 }
-PB_HD Fx fx_mul(const Fx& a, const Fx& b) {
+PB_HDNI Fx fx_mul(const Fx& a, const Fx& b) {
     Wide<14> p = w_mul(a, b);
     Fx r;
 #pragma unroll
@@ -73,7 +73,7 @@ PB_HD Fx fx_from_double(double v) {
 }
 
 // Dec (non-negative, value < 2^32) -> Fx
-PB_HDN Fx fx_from_dec(const Dec& x, bool* ok) {
+PB_HDNI Fx fx_from_dec(const Dec& x, bool* ok) {
     Fx r;
     w_zero(r);
     *ok = true;
@@ -103,7 +103,7 @@ PB_HDN Fx fx_from_dec(const Dec& x, bool* ok) {
 }
 
 // exp(T) for signed T; result must be < 2^32.
-PB_HDN Fx fx_exp(const SFx& T, bool* ok) {
+PB_HDNI Fx fx_exp(const SFx& T, bool* ok) {
     *ok = true;
     const Fx ln2 = fx_table(TBL(fx_ln2));
     Fx r;
@@ -181,7 +181,7 @@ PB_HDN Fx fx_exp(const SFx& T, bool* ok) {
 }
 
 // ln(X), X > 0
-PB_HDN SFx fx_ln(const Fx& X, bool* ok) {
+PB_HDNI SFx fx_ln(const Fx& X, bool* ok) {
     SFx L;
     w_zero(L.m);
     L.neg = 0;
@@ -254,7 +254,7 @@ PB_HDN SFx fx_ln(const Fx& X, bool* ok) {
 }
 
 // Fx (positive) -> Dec rounded half-even to prec digits
-PB_HDN Dec fx_to_dec(const Fx& V, int prec, bool* ok) {
+PB_HDNI Dec fx_to_dec(const Fx& V, int prec, bool* ok) {
     Dec r;
     w_zero(r.c);
     r.e = 0;
@@ -311,7 +311,7 @@ PB_HDN Dec fx_to_dec(const Fx& V, int prec, bool* ok) {
 }
 
 // x ** y, x > 0 (Dec), y given in fixed point with sign (non-integer on this path)
-PB_HDN Dec dec_pow_fx(const Dec& x, const Fx& y, int yneg, int prec, bool* ok) {
+PB_HDNI Dec dec_pow_fx(const Dec& x, const Fx& y, int yneg, int prec, bool* ok) {
     if (dec_is_one_abs(x)) {          // _qcheck_pow_one, non-integer exponent: 1.000...0 with prec digits
         Dec r;
         r.c = w_pow10<4>(prec - 1);
@@ -332,7 +332,7 @@ PB_HDN Dec dec_pow_fx(const Dec& x, const Fx& y, int yneg, int prec, bool* ok) {
     return r;
 }
 // Same with ln(x) supplied (ORF scoring reuses ln(1-pstop) for three exponents)
-PB_HDN Dec dec_pow_ln(const SFx& lnx, const Fx& y, int prec, bool* ok) {
+PB_HDNI Dec dec_pow_ln(const SFx& lnx, const Fx& y, int prec, bool* ok) {
     bool ok3, ok4;
     SFx T;
     T.m = fx_mul(lnx.m, y);

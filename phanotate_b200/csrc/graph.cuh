@@ -8,7 +8,7 @@
 // a 33-digit integer power each and are stored in CSR by source node.  Bridges over >500-bp
 // uncovered runs are rare and stored per contig.
 #pragma once
-#include "score.cuh"
+#include "hold.cuh"
 #include "dec2double.cuh"
 
 PB_HD bool kind_is_entry(int k) { return k == K_FSTART || k == K_RSTOP; }
@@ -107,12 +107,9 @@ PB_HDN void overlaps_of(const Batch& B, i32 ni, bool fill) {
             int ok = overlap_kind(B, j, ni);
             if (!ok) continue;
             if (fill) {
-                Dec w = overlap_score(B, c, j, ni, ok == 2);
                 B.ov_dst[k] = j;
-                B.ov_w[k] = w;
-                WInt wi;
-                if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
-                B.ov_wint[k] = wi;
+                B.ov_src[k] = ni;
+                B.ov_diff[k] = (u8)(ok == 2);
                 k++;
             }
             cnt++;
@@ -125,6 +122,17 @@ PB_HDN void st_ov_count(const Batch& B, i64 ni) {
 }
 PB_HDN void st_ov_fill(const Batch& B, i64 ni) {
     if (ni < B.nn) overlaps_of(B, (i32)ni, true);
+}
+// Stage 10b: weight of one overlap edge (a 33-digit integer power each).  item = overlap edge
+PB_HDN void st_ov_weight(const Batch& B, i64 k) {
+    if (k >= B.nov) return;
+    const i32 x = B.ov_src[k], e = B.ov_dst[k];
+    const int c = contig_of_node(B, x);
+    Dec w = overlap_score(B, c, e, x, B.ov_diff[k] != 0);
+    B.ov_w[k] = w;
+    WInt wi;
+    if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+    B.ov_wint[k] = wi;
 }
 
 // Stage 11: bridges over uncovered runs longer than 500 bp (functions.py:320-354).  item = contig

@@ -1,0 +1,298 @@
+// ORF scoring, split for the GPU (functions.py:286-301, orfs.py:122-127,162-173):
+//
+//   st_orf_factors  per ORF, uniform work: pstop, the six factors ((1-pstop)**pos_max[i])**pos_min[j]
+//                   (i != j), each also in "reciprocal-scaled" form for the fast multiply; length bin.
+//   st_len_scatter  counting sort of the ORFs by codon count (longest first) so that the lanes of
+//                   a warp run the same number of product steps.
+//   hold_run        per ORF in sorted order: hold *= factor[class(codon)] for every codon, then
+//                   Orf.score().  One step is one 28-digit Decimal multiplication with half-even
+//                   rounding; the fast path does it with ONE 3x4-limb product:
+//                       a*b/10^s = a * floor(b*2^124/10^s) / 2^124 + [0, 2^-30)
+//                   so integer part and rounding direction are known unless the top 32 fraction bits
+//                   fall within 2^-27 of 0, 1/2 or 1 -- then (p ~ 1e-8) the exact generic dec_mul runs.
+#pragma once
+#include "score.cuh"
+
+struct HoldFac {      // one factor b (28 digits) prepared for the fast multiply; 48 bytes = 3 x 16
+    u32 c27[4];       // floor(b * 2^124 / 10^27)
+    u32 c28[4];       // floor(b * 2^124 / 10^28)
+    u32 btop[2];      // b >> 30
+    i32 e;            // exponent of b
+    u32 ok;           // 1 if b has exactly 28 digits (fast path usable)
+};
+#ifdef __CUDACC__
+typedef uint4 U4;
+#else
+struct U4 {
+    u32 x, y, z, w;
+};
+#endif
+#define HOLD_BINS 2048
+
+PB_HD int fac_index(int imax, int imin) { return (imax - 1) * 2 + (imin - 1) - (imin > imax ? 1 : 0); }
+PB_HD int orf_steps(int start, int stop, bool rev) { return rev ? (start - stop + 2) / 3 : (stop - start + 2) / 3; }
+
+PB_HDNI void holdfac_prepare(const Dec& b, HoldFac& f) {
+    const u32 R27[6] = {0x524f8e02u, 0x7aa9a3eeu, 0xbaf51326u, 0x8f03f243u, 0xf3a68dbcu, 0x00000004u};   // 2^252/10^27
+    const u32 R28[6] = {0x3b6e5b00u, 0x0c4429feu, 0xc5e54eb7u, 0x41806506u, 0x7ec3daf9u, 0x00000000u};   // 2^252/10^28
+    f.e = b.e;
+    Wide<4> lo = w_pow10<4>(27), hi = w_pow10<4>(28);
+    f.ok = (w_cmp(b.c, lo) >= 0 && w_cmp(b.c, hi) < 0) ? 1u : 0u;
+    Wide<3> bc = w_resize<3>(b.c);
+    Wide<6> r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.w[i] = R27[i];
+    Wide<9> p = w_mul(bc, r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) f.c27[i] = p.w[i + 4];          // >> 128
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.w[i] = R28[i];
+    p = w_mul(bc, r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) f.c28[i] = p.w[i + 4];
+    Wide<4> t = w_shr(b.c, 30);
+    f.btop[0] = t.w[0];
+    f.btop[1] = t.w[1];
+}
+
+// Stage 7a: pstop and the six factors of one ORF.  item = ORF id
+PB_HDN void st_orf_factors(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    int lo = 0, hi = B.nc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.corf[mid] <= oi) lo = mid;
+        else hi = mid;
+    }
+    const int c = lo;
+    CStat* cs = B.cs + c;
+    const u8* s = B.seq + B.coff[c];
+    const int L = cs->L;
+    const int start = B.o_start[oi], stop = B.o_stop[oi];
+    const bool rev = B.o_frame[oi] < 0;
+    int x0 = rev ? stop - 1 : start - 1, x1 = rev ? start + 2 : stop + 2;   // extent of orf.seq (functions.py:206,219,234,246)
+    if (x0 < 0) x0 = 0;
+    if (x1 > L) x1 = L;
+    u32 cnt[4] = {0, 0, 0, 0};
+    for (int q = x0; q < x1; q++) {
+        int cd = base_code(lower(s[q]));
+        if (cd < 4) cnt[cd]++;
+    }
+    u32 na = cnt[0], nt = cnt[3], ng = cnt[2];
+    if (rev) {
+        na = cnt[3];
+        nt = cnt[0];
+        ng = cnt[1];
+    }
+    Dec len = dec_from_u64((u64)(x1 - x0));
+    Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);
+    Dec pstop = pstop_formula(Pa, Pt, Pg);
+    B.o_pstop[oi] = pstop;
+    Dec x = dec_sub(dec_one(), pstop);
+    bool okall = true;
+    const bool xone = dec_is_one_abs(x);
+    SFx lnx;
+    w_zero(lnx.m);
+    lnx.neg = 0;
+    if (!xone) {
+        bool o1, o2;
+        Fx X = fx_from_dec(x, &o1);
+        lnx = fx_ln(X, &o2);
+        okall = okall && o1 && o2;
+    }
+    u32 allok = 1;
+    for (int im = 1; im <= 3; im++) {
+        Dec A;
+        bool o = true;
+        if (cs->max_one[im]) A = x;                                   // x ** Decimal(1) == x
+        else if (xone) A = dec_pow_fx(x, cs->fmax[im], 0, PB_PREC, &o);
+        else A = dec_pow_ln(lnx, cs->fmax[im], PB_PREC, &o);
+        okall = okall && o;
+        SFx lnA;
+        bool haveL = false;
+        const bool aone = dec_is_one_abs(A);
+        for (int il = 1; il <= 3; il++) {
+            if (il == im) continue;
+            Dec f;
+            bool o2 = true;
+            if (cs->min_one[il]) f = A;
+            else if (aone) f = dec_pow_fx(A, cs->fmin[il], 0, PB_PREC, &o2);
+            else {
+                if (!haveL) {
+                    bool q1, q2;
+                    Fx XA = fx_from_dec(A, &q1);
+                    lnA = fx_ln(XA, &q2);
+                    okall = okall && q1 && q2;
+                    haveL = true;
+                }
+                f = dec_pow_ln(lnA, cs->fmin[il], PB_PREC, &o2);
+            }
+            okall = okall && o2;
+            const int k = fac_index(im, il);
+            B.o_fac[oi * 6 + k] = f;
+            HoldFac hf;
+            holdfac_prepare(f, hf);
+            allok &= hf.ok;
+            B.o_hf[oi * 6 + k] = hf;
+        }
+    }
+    if (!okall) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+    int n = orf_steps(start, stop, rev);
+    int bin = n < HOLD_BINS - 1 ? n : HOLD_BINS - 1;
+    B.o_bin[oi] = (unsigned short)(bin | (allok ? 0x8000 : 0));
+    PB_ATOMIC_ADD(&B.len_hist[HOLD_BINS - 1 - bin], 1u);              // reversed: longest ORFs first
+}
+PB_HDN void st_len_scatter(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    int bin = B.o_bin[oi] & 0x7FFF;
+    u32 pos = PB_ATOMIC_ADD_RET(&B.len_cursor[HOLD_BINS - 1 - bin], 1u);
+    B.o_order[B.len_hist[HOLD_BINS - 1 - bin] + pos] = (i32)oi;
+}
+
+// one multiplication hold * b.  a = coefficient of hold (28 digits, three limbs), eh its exponent.
+// Returns false when the rounding cannot be decided from 32 fraction bits (caller runs the exact path).
+PB_HD bool hold_step_fast(u32& a0, u32& a1, u32& a2, i32& eh, const U4& c27, const U4& c28, const U4& misc) {
+    // which power of ten is dropped: a*b >= 10^55 <=> 28 digits are dropped
+    const u64 atop = ((u64)a2 << 34) | ((u64)a1 << 2) | (a0 >> 30);
+    const u64 btop = ((u64)misc.y << 32) | misc.x;
+#ifdef __CUDA_ARCH__
+    const u64 hi = __umul64hi(atop, btop);
+#else
+    const u64 hi = (u64)(((unsigned __int128)atop * btop) >> 64);
+#endif
+    const bool big = hi >= 0x06867a5a867f103bull;        // floor(10^55 / 2^124)
+    const u32 c0 = big ? c28.x : c27.x, c1 = big ? c28.y : c27.y, c2 = big ? c28.z : c27.z, c3 = big ? c28.w : c27.w;
+    // p = a * c, seven limbs, column by column
+    u32 p[7];
+    {
+        u64 acc;
+        u32 hi3;
+        u64 t;
+#define MAC(x, y)                  \
+    t = (u64)(x) * (y);            \
+    acc += t;                      \
+    hi3 += (acc < t) ? 1u : 0u;
+#define NEXT(k)                              \
+    p[k] = (u32)acc;                         \
+    acc = (acc >> 32) | ((u64)hi3 << 32);    \
+    hi3 = 0;
+        acc = 0;
+        hi3 = 0;
+        MAC(a0, c0) NEXT(0)
+        MAC(a0, c1) MAC(a1, c0) NEXT(1)
+        MAC(a0, c2) MAC(a1, c1) MAC(a2, c0) NEXT(2)
+        MAC(a0, c3) MAC(a1, c2) MAC(a2, c1) NEXT(3)
+        MAC(a1, c3) MAC(a2, c2) NEXT(4)
+        MAC(a2, c3) NEXT(5)
+        p[6] = (u32)acc;
+#undef MAC
+#undef NEXT
+    }
+    // integer part = p >> 124, fraction top 32 bits = bits 92..123
+    u32 i0 = (p[3] >> 28) | (p[4] << 4), i1 = (p[4] >> 28) | (p[5] << 4), i2 = (p[5] >> 28) | (p[6] << 4);
+    const u32 i3 = p[6] >> 28;
+    const u32 fr = (p[2] >> 28) | (p[3] << 4);
+    // 10^27 <= I < 10^28 must hold (otherwise the scale guess was off by one ulp: exact path)
+    const bool ge27 = (i2 > 0x033b2e3cu) || (i2 == 0x033b2e3cu && (i1 > 0x9fd0803cu || (i1 == 0x9fd0803cu && i0 >= 0xe8000000u)));
+    const bool lt28 = (i2 < 0x204fce5eu) || (i2 == 0x204fce5eu && (i1 < 0x3e250261u || (i1 == 0x3e250261u && i0 < 0x10000000u)));
+    if (i3 != 0 || !ge27 || !lt28) return false;
+    if (fr < 0x7FFFFF00u) {
+        // round down
+    } else if (fr > 0x80000000u && fr < 0xFFFFFF00u) {
+        i0 += 1;                                   // round up; carry
+        if (i0 == 0) {
+            i1 += 1;
+            if (i1 == 0) i2 += 1;
+        }
+        if (i2 == 0x204fce5eu && i1 == 0x3e250261u && i0 == 0x10000000u) {   // 10^28 -> 10^27, exponent + 1
+            i0 = 0xe8000000u;
+            i1 = 0x9fd0803cu;
+            i2 = 0x033b2e3cu;
+            eh += 1;
+        }
+    } else {
+        return false;
+    }
+    a0 = i0;
+    a1 = i1;
+    a2 = i2;
+    eh += (i32)misc.z + (big ? 28 : 27);
+    return true;
+}
+
+// Stage 7b+c: the per-codon product and Orf.score() of ORF oi.  S holds this ORF's six HoldFac as
+// 18 U4 words with stride BD (shared memory on the GPU: S[(k*3+v)*BD + t]).
+PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
+    int lo = 0, hi = B.nc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (B.corf[mid] <= oi) lo = mid;
+        else hi = mid;
+    }
+    const int c = lo;
+    CStat* cs = B.cs + c;
+    const u8* meta = B.meta + B.coff[c];
+    const int start = B.o_start[oi], stop = B.o_stop[oi];
+    const bool rev = B.o_frame[oi] < 0;
+    const bool fastok = (B.o_bin[oi] & 0x8000) != 0;
+    const int step = rev ? -3 : 3;
+    const int n = orf_steps(start, stop, rev);
+    Dec hold = dec_one();
+    u32 a0 = 0, a1 = 0, a2 = 0;
+    i32 eh = 0;
+    bool infast = false;                     // hold currently lives in (a0,a1,a2,eh)
+    int b = start;
+    for (int it = 0; it < n; it++, b += step) {
+        const int code = meta[b - 1] >> 3;
+        const int k = TBL(gc_fac_index)[rev ? 1 : 0][code];
+        if (fastok) {
+            if (!infast) {
+                if (it == 0) {               // 1 * f == f exactly
+                    const Dec f = B.o_fac[(i64)oi * 6 + k];
+                    a0 = f.c.w[0];
+                    a1 = f.c.w[1];
+                    a2 = f.c.w[2];
+                    eh = f.e;
+                    infast = true;
+                    continue;
+                }
+            } else {
+                const U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
+                if (hold_step_fast(a0, a1, a2, eh, c27, c28, misc)) continue;
+                // undecidable from 32 fraction bits: exact multiplication, then back to the fast path
+                Dec h;
+                h.c.w[0] = a0;
+                h.c.w[1] = a1;
+                h.c.w[2] = a2;
+                h.c.w[3] = 0;
+                h.e = eh;
+                h.neg = 0;
+                h = dec_mul(h, B.o_fac[(i64)oi * 6 + k]);
+                a0 = h.c.w[0];
+                a1 = h.c.w[1];
+                a2 = h.c.w[2];
+                eh = h.e;
+                continue;
+            }
+        }
+        hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);             // functions.py:293,298 (generic path)
+    }
+    if (infast) {
+        hold.c.w[0] = a0;
+        hold.c.w[1] = a1;
+        hold.c.w[2] = a2;
+        hold.c.w[3] = 0;
+        hold.e = eh;
+        hold.neg = 0;
+    }
+    // Orf.score (orfs.py:122-127)
+    Dec sc = dec_div(dec_one(), hold);
+    int sw = B.o_sw[oi];
+    if (sw >= 0) sc = dec_mul(sc, B.P.startw[sw]);
+    sc = dec_mul(sc, cs->wrbs[B.o_rbs[oi]]);
+    sc.neg ^= 1;
+    B.o_weight[oi] = sc;
+    WInt wi;
+    if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+    B.o_wint[oi] = wi;
+}

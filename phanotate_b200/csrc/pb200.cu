@@ -44,10 +44,13 @@ PB_KERNEL(st_scan)
 PB_KERNEL(st_mark)
 PB_KERNEL(st_count64)
 PB_KERNEL(st_contig_offsets)
+PB_KERNEL(st_node_pos)
 PB_KERNEL(st_fill)
+PB_KERNEL(st_orf_factors)
+PB_KERNEL(st_len_scatter)
+PB_KERNEL(st_ov_weight)
 PB_KERNEL(st_contig_stats)
 PB_KERNEL(st_gap_lut)
-PB_KERNEL(st_score_orf)
 PB_KERNEL(st_node_attrs)
 PB_KERNEL(st_ov_count)
 PB_KERNEL(st_ov_fill)
@@ -64,6 +67,19 @@ __global__ void __launch_bounds__(PB_BLOCK) k_solve(const Batch B, i32 nc) {
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 c = warp; c < nc; c += nwarps) solve_contig(B, (int)c, lane, 32);
+}
+// per-codon product + Orf.score, ORFs in length-sorted order; each thread keeps its six prepared
+// factors in shared memory (18 x 16 B, stride = block size: conflict-free 128-bit loads)
+__global__ void __launch_bounds__(PB_BLOCK) k_hold(const Batch B) {
+    __shared__ U4 S[18 * PB_BLOCK];
+    const int t = threadIdx.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + t; i < B.no; i += (i64)gridDim.x * blockDim.x) {
+        const i32 oi = B.o_order[i];
+        const U4* src = (const U4*)(B.o_hf + (i64)oi * 6);
+#pragma unroll
+        for (int j = 0; j < 18; j++) S[j * PB_BLOCK + t] = src[j];
+        hold_run(B, oi, S, PB_BLOCK, t);
+    }
 }
 __global__ void k_pack_orfs(const Batch B, OrfRec* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.no; i += (i64)gridDim.x * blockDim.x) pack_orf(B, i, out);
@@ -255,6 +271,21 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         ctx->launches++;                                                                         \
         CK(cudaGetLastError());                                                                  \
     } while (0)
+#define PB_RUN_HOLD(no_)                                                                         \
+    do {                                                                                         \
+        if ((no_) > 0) {                                                                         \
+            StageTime t_;                                                                        \
+            t_.name = "hold";                                                                    \
+            t_.a = ev_get(ctx);                                                                  \
+            t_.b = ev_get(ctx);                                                                  \
+            cudaEventRecord(t_.a, ctx->stream);                                                  \
+            k_hold<<<grid_for(ctx, (i64)(no_), PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B);        \
+            cudaEventRecord(t_.b, ctx->stream);                                                  \
+            ctx->times.push_back(t_);                                                            \
+            ctx->launches++;                                                                     \
+            CK(cudaGetLastError());                                                              \
+        }                                                                                        \
+    } while (0)
 #define PB_SCAN64(ptr, n)                          \
     do {                                           \
         if (dev_scan<u64>(ctx, (ptr), (n))) return -1; \
@@ -330,6 +361,14 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
     do {                                                               \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
         ctx->launches++;                                               \
+    } while (0)
+#define PB_RUN_HOLD(no_)                                                   \
+    do {                                                                   \
+        for (i64 i_ = 0; i_ < (i64)(no_); i_++) {                          \
+            const i32 oi_ = B.o_order[i_];                                 \
+            hold_run(B, oi_, (const U4*)(B.o_hf + (i64)oi_ * 6), 1, 0);    \
+        }                                                                  \
+        ctx->launches++;                                                   \
     } while (0)
 #define PB_SCAN64(ptr, n) dev_scan<u64>(ctx, (ptr), (n))
 #define PB_SCAN32(ptr, n) dev_scan<u32>(ctx, (ptr), (n))

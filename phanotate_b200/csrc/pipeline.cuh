@@ -137,13 +137,30 @@ struct Batch {
     i32 nedges;
     u32* ed_cnt;          // [nn+1] out-degree (all edge kinds) then exclusive offsets
     EdgeRec* edges;
+    // node-parallel fill / ORF scoring split
+    u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
+    Dec* o_fac;           // [no*6] the six GC-frame factors of every ORF
+    struct HoldFac* o_hf; // [no*6] the same, prepared for the fast multiply
+    unsigned short* o_bin;   // [no] codon count bin | 0x8000 if the fast path applies
+    u32* len_hist;        // [HOLD_BINS+1]
+    u32* len_cursor;      // [HOLD_BINS]
+    i32* o_order;         // [no] ORF ids sorted by codon count, longest first
+    i32* ov_src;          // [nov]
+    u8* ov_diff;          // [nov]
 };
 
 #ifdef __CUDA_ARCH__
 #define PB_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define PB_ATOMIC_ADD_RET(p, v) atomicAdd((p), (v))
 #define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
 #else
 #define PB_ATOMIC_ADD(p, v) (*(p) += (v))
+static inline u32 pb_fetch_add(u32* p, u32 v) {
+    u32 o = *p;
+    *p += v;
+    return o;
+}
+#define PB_ATOMIC_ADD_RET(p, v) pb_fetch_add((p), (v))
 #define PB_ATOMIC_OR(p, v) (*(p) |= (v))
 #endif
 
@@ -178,7 +195,7 @@ PB_HD int contig_of(const Batch& B, i64 g) {
 // RBS motif score of one window, scalar form (functions.py:48-138).  s = contig bases, window =
 // s[i : i+21] clipped at L.  rev: score_rbs(rev_comp(window)).  Handles truncated windows and
 // ambiguity codes (a motif only ever matches plain acgt letters).
-PB_HDN int rbs_score_scalar(const u8* s, int L, int i, bool rev) {
+PB_HDNI int rbs_score_scalar(const u8* s, int L, int i, bool rev) {
     if (i < 0 || i >= L) return 0;
     int W = L - i;
     if (W > 21) W = 21;
@@ -524,12 +541,19 @@ PB_HDN void st_contig_offsets(const Batch& B, i64 c) {
     }
 }
 
-// Stage 4: fill node and ORF records; RBS training histogram; GC-frame training counts.
-// item = base position of the batch
-PB_HDN void st_fill(const Batch& B, i64 g) {
+// Stage 4a: global position of every node.  item = base position of the batch
+PB_HDN void st_node_pos(const Batch& B, i64 g) {
     if (g >= B.nb) return;
     u8 flag = B.nflag[g];
     if (!flag) return;
+    if (flag & 1) B.n_gpos[node_index(B, g, 0)] = ((u64)g << 1);
+    if (flag & 2) B.n_gpos[node_index(B, g, 1)] = ((u64)g << 1) | 1u;
+}
+// Stage 4b: fill node and ORF records; RBS training histogram; GC-frame training counts.  item = node
+PB_HDN void st_fill(const Batch& B, i64 node) {
+    if (node >= B.nn) return;
+    const i64 g = (i64)(B.n_gpos[node] >> 1);
+    const u8 flag = (B.n_gpos[node] & 1) ? (u8)(B.nflag[g] & (2 | 8)) : (u8)(B.nflag[g] & (1 | 4));
     int c = contig_of(B, g);
     i64 cb = B.coff[c];
     CView v;
@@ -540,7 +564,7 @@ PB_HDN void st_fill(const Batch& B, i64 g) {
     int p = (int)(g - cb) + 1;
     int f = (p - 1) % 3 + 1;
     if (flag & 1) {
-        i32 ni = node_index(B, g, 0);
+        i32 ni = (i32)node;
         i32 oi = orf_index(B, g);
         bool rev = (flag & 4) != 0;
         int key, len, trig = 0, rbs, sw;
@@ -570,7 +594,7 @@ PB_HDN void st_fill(const Batch& B, i64 g) {
         B.o_node[oi] = ni;
     }
     if (flag & 2) {
-        i32 ni = node_index(B, g, 1);
+        i32 ni = (i32)node;
         bool rev = (flag & 8) != 0;
         const int minlen = B.P.min_orf_len;
         int far, trig;

@@ -6,7 +6,7 @@
 PB_HD Dec dec_one() { return dec_from_u64(1); }
 
 // Pt*Pa*Pa + Pt*Pg*Pa + Pt*Pa*Pg, left to right, every operation rounded (functions.py:178, orfs.py:173)
-PB_HDN Dec pstop_formula(const Dec& Pa, const Dec& Pt, const Dec& Pg) {
+PB_HDNI Dec pstop_formula(const Dec& Pa, const Dec& Pt, const Dec& Pg) {
     Dec t1 = dec_mul(dec_mul(Pt, Pa), Pa);
     Dec t2 = dec_mul(dec_mul(Pt, Pg), Pa);
     Dec t3 = dec_mul(dec_mul(Pt, Pa), Pg);
@@ -171,7 +171,7 @@ PB_HD WInt wint_inf() {
     r.w[WN - 1] = 0x7FFFFFFFu;
     return r;
 }
-PB_HDN bool dec_to_wint(const Dec& d, WInt& out) {
+PB_HDNI bool dec_to_wint(const Dec& d, WInt& out) {
     Wide<WN> mag;
     bool ok = dec_to_milli_int<WN>(d, mag);
     if (ok && (mag.w[WN - 1] >> 16)) ok = false;      // |w| < 2^240: sums of 2^14 weights stay below the INF marker

@@ -8,9 +8,11 @@
 #if defined(__CUDACC__)
 #define PB_HD __host__ __device__ __forceinline__
 #define PB_HDN __host__ __device__
+#define PB_HDNI __host__ __device__ __noinline__      /* one copy in the kernel image: keeps the hot loops inside the I-cache */
 #else
 #define PB_HD inline
 #define PB_HDN
+#define PB_HDNI __attribute__((noinline))
 #endif
 
 typedef uint32_t u32;
@@ -156,27 +158,44 @@ PB_HD int w_bitlen(const Wide<N>& a) {
     }
     return 0;
 }
+// variable shifts with compile-time limb indices only (keeps the limbs in registers on the GPU)
 template <int N>
 PB_HD Wide<N> w_shr(const Wide<N>& a, int s) {     // logical right shift, 0 <= s < 32*N
-    Wide<N> r;
-    int ws = s >> 5, bs = s & 31;
+    Wide<N> r = a;
+    const int ws = s >> 5, bs = s & 31;
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        u32 lo = (i + ws < N) ? a.w[(i + ws < N) ? i + ws : 0] : 0u;
-        u32 hi = (i + ws + 1 < N) ? a.w[(i + ws + 1 < N) ? i + ws + 1 : 0] : 0u;
-        r.w[i] = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+    for (int k = 16; k >= 1; k >>= 1) {
+        if (k < N && (ws & k)) {
+#pragma unroll
+            for (int i = 0; i < N; i++) r.w[i] = (i + k < N) ? r.w[(i + k < N) ? i + k : 0] : 0u;
+        }
+    }
+    if (bs) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            u32 hi = (i + 1 < N) ? r.w[(i + 1 < N) ? i + 1 : 0] : 0u;
+            r.w[i] = (r.w[i] >> bs) | (hi << (32 - bs));
+        }
     }
     return r;
 }
 template <int N>
 PB_HD Wide<N> w_shl(const Wide<N>& a, int s) {     // left shift, bits shifted out are lost
-    Wide<N> r;
-    int ws = s >> 5, bs = s & 31;
+    Wide<N> r = a;
+    const int ws = s >> 5, bs = s & 31;
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        u32 hi = (i - ws >= 0) ? a.w[(i - ws >= 0) ? i - ws : 0] : 0u;
-        u32 lo = (i - ws - 1 >= 0) ? a.w[(i - ws - 1 >= 0) ? i - ws - 1 : 0] : 0u;
-        r.w[i] = bs ? ((hi << bs) | (lo >> (32 - bs))) : hi;
+    for (int k = 16; k >= 1; k >>= 1) {
+        if (k < N && (ws & k)) {
+#pragma unroll
+            for (int i = N - 1; i >= 0; i--) r.w[i] = (i - k >= 0) ? r.w[(i - k >= 0) ? i - k : 0] : 0u;
+        }
+    }
+    if (bs) {
+#pragma unroll
+        for (int i = N - 1; i >= 0; i--) {
+            u32 lo = (i - 1 >= 0) ? r.w[(i - 1 >= 0) ? i - 1 : 0] : 0u;
+            r.w[i] = (r.w[i] << bs) | (lo >> (32 - bs));
+        }
     }
     return r;
 }
@@ -259,7 +278,7 @@ PB_HD void w_round_drop(Wide<N>& a, int k, bool sticky_in, bool* inexact) {
 }
 // Knuth algorithm D: q = floor(u / v), r = u mod v.  v != 0.  NU >= NV.
 template <int NU, int NV>
-PB_HDN void w_divmod(const Wide<NU>& u_in, const Wide<NV>& v_in, Wide<NU>& q, Wide<NV>& r) {
+PB_HDNI void w_divmod(const Wide<NU>& u_in, const Wide<NV>& v_in, Wide<NU>& q, Wide<NV>& r) {
     int n = NV;
     while (n > 0 && v_in.w[n - 1] == 0) n--;
     w_zero(q);

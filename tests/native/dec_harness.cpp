@@ -3,6 +3,8 @@
 // Python's decimal (libmpdec) on the CPU box.  Not part of the product, never loaded by it.
 #include "../../phanotate_b200/csrc/fxpow.cuh"
 #include "../../phanotate_b200/csrc/frepr.cuh"
+#include "../../phanotate_b200/csrc/hold.cuh"
+#include "../../phanotate_b200/csrc/dec2double.cuh"
 
 struct TDec {
     u64 lo, hi;
@@ -67,6 +69,34 @@ void t_repr(int n, const double* v, TDec* o, int* okv) {
     for (int i = 0; i < n; i++) {
         bool ok;
         o[i] = out(dec_from_double_repr(v[i], &ok));
+        okv[i] = ok;
+    }
+}
+// fast 28x28-digit multiply used by the per-codon product; okv = 1 fast path decided, 0 = fell back
+void t_hold_fast(int n, const TDec* a, const TDec* b, TDec* o, int* okv) {
+    for (int i = 0; i < n; i++) {
+        Dec x = in(a[i]), y = in(b[i]);
+        HoldFac f;
+        holdfac_prepare(y, f);
+        U4 c27 = {f.c27[0], f.c27[1], f.c27[2], f.c27[3]}, c28 = {f.c28[0], f.c28[1], f.c28[2], f.c28[3]};
+        U4 misc = {f.btop[0], f.btop[1], (u32)f.e, f.ok};
+        u32 a0 = x.c.w[0], a1 = x.c.w[1], a2 = x.c.w[2];
+        i32 eh = x.e;
+        bool ok = f.ok && hold_step_fast(a0, a1, a2, eh, c27, c28, misc);
+        Dec r;
+        if (ok) {
+            r.c.w[0] = a0; r.c.w[1] = a1; r.c.w[2] = a2; r.c.w[3] = 0; r.e = eh; r.neg = 0;
+        } else {
+            r = dec_mul(x, y);
+        }
+        okv[i] = ok;
+        o[i] = out(r);
+    }
+}
+void t_to_double(int n, const TDec* a, double* o, int* okv) {
+    for (int i = 0; i < n; i++) {
+        bool ok;
+        o[i] = dec_to_double(in(a[i]), &ok);
         okv[i] = ok;
     }
 }

@@ -23,7 +23,8 @@ TDEC = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("e", "<i4"), ("neg", "<i4")])
 @pytest.fixture(scope="module")
 def lib():
     deps = [SRC] + [os.path.join(HERE, "..", "phanotate_b200", "csrc", f)
-                    for f in ("wide.cuh", "dec.cuh", "fxpow.cuh", "frepr.cuh", "tables.inc")]
+                    for f in ("wide.cuh", "dec.cuh", "fxpow.cuh", "frepr.cuh", "tables.inc", "hold.cuh", "score.cuh", "pipeline.cuh",
+                              "dec2double.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", SO, SRC])
     return ctypes.CDLL(SO)
@@ -200,3 +201,51 @@ def test_milli_integer(lib):
                 ctx.prec = 100
                 want = abs(int((x * 1000).to_integral_value(rounding="ROUND_DOWN")))
             assert got == want, (x, got, want)
+
+
+def test_fast_hold_multiply_is_exact(lib):
+    """hold * factor for 28-digit operands (functions.py:293): the one-product fast path must either
+    decide the half-even rounding correctly or hand over to the exact multiply."""
+    rng = random.Random(11)
+    xs, ys, plain = [], [], []
+    for i in range(200000):
+        a = rng.randrange(10 ** 27, 10 ** 28)
+        b = rng.randrange(10 ** 27, 10 ** 28)
+        plain.append(all(i % m for m in (7, 11, 13, 17)))
+        if i % 7 == 0:      # products just around 10^55 (27 vs 28 dropped digits)
+            b = (10 ** 55 // a) + rng.randrange(-3, 4)
+            b = min(max(b, 10 ** 27), 10 ** 28 - 1)
+        if i % 11 == 0:     # products whose dropped part is (almost) exactly one half
+            k = rng.randrange(10 ** 27, 10 ** 28)
+            a = 2 * rng.randrange(5 * 10 ** 26, 5 * 10 ** 27) + 1
+            b = ((2 * k + 1) * 10 ** 27 // (2 * a)) + rng.randrange(-1, 2)
+            b = min(max(b, 10 ** 27), 10 ** 28 - 1)
+        if i % 13 == 0:
+            a, b = 10 ** 28 - 1 - rng.randrange(0, 3), 10 ** 28 - 1 - rng.randrange(0, 3)
+        if i % 17 == 0:
+            a = 10 ** 27 + rng.randrange(0, 3)
+        xs.append(Decimal((0, tuple(map(int, str(a))), -28)))
+        ys.append(Decimal((0, tuple(map(int, str(b))), rng.choice([-28, -29, -31]))))
+    A, Bv = pack(xs), pack(ys)
+    o = np.zeros(len(xs), dtype=TDEC)
+    ok = np.zeros(len(xs), dtype=np.int32)
+    lib.t_hold_fast(len(xs), P(A), P(Bv), P(o), P(ok))
+    assert ok[np.array(plain)].mean() > 0.9999      # random operands: the fast path decides practically always
+    getcontext().prec = 28
+    for x, y, g in zip(xs, ys, unpack(o)):
+        assert same(x * y, g), (x, y, x * y, g)
+
+
+def test_dec_to_double_is_float_of_decimal(lib):
+    rng = random.Random(12)
+    xs = [rand_dec(rng) for _ in range(20000)]
+    xs += [Decimal("-4.827980747824565E+2"), Decimal("-6.1E+28"), Decimal("1E+60"), Decimal("4.9406564584124654E-30")]
+    xs = [x for x in xs if x == 0 or -70 < x.adjusted() < 100]
+    a = pack(xs)
+    o = np.zeros(len(xs), dtype=np.float64)
+    ok = np.zeros(len(xs), dtype=np.int32)
+    lib.t_to_double(len(xs), P(a), P(o), P(ok))
+    for x, g, k in zip(xs, o, ok):
+        if k:
+            assert float(x) == g and str(float(x)) == str(g), (x, float(x), g)
+    assert ok.mean() > 0.9
