@@ -187,24 +187,14 @@ def main():
             dist.barrier()
 
     def gather_calls():
-        """cross-contig gather of the call tables to rank 0 over NCCL (only collective of the path)."""
+        """cross-contig gather of the call tables to rank 0 over NCCL (the only collective of the path)."""
         if dist is None:
             return
+        from phanotate_b200.dist import DeviceCalls, gather_call_tables
         n = eng.sizes()[6]
-        cnt = torch.tensor([n], device="cuda", dtype=torch.int64)
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        mx = int(max(int(c.item()) for c in allc))
         ptr = eng.lib.pb200_device_calls(eng.ctx)
-
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (max(n, 1) * N.CALL.itemsize,), "typestr": "|u1",
-                                        "data": (int(ptr), True), "version": 2}
-        mine = torch.zeros(max(mx, 1) * N.CALL.itemsize, dtype=torch.uint8, device="cuda")
-        if n:
-            mine[:n * N.CALL.itemsize] = torch.as_tensor(_Arr(), device="cuda")
-        out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, out, dst=0)
+        mine = torch.as_tensor(DeviceCalls(ptr, n), device="cuda") if n else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        gather_call_tables(mine, n, dist, rank, world)
         if rank == 0:
             torch.cuda.synchronize()
 

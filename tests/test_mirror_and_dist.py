@@ -1,0 +1,169 @@
+"""Drop-in surface (phanotate_modules / fastpathz / phanotate.py) and the multi-rank host logic.
+
+CPU: the mirror is driven exactly like reference phanotate.py:40-76 drives the reference, on top of the
+host build of the stage functions (test-only).  GPU (-m gpu): the same through the CUDA library.
+"""
+import io
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import INDEX, golden_text, md5, seq_of
+from phanotate_b200 import _native as N
+from phanotate_b200 import dist as pdist
+from phanotate_b200.engine import Engine, parse_start_codons
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HOSTSIM = os.path.join(ROOT, "tests", "native", "pb200_hostsim.so")
+
+
+class Locus:
+    start_codons = parse_start_codons("atg:0.85,gtg:0.10,ttg:0.05")
+    stop_codons = ['tag', 'tga', 'taa']
+    min_orf_len = 90
+
+    def __init__(self, dna):
+        self._d = dna
+
+    def seq(self):
+        return self._d
+
+    def length(self):
+        return len(self._d)
+
+
+def drive_like_reference(name):
+    """phanotate.py:40-76 with our modules substituted for the reference's."""
+    import fastpathz as fz
+    from phanotate_modules import functions
+    from phanotate_modules.edges import Edge
+    from phanotate_modules.nodes import Node  # noqa: F401  (eval)
+    from phanotate_modules.file_handling import pairwise
+    locus = Locus(seq_of(name))
+    orfs = functions.get_orfs(locus)
+    graph = functions.get_graph(orfs)
+    orf_txt = "".join("%d,%d,%d,%d,%s,%s\n" % (o.start, o.stop, o.frame, o.rbs_score, o.pstop, o.weight)
+                      for o in orfs.iter_orfs())
+    edge_txt = "".join(str(e) + "\n" for e in graph.iteredges())
+    source = "Node('source','source',0,0)"
+    target = "Node('target','target',0," + str(locus.length() + 1) + ")"
+    fz.empty_graph()
+    for e in graph.iteredges():
+        fz.add_edge(str(e))
+    path = fz.get_path(source=source, target=target)[1:] if len(graph) > 2 else []
+    rows = []
+    for s, t in pairwise(path):
+        left, right = eval(s), eval(t)
+        w = graph.weight(Edge(left, right, 0))
+        rows.append("%d\t%d\t%s\t%s\n" % (left.position, right.position + 2, '+' if left.frame > 0 else '-', '%E' % w))
+    return orf_txt, edge_txt, "".join(rows), orfs, graph
+
+
+def _check(name):
+    orf_txt, edge_txt, calls, orfs, graph = drive_like_reference(name)
+    g = INDEX[name]
+    assert md5(orf_txt) == g["orfs_md5"] and md5(edge_txt) == g["edges_md5"] and md5(calls) == g["calls_md5"]
+    assert len(graph) == g["n_nodes"] and len(orfs) == g["n_families"]
+    assert str(orfs.pstop) == g["pstop"]
+    o = next(orfs.iter_orfs())
+    assert o.has_stop() or o.stop + 2 >= orfs.contig_length - 2 or o.frame < 0
+    assert orfs.get_orf(o.start, o.stop) is o and orfs.other_end[o.start] == o.stop
+
+
+@pytest.fixture()
+def sim_engine():
+    import fastpathz
+    from phanotate_modules import functions
+    if not os.path.exists(HOSTSIM):
+        pytest.skip("host build missing (tests/test_abi_host.py builds it)")
+    e = Engine(0, lib_path=HOSTSIM)
+    functions.set_engine(e)
+    fastpathz._engine = e
+    yield e
+    functions.set_engine(None)
+    fastpathz._engine = None
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["phiX174", "stress13", "stress26", "lambda"])
+def test_mirror_driven_like_reference_cpu(sim_engine, name):
+    _check(name)
+
+
+def test_cli_tabular_output_cpu(sim_engine, capsys):
+    import phanotate
+    phanotate.main([os.path.join(ROOT, "tests", "data", "phiX174.fasta")])
+    out = capsys.readouterr().out
+    want = "#id:\tphiX174\n#START\tSTOP\tFRAME\tCONTIG\tSCORE\n"
+    for line in golden_text("phiX174", "calls.tsv").splitlines():
+        l, r, s, sc = line.split("\t")
+        want += "%s\t%s\t%s\tphiX174\t%s\n" % (l, r, s, sc)
+    assert out == want
+
+
+def test_cli_dump_matches_reference_cpu(sim_engine, capsys):
+    import phanotate
+    phanotate.main([os.path.join(ROOT, "tests", "data", "phiX174.fasta"), "--dump"])
+    assert capsys.readouterr().out == golden_text("phiX174", "edges.txt.gz")
+
+
+def test_cli_genbank_header_like_readme_cpu(sim_engine, capsys):
+    import phanotate
+    phanotate.main([os.path.join(ROOT, "tests", "data", "phiX174.fasta"), "-f", "genbank"])
+    out = capsys.readouterr().out.splitlines()
+    assert out[2:6] == ["     CDS             100..627", "                     /note=score:-4.827981E+02",
+                        "     CDS             687..1622", "                     /note=score:-4.857517E+06"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["phiX174", "stress13", "T4"])
+def test_mirror_driven_like_reference_gpu(name):
+    import fastpathz
+    from phanotate_modules import functions
+    functions.set_engine(None)
+    fastpathz._engine = None
+    _check(name)
+
+
+def test_lpt_sharding_balances_and_covers():
+    rng = np.random.default_rng(3)
+    lens = rng.integers(1000, 200000, size=500)
+    parts = pdist.shard_contigs(lens, 8)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(500))
+    loads = [int(lens[p].sum()) for p in parts]
+    assert max(loads) - min(loads) <= int(lens.max())
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from phanotate_b200 import _native as N
+from phanotate_b200.dist import gather_call_tables
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n = [3, 0][rank] if world == 2 else rank + 1
+rows = np.zeros(n, dtype=N.CALL)
+rows["contig"] = rank; rows["left"] = np.arange(n) * 10 + 1; rows["right"] = rows["left"] + 92; rows["strand"] = 1
+mine = torch.from_numpy(rows.view(np.uint8).copy()) if n else torch.zeros(1, dtype=torch.uint8)
+out = gather_call_tables(mine, n, dist, rank, world)
+if rank == 0:
+    got = [np.frombuffer(o.numpy().tobytes(), dtype=N.CALL) for o in out]
+    assert [len(g) for g in got] == [3, 0], [len(g) for g in got]
+    assert list(got[0]["left"]) == [1, 11, 21] and all(got[0]["contig"] == 0)
+    print("GATHER_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_call_table_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
