@@ -166,7 +166,12 @@ def main():
         return
 
     dist = torch = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -245,6 +250,10 @@ def main():
         dev_s = dev_ms / 1e3
         job_bp, job_calls = total_bp, ncalls
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         # N=1: device time from CUDA events on the library's stream; N>1: max-over-ranks wall incl. the NCCL gather
         t_value = dev_s if world == 1 else wall

@@ -38,12 +38,40 @@ PB_HD Fx fx_one() {
     r.w[6] = 1;
     return r;
 }
-PB_HDNI Fx fx_mul(const Fx& a, const Fx& b) {
-    Wide<14> p = w_mul(a, b);
+// a*b >> 192 from the partial products a_i*b_j with i+j >= CUT and j <= JMAX only.
+// Dropped columns sum to < 2^(32*CUT - 348) (absolute), so CUT = 4 costs < 2^-220; larger CUTs are
+// used where the result is multiplied by further small factors (Horner steps of exp).
+// JMAX = 5 is for operands known to be < 1 (limb 6 zero).
+template <int CUT, int JMAX>
+PB_HD Fx fx_mul_cols(const Fx& a, const Fx& b) {
     Fx r;
+    u64 acc = 0;
+    u32 hi = 0;
 #pragma unroll
-    for (int i = 0; i < FX_N; i++) r.w[i] = p.w[i + 6];
+    for (int k = CUT; k <= 12; k++) {
+#pragma unroll
+        for (int i = 0; i < FX_N; i++) {
+            const int j = k - i;
+            if (j >= 0 && j <= JMAX) {
+                u64 p = (u64)a.w[i] * b.w[j];
+                acc += p;
+                hi += (acc < p) ? 1u : 0u;
+            }
+        }
+        if (k >= 6) r.w[k - 6] = (u32)acc;
+        acc = (acc >> 32) | ((u64)hi << 32);
+        hi = 0;
+    }
     return r;
+}
+PB_HDNI Fx fx_mul(const Fx& a, const Fx& b) { return fx_mul_cols<4, 6>(a, b); }
+// Horner step of exp: p*u with u < 2^-24; `rest` = number of further multiplications by u the result
+// still goes through, which relaxes the absolute accuracy needed here by 2^(24*rest)
+PB_HDNI Fx fx_mul_u(const Fx& p, const Fx& u, int rest) {
+    // three variants only: instruction-cache footprint matters more than the last few skipped columns
+    if (rest <= 1) return fx_mul_cols<4, 5>(p, u);
+    if (rest <= 4) return fx_mul_cols<7, 5>(p, u);
+    return fx_mul_cols<9, 5>(p, u);
 }
 PB_HD double fx_to_double(const Fx& a) {
     int bl = w_bitlen(a);
@@ -160,7 +188,7 @@ PB_HDNI Fx fx_exp(const SFx& T, bool* ok) {
     Fx p = fx_table(TBL(fx_invfact)[8]);
 #pragma unroll 1
     for (int n = 7; n >= 0; n--) {
-        p = fx_mul(p, u);
+        p = fx_mul_u(p, u, n);
         Fx cn = fx_table(TBL(fx_invfact)[n]);
         w_add(p, cn);
     }
@@ -331,8 +359,53 @@ PB_HDNI Dec dec_pow_fx(const Dec& x, const Fx& y, int yneg, int prec, bool* ok) 
     *ok = ok1 && ok2 && ok3 && ok4;
     return r;
 }
+// ln of a = round28(V) given V = exp(T) in full precision:  ln a = T + log1p((a - V)/V).
+// |(a-V)/V| <= 5e-29, so log1p is its argument to 2^-187 and 1/V is only needed to ~100 bits
+// (one Newton step from a double seed).  Saves a full ln (one exp) per use.
+PB_HDNI SFx fx_ln_of_rounded(const Dec& a, const Fx& V, const SFx& T, bool* ok) {
+    bool o1;
+    Fx Af = fx_from_dec(a, &o1);
+    *ok = o1;
+    Fx d;
+    int dneg;
+    if (w_cmp(Af, V) >= 0) {
+        d = Af;
+        w_sub(d, V);
+        dneg = 0;
+    } else {
+        d = V;
+        w_sub(d, Af);
+        dneg = 1;
+    }
+    // r ~ 1/V : r0 from double, r1 = r0 * (2 - V*r0)
+    Fx r0 = fx_from_double(1.0 / fx_to_double(V));
+    Fx t = fx_mul(V, r0);
+    Fx two;
+    w_zero(two);
+    two.w[6] = 2;
+    w_sub(two, t);
+    Fx r1 = fx_mul(r0, two);
+    Fx delta = fx_mul(d, r1);
+    // L = T + delta (signed)
+    SFx L;
+    if (T.neg == dneg) {
+        L.m = T.m;
+        w_add(L.m, delta);
+        L.neg = T.neg;
+    } else if (w_cmp(T.m, delta) >= 0) {
+        L.m = T.m;
+        w_sub(L.m, delta);
+        L.neg = T.neg;
+    } else {
+        L.m = delta;
+        w_sub(L.m, T.m);
+        L.neg = dneg;
+    }
+    return L;
+}
+
 // Same with ln(x) supplied (ORF scoring reuses ln(1-pstop) for three exponents)
-PB_HDNI Dec dec_pow_ln(const SFx& lnx, const Fx& y, int prec, bool* ok) {
+PB_HDNI Dec dec_pow_ln(const SFx& lnx, const Fx& y, int prec, bool* ok, SFx* Tout = 0, Fx* Vout = 0) {
     bool ok3, ok4;
     SFx T;
     T.m = fx_mul(lnx.m, y);
@@ -340,5 +413,7 @@ PB_HDNI Dec dec_pow_ln(const SFx& lnx, const Fx& y, int prec, bool* ok) {
     Fx V = fx_exp(T, &ok3);
     Dec r = fx_to_dec(V, prec, &ok4);
     *ok = ok3 && ok4;
+    if (Tout) *Tout = T;
+    if (Vout) *Vout = V;
     return r;
 }

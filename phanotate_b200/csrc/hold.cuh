@@ -55,19 +55,22 @@ PB_HDNI void holdfac_prepare(const Dec& b, HoldFac& f) {
     f.btop[1] = t.w[1];
 }
 
-// Stage 7a: pstop and the six factors of one ORF.  item = ORF id
-PB_HDN void st_orf_factors(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
+PB_HD int contig_of_orf(const Batch& B, i64 oi) {
     int lo = 0, hi = B.nc;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (B.corf[mid] <= oi) lo = mid;
         else hi = mid;
     }
-    const int c = lo;
-    CStat* cs = B.cs + c;
+    return lo;
+}
+// Stage 7a (split into small kernels: each keeps its instruction working set inside the I-cache).
+// S1: base composition -> pstop, x = 1 - pstop.  item = ORF
+PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    const int c = contig_of_orf(B, oi);
     const u8* s = B.seq + B.coff[c];
-    const int L = cs->L;
+    const int L = B.cs[c].L;
     const int start = B.o_start[oi], stop = B.o_stop[oi];
     const bool rev = B.o_frame[oi] < 0;
     int x0 = rev ? stop - 1 : start - 1, x1 = rev ? start + 2 : stop + 2;   // extent of orf.seq (functions.py:206,219,234,246)
@@ -88,56 +91,81 @@ PB_HDN void st_orf_factors(const Batch& B, i64 oi) {
     Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);
     Dec pstop = pstop_formula(Pa, Pt, Pg);
     B.o_pstop[oi] = pstop;
-    Dec x = dec_sub(dec_one(), pstop);
-    bool okall = true;
-    const bool xone = dec_is_one_abs(x);
+    B.o_x[oi] = dec_sub(dec_one(), pstop);
+}
+// S2: ln(1 - pstop).  item = ORF
+PB_HDN void st_orf_lnx(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    const Dec x = B.o_x[oi];
     SFx lnx;
     w_zero(lnx.m);
     lnx.neg = 0;
-    if (!xone) {
+    if (!dec_is_one_abs(x)) {
         bool o1, o2;
         Fx X = fx_from_dec(x, &o1);
         lnx = fx_ln(X, &o2);
-        okall = okall && o1 && o2;
+        if (!(o1 && o2)) PB_ATOMIC_OR(&B.cs[contig_of_orf(B, oi)].err, (u32)ERR_RANGE);
     }
+    B.o_lnx[oi] = lnx;
+}
+// S3: A_im = x ** pos_max[im] and ln(A_im).  item = ORF*3 + (im-1)
+PB_HDN void st_orf_powA(const Batch& B, i64 item) {
+    const i64 oi = item / 3;
+    if (oi >= B.no) return;
+    const int im = (int)(item % 3) + 1;
+    const int c = contig_of_orf(B, oi);
+    const CStat* cs = B.cs + c;
+    const Dec x = B.o_x[oi];
+    const bool xone = dec_is_one_abs(x);
+    Dec A;
+    SFx lnA = B.o_lnx[oi];
+    bool ok = true;
+    if (cs->max_one[im]) {
+        A = x;                                                        // x ** Decimal(1) == x
+    } else if (xone) {
+        A = dec_pow_fx(x, cs->fmax[im], 0, PB_PREC, &ok);             // 1.000...0 (_qcheck_pow_one)
+    } else {
+        SFx T;
+        Fx V;
+        bool o2;
+        A = dec_pow_ln(lnA, cs->fmax[im], PB_PREC, &ok, &T, &V);
+        lnA = fx_ln_of_rounded(A, V, T, &o2);
+        ok = ok && o2;
+    }
+    if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
+    B.o_A[item] = A;
+    B.o_lnA[item] = lnA;
+}
+// S4: F_k = A_im ** pos_min[il].  item = ORF*6 + k
+PB_HDN void st_orf_powF(const Batch& B, i64 item) {
+    const i64 oi = item / 6;
+    if (oi >= B.no) return;
+    const int k = (int)(item % 6);
+    const int im = k / 2 + 1;
+    const int il = (k % 2) + 1 + (((k % 2) + 1 >= im) ? 1 : 0);      // inverse of fac_index
+    const int c = contig_of_orf(B, oi);
+    const CStat* cs = B.cs + c;
+    const Dec A = B.o_A[oi * 3 + (im - 1)];
+    Dec f;
+    bool ok = true;
+    if (cs->min_one[il]) f = A;
+    else if (dec_is_one_abs(A)) f = dec_pow_fx(A, cs->fmin[il], 0, PB_PREC, &ok);
+    else f = dec_pow_ln(B.o_lnA[oi * 3 + (im - 1)], cs->fmin[il], PB_PREC, &ok);
+    if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
+    B.o_fac[item] = f;
+}
+// S5: prepared factors, length bin, histogram for the counting sort.  item = ORF
+PB_HDN void st_orf_prepare(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
     u32 allok = 1;
-    for (int im = 1; im <= 3; im++) {
-        Dec A;
-        bool o = true;
-        if (cs->max_one[im]) A = x;                                   // x ** Decimal(1) == x
-        else if (xone) A = dec_pow_fx(x, cs->fmax[im], 0, PB_PREC, &o);
-        else A = dec_pow_ln(lnx, cs->fmax[im], PB_PREC, &o);
-        okall = okall && o;
-        SFx lnA;
-        bool haveL = false;
-        const bool aone = dec_is_one_abs(A);
-        for (int il = 1; il <= 3; il++) {
-            if (il == im) continue;
-            Dec f;
-            bool o2 = true;
-            if (cs->min_one[il]) f = A;
-            else if (aone) f = dec_pow_fx(A, cs->fmin[il], 0, PB_PREC, &o2);
-            else {
-                if (!haveL) {
-                    bool q1, q2;
-                    Fx XA = fx_from_dec(A, &q1);
-                    lnA = fx_ln(XA, &q2);
-                    okall = okall && q1 && q2;
-                    haveL = true;
-                }
-                f = dec_pow_ln(lnA, cs->fmin[il], PB_PREC, &o2);
-            }
-            okall = okall && o2;
-            const int k = fac_index(im, il);
-            B.o_fac[oi * 6 + k] = f;
-            HoldFac hf;
-            holdfac_prepare(f, hf);
-            allok &= hf.ok;
-            B.o_hf[oi * 6 + k] = hf;
-        }
+    for (int k = 0; k < 6; k++) {
+        HoldFac hf;
+        holdfac_prepare(B.o_fac[oi * 6 + k], hf);
+        allok &= hf.ok;
+        B.o_hf[oi * 6 + k] = hf;
     }
-    if (!okall) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
-    int n = orf_steps(start, stop, rev);
+    const bool rev = B.o_frame[oi] < 0;
+    int n = orf_steps(B.o_start[oi], B.o_stop[oi], rev);
     int bin = n < HOLD_BINS - 1 ? n : HOLD_BINS - 1;
     B.o_bin[oi] = (unsigned short)(bin | (allok ? 0x8000 : 0));
     PB_ATOMIC_ADD(&B.len_hist[HOLD_BINS - 1 - bin], 1u);              // reversed: longest ORFs first

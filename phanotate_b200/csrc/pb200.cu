@@ -46,7 +46,11 @@ PB_KERNEL(st_count64)
 PB_KERNEL(st_contig_offsets)
 PB_KERNEL(st_node_pos)
 PB_KERNEL(st_fill)
-PB_KERNEL(st_orf_factors)
+PB_KERNEL(st_orf_pstop)
+PB_KERNEL(st_orf_lnx)
+PB_KERNEL(st_orf_powA)
+PB_KERNEL(st_orf_powF)
+PB_KERNEL(st_orf_prepare)
 PB_KERNEL(st_len_scatter)
 PB_KERNEL(st_ov_weight)
 PB_KERNEL(st_contig_stats)

@@ -139,6 +139,10 @@ struct Batch {
     EdgeRec* edges;
     // node-parallel fill / ORF scoring split
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
+    Dec* o_x;             // [no] 1 - pstop
+    SFx* o_lnx;           // [no] ln(1 - pstop), Q32.192
+    Dec* o_A;             // [no*3] x ** pos_max[im]
+    SFx* o_lnA;           // [no*3]
     Dec* o_fac;           // [no*6] the six GC-frame factors of every ORF
     struct HoldFac* o_hf; // [no*6] the same, prepared for the fast multiply
     unsigned short* o_bin;   // [no] codon count bin | 0x8000 if the fast path applies

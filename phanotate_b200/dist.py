@@ -48,4 +48,4 @@ class DeviceCalls:
 
     def __init__(self, ptr: int, n_rows: int):
         self.__cuda_array_interface__ = {"shape": (max(n_rows, 1) * N.CALL.itemsize,), "typestr": "|u1",
-                                         "data": (int(ptr), True), "version": 2}
+                                         "data": (int(ptr), False), "version": 2}

@@ -100,6 +100,45 @@ void t_to_double(int n, const TDec* a, double* o, int* okv) {
         okv[i] = ok;
     }
 }
+// raw fixed-point exp / ln for accuracy measurements: in/out are 7 little-endian u32 limbs (Q32.192)
+void t_fx_exp(int n, const u32* t_limbs, const int* neg, u32* out_limbs, int* okv) {
+    for (int i = 0; i < n; i++) {
+        SFx T;
+        for (int j = 0; j < 7; j++) T.m.w[j] = t_limbs[i * 7 + j];
+        T.neg = neg[i];
+        bool ok;
+        Fx v = fx_exp(T, &ok);
+        okv[i] = ok;
+        for (int j = 0; j < 7; j++) out_limbs[i * 7 + j] = v.w[j];
+    }
+}
+void t_fx_ln(int n, const u32* x_limbs, u32* out_limbs, int* out_neg, int* okv) {
+    for (int i = 0; i < n; i++) {
+        Fx X;
+        for (int j = 0; j < 7; j++) X.w[j] = x_limbs[i * 7 + j];
+        bool ok;
+        SFx L = fx_ln(X, &ok);
+        okv[i] = ok;
+        out_neg[i] = L.neg;
+        for (int j = 0; j < 7; j++) out_limbs[i * 7 + j] = L.m.w[j];
+    }
+}
+// V = exp(-t); a = round28(V); returns a and ln(a) via the shortcut fx_ln_of_rounded
+void t_ln_rounded(int n, const u32* t_limbs, TDec* a_out, u32* ln_limbs, int* ln_neg, int* okv) {
+    for (int i = 0; i < n; i++) {
+        SFx T;
+        for (int j = 0; j < 7; j++) T.m.w[j] = t_limbs[i * 7 + j];
+        T.neg = 1;
+        bool o1, o2, o3;
+        Fx V = fx_exp(T, &o1);
+        Dec a = fx_to_dec(V, 28, &o2);
+        SFx L = fx_ln_of_rounded(a, V, T, &o3);
+        okv[i] = o1 && o2 && o3;
+        a_out[i] = out(a);
+        ln_neg[i] = L.neg;
+        for (int j = 0; j < 7; j++) ln_limbs[i * 7 + j] = L.m.w[j];
+    }
+}
 void t_milli(int n, const TDec* a, u32* mag /* n x 8 */, int* okv) {
     for (int i = 0; i < n; i++) {
         Wide<8> m;

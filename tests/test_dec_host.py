@@ -249,3 +249,78 @@ def test_dec_to_double_is_float_of_decimal(lib):
         if k:
             assert float(x) == g and str(float(x)) == str(g), (x, float(x), g)
     assert ok.mean() > 0.9
+
+
+def _limbs(v):
+    return [(v >> (32 * j)) & 0xFFFFFFFF for j in range(7)]
+
+
+def _unlimbs(a):
+    return sum(int(x) << (32 * j) for j, x in enumerate(a))
+
+
+def test_fixed_point_exp_ln_absolute_accuracy(lib):
+    """exp and ln in Q32.192 must be good to ~2^-180 absolute: the single rounding to 28 digits that follows
+    (csrc/fxpow.cuh) is then wrong only if exp(y ln x) lies within 1e-50 of a rounding boundary."""
+    rng = random.Random(21)
+    with localcontext() as ctx:
+        ctx.prec = 90
+        ONE = 1 << 192
+        ts, negs = [], []
+        for _ in range(3000):
+            mag = rng.choice([1e-20, 1e-9, 1e-4, 0.01, 0.2, 0.7, 3.0, 17.0])
+            t = int(Decimal(rng.random() * mag) * ONE)
+            ts.append(t)
+            negs.append(1 if (mag > 1 or rng.random() < 0.8) else 0)
+        tl = np.array([_limbs(t) for t in ts], dtype=np.uint32)
+        ng = np.array(negs, dtype=np.int32)
+        out = np.zeros_like(tl)
+        ok = np.zeros(len(ts), dtype=np.int32)
+        lib.t_fx_exp(len(ts), P(tl), P(ng), P(out), P(ok))
+        assert ok.all()
+        worst = 0
+        for t, s, o in zip(ts, negs, out):
+            x = Decimal(t) / ONE
+            want = (-x if s else x).exp() * ONE
+            worst = max(worst, abs(Decimal(_unlimbs(o)) - want) / max(Decimal(1), want / ONE))
+        print("exp worst", float(worst))
+        assert worst < 2 ** 12, worst            # error below 2^-180 relative to max(1, value)
+        xs = []
+        for _ in range(3000):
+            kind = rng.random()
+            x = 1 - rng.random() * rng.choice([1e-12, 1e-6, 0.01, 0.15]) if kind < 0.7 else rng.uniform(0.05, 1.9)
+            xs.append(int(Decimal(x) * ONE))
+        xl = np.array([_limbs(x) for x in xs], dtype=np.uint32)
+        out = np.zeros_like(xl)
+        neg = np.zeros(len(xs), dtype=np.int32)
+        lib.t_fx_ln(len(xs), P(xl), P(out), P(neg), P(ok))
+        assert ok.all()
+        worst = 0
+        for x, s, o in zip(xs, neg, out):
+            want = (Decimal(x) / ONE).ln() * ONE
+            got = Decimal(_unlimbs(o)) * (-1 if s else 1)
+            worst = max(worst, abs(got - want))
+        assert worst < 2 ** 12, worst
+
+
+def test_ln_of_rounded_power_shortcut(lib):
+    """ln(round28(exp(T))) = T + (a-V)/V must match the true ln(a) to ~2^-180 (csrc/fxpow.cuh)."""
+    rng = random.Random(22)
+    with localcontext() as ctx:
+        ctx.prec = 90
+        ONE = 1 << 192
+        ts = [int(Decimal(rng.random() * rng.choice([1e-12, 1e-6, 1e-3, 0.05, 0.17])) * ONE) for _ in range(3000)]
+        tl = np.array([_limbs(t) for t in ts], dtype=np.uint32)
+        a = np.zeros(len(ts), dtype=TDEC)
+        out = np.zeros_like(tl)
+        neg = np.zeros(len(ts), dtype=np.int32)
+        ok = np.zeros(len(ts), dtype=np.int32)
+        lib.t_ln_rounded(len(ts), P(tl), P(a), P(out), P(neg), P(ok))
+        assert ok.all()
+        worst = 0
+        for av, s, o in zip(unpack(a), neg, out):
+            want = av.ln() * ONE
+            got = Decimal(_unlimbs(o)) * (-1 if s else 1)
+            worst = max(worst, abs(got - want))
+        print("ln-of-rounded worst", float(worst))
+        assert worst < 2 ** 12, worst
