@@ -123,93 +123,121 @@ PB_HDN void st_ov_count(const Batch& B, i64 ni) {
 PB_HDN void st_ov_fill(const Batch& B, i64 ni) {
     if (ni < B.nn) overlaps_of(B, (i32)ni, true);
 }
-// Stage 10b: weight of one overlap edge (a 33-digit integer power each).  item = overlap edge
-PB_HDN void st_ov_weight(const Batch& B, i64 k) {
+// Stage 10b-d: weight of one overlap edge in three small kernels (instruction-cache footprint):
+//   pbar:   o = 1 - ave([o1,o2])                     (functions.py:140-141,386; 26-27)
+//   pow:    o ** Decimal(r-l+3), a 33-digit square-and-multiply (functions.py:30)
+//   weight: 1/score (+ 1/0.05 if 'diff'), integer weight (functions.py:31-34)
+// item = overlap edge
+PB_HDN void st_ov_pbar(const Batch& B, i64 k) {
     if (k >= B.nov) return;
     const i32 x = B.ov_src[k], e = B.ov_dst[k];
     const int c = contig_of_node(B, x);
-    Dec w = overlap_score(B, c, e, x, B.ov_diff[k] != 0);
-    B.ov_w[k] = w;
+    Dec t = dec_add(dec_from_u64(0), node_o(B, c, e));
+    t = dec_add(t, node_o(B, c, x));
+    Dec pbar = dec_div(t, dec_from_u64(2));
+    B.ov_w[k] = dec_sub(dec_one(), pbar);
+}
+PB_HDN void st_ov_pow(const Batch& B, i64 k) {
+    if (k >= B.nov) return;
+    const i32 x = B.ov_src[k], e = B.ov_dst[k];
+    B.ov_w[k] = dec_powi(B.ov_w[k], (u32)(B.n_pos[x] - B.n_pos[e] + 3));
+}
+PB_HDN void st_ov_weight(const Batch& B, i64 k) {
+    if (k >= B.nov) return;
+    const int c = contig_of_node(B, B.ov_src[k]);
+    Dec sc = dec_div(dec_one(), B.ov_w[k]);
+    if (B.ov_diff[k]) sc = dec_add(sc, dec_twenty());
+    B.ov_w[k] = sc;
     WInt wi;
-    if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+    if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
     B.ov_wint[k] = wi;
 }
 
-// Stage 11: bridges over uncovered runs longer than 500 bp (functions.py:320-354).  item = contig
-PB_HDN void bridges_of(const Batch& B, int c, bool fill) {
+// Stage 11: bridges over uncovered runs longer than 500 bp (functions.py:320-354).
+// Coverage = union over families of [min(start,stop), min(max(start,stop), L-1)) of the longest ORF.
+// Interval starts are entry nodes (a reverse stop-key node, or the farthest start of a forward
+// family), already sorted by position, so "last covered base before node i" is an exclusive prefix
+// maximum over the node list: one warp per contig computes it (reach_contig), then every interval
+// start that begins more than 500 bp after it enumerates its bridging pairs (item = node).
+PB_HD bool bridge_interval(const Batch& B, i32 i, int L, int& mi, int& me) {
+    const int kind = B.n_kind[i] & 3;
+    if (kind == K_RSTOP || (kind == K_FSTART && B.n_mate[B.n_mate[i]] == i)) {
+        mi = B.n_pos[i];
+        int ma = B.n_pos[B.n_mate[i]];
+        me = ma < L - 1 ? ma : L - 1;           // covered: mi .. me-1
+        return me > mi;
+    }
+    return false;
+}
+PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    const int L = B.cs[c].L;
+    int run = 0;
+    for (i32 base = nb; base < ne; base += NL) {
+        const i32 i = base + lane;
+        int v = 0, mi, me;
+        if (i < ne && bridge_interval(B, i, L, mi, me)) v = me - 1;
+        int incl = v;
+#ifdef __CUDA_ARCH__
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o && t > incl) incl = t;
+        }
+        int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) prev = 0;
+        int excl = prev > run ? prev : run;
+        int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#else
+        int excl = run, tot = incl;
+#endif
+        if (i < ne) B.n_reach[i] = excl;
+        if (tot > run) run = tot;
+    }
+}
+PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
+    const int c = contig_of_node(B, i);
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
     const int L = B.cs[c].L;
     u32 cnt = 0;
-    u32 k = fill ? B.br_cnt[c] : 0;
-    int last = 0;
-    for (i32 i = nb; i < ne; i++) {
-        const int kind = B.n_kind[i] & 3;
-        int mi, ma;
-        if (kind == K_RSTOP) {
-            mi = B.n_pos[i];
-            ma = B.n_pos[B.n_mate[i]];
-        } else if (kind == K_FSTART && B.n_mate[B.n_mate[i]] == i) {   // the longest ORF of its family
-            mi = B.n_pos[i];
-            ma = B.n_pos[B.n_mate[i]];
-        } else continue;
-        int me = ma < L - 1 ? ma : L - 1;       // covered: mi .. me-1
-        if (me <= mi) continue;
-        if (mi > last && mi - last > 500) {
-            const int base = mi;
-            // left: exits with last-500 < l <= last+1 ; right: entries with base-1 <= r < base+500
-            for (i32 r = i; r < ne && B.n_pos[r] < base + 500; r++) {
-                if (B.n_pos[r] < base - 1 || !kind_is_entry(B.n_kind[r] & 3)) continue;
-                for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
-                    if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
-                    int len = B.n_pos[r] - B.n_pos[l] - 3;
-                    if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
-                    if (fill) {
-                        Dec w = gap_score(B, c, len, false);
-                        B.br_src[k] = l;
-                        B.br_dst[k] = r;
-                        B.br_w[k] = w;
-                        WInt wi;
-                        if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
-                        B.br_wint[k] = wi;
-                        k++;
-                    }
-                    cnt++;
+    u32 k = fill ? B.br_cnt[i] : 0;
+    int mi, me;
+    const int last = B.n_reach[i];
+    if (bridge_interval(B, i, L, mi, me) && mi > last && mi - last > 500) {
+        const int base = mi;
+        // left: exits with last-500 < l <= last+1 ; right: entries with base-1 <= r < base+500
+        i32 r0 = i;
+        while (r0 > nb && B.n_pos[r0 - 1] >= base - 1) r0--;          // same-position twins sort before i
+        for (i32 r = r0; r < ne && B.n_pos[r] < base + 500; r++) {
+            if (B.n_pos[r] < base - 1 || !kind_is_entry(B.n_kind[r] & 3)) continue;
+            for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
+                if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
+                int len = B.n_pos[r] - B.n_pos[l] - 3;
+                if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
+                if (fill) {
+                    Dec w = gap_score(B, c, len, false);
+                    B.br_src[k] = l;
+                    B.br_dst[k] = r;
+                    B.br_w[k] = w;
+                    WInt wi;
+                    if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+                    B.br_wint[k] = wi;
+                    k++;
                 }
-            }
-            // entries to the right may sit before index i (same position twins): scan back over equal positions
-            for (i32 r = i - 1; r >= nb && B.n_pos[r] >= base - 1; r--) {
-                if (!kind_is_entry(B.n_kind[r] & 3)) continue;
-                for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
-                    if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
-                    int len = B.n_pos[r] - B.n_pos[l] - 3;
-                    if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
-                    if (fill) {
-                        Dec w = gap_score(B, c, len, false);
-                        B.br_src[k] = l;
-                        B.br_dst[k] = r;
-                        B.br_w[k] = w;
-                        WInt wi;
-                        if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
-                        B.br_wint[k] = wi;
-                        k++;
-                    }
-                    cnt++;
-                }
+                cnt++;
             }
         }
-        if (me - 1 > last) last = me - 1;
     }
-    if (!fill) B.br_cnt[c] = cnt;
+    if (!fill) B.br_cnt[i] = cnt;
 }
-PB_HDN void st_br_count(const Batch& B, i64 c) {
-    if (c < B.nc) bridges_of(B, (int)c, false);
+PB_HDN void st_br_count(const Batch& B, i64 i) {
+    if (i < B.nn) bridges_of(B, (i32)i, false);
 }
-PB_HDN void st_br_fill(const Batch& B, i64 c) {
-    if (c < B.nc) bridges_of(B, (int)c, true);
+PB_HDN void st_br_fill(const Batch& B, i64 i) {
+    if (i < B.nn) bridges_of(B, (i32)i, true);
 }
 
 // integer weight of score_gap(len,'same'|'diff') as the solver sees it
-PB_HDN WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok) {
+PB_HD WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok, bool generic = false) {
     *ok = true;
     if (len <= 300) {
         i64 k = (i64)c * GAPN + (len + 2);
@@ -217,6 +245,10 @@ PB_HDN WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok) {
     }
     if (len <= 999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi3);
     if (len <= 9999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi4);
+    if (!generic) {          // the solver only sees len < 500 (connect) and len <= 2000 (terminals)
+        *ok = false;
+        return wint_from_i64(0);
+    }
     WInt w;
     *ok = dec_to_wint(gap_score(B, c, len, diff), w);
     return w;
@@ -278,7 +310,7 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
         }
     }
     PB_SYNCWARP();
-    const u32 brb = B.br_cnt[c], bre = B.br_cnt[c + 1];
+    const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
     i32 i = nb;
     i64 budget = 64 * (i64)(ne - nb) + 1024;
     while (i < ne) {
@@ -419,26 +451,29 @@ PB_HDN void st_backtrack(const Batch& B, i64 c64) {
     B.call_cnt[c] = (u32)n;
     cs->n_calls = n;
 }
-// call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them
-PB_HDN void st_gather_calls(const Batch& B, i64 c) {
-    if (c >= B.nc) return;
-    const i32* src = B.call_tmp + B.corf[c];
-    u32 o = B.call_cnt[c], n = B.call_cnt[c + 1] - o;
-    for (u32 k = 0; k < n; k++) {
-        const i32 orf = src[k];
-        B.call_orf[o + k] = orf;
-        CallRec r;
-        const bool rev = B.o_frame[orf] < 0;
-        r.contig = (i32)c;
-        r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
-        r.right = (rev ? B.o_start[orf] : B.o_stop[orf]) + 2;     // right = exit node position + 2
-        r.strand = rev ? -1 : 1;
-        r.weight = B.o_weight[orf];
-        bool ok;
-        r.score = dec_to_double(r.weight, &ok);
-        if (!ok) B.cs[c].err |= ERR_RANGE;
-        B.calls[o + k] = r;
+// call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them.  item = call
+PB_HDN void st_gather_calls(const Batch& B, i64 k) {
+    if (k >= B.ncalls) return;
+    int lo = 0, hi = B.nc;                 // contig of call k: call_cnt[lo] <= k < call_cnt[lo+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((i64)B.call_cnt[mid] <= k) lo = mid;
+        else hi = mid;
     }
+    const int c = lo;
+    const i32 orf = B.call_tmp[B.corf[c] + (k - B.call_cnt[c])];
+    B.call_orf[k] = orf;
+    CallRec r;
+    const bool rev = B.o_frame[orf] < 0;
+    r.contig = (i32)c;
+    r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
+    r.right = (rev ? B.o_start[orf] : B.o_stop[orf]) + 2;     // right = exit node position + 2
+    r.strand = rev ? -1 : 1;
+    r.weight = B.o_weight[orf];
+    bool ok;
+    r.score = dec_to_double(r.weight, &ok);
+    if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
+    B.calls[k] = r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,7 +519,7 @@ PB_HDN void edges_of(const Batch& B, i32 u, bool fill) {
             EMIT(u, j, EK_GAP, gap_score(B, c, d - 3, diff));
         }
         for (u32 k = B.ov_cnt[u]; k < B.ov_cnt[u + 1]; k++) EMIT(u, B.ov_dst[k], EK_OVERLAP, B.ov_w[k]);
-        for (u32 k = B.br_cnt[c]; k < B.br_cnt[c + 1]; k++)
+        for (u32 k = B.br_cnt[B.cnode[c]]; k < B.br_cnt[ne]; k++)
             if (B.br_src[k] == u) EMIT(u, B.br_dst[k], EK_BRIDGE, B.br_w[k]);
         if (L - pu <= 2000) EMIT(u, -3, EK_TARGET, gap_score(B, c, L - pu, false));
     }

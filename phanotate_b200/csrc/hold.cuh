@@ -251,14 +251,7 @@ PB_HD bool hold_step_fast(u32& a0, u32& a1, u32& a2, i32& eh, const U4& c27, con
 // Stage 7b+c: the per-codon product and Orf.score() of ORF oi.  S holds this ORF's six HoldFac as
 // 18 U4 words with stride BD (shared memory on the GPU: S[(k*3+v)*BD + t]).
 PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (B.corf[mid] <= oi) lo = mid;
-        else hi = mid;
-    }
-    const int c = lo;
-    CStat* cs = B.cs + c;
+    const int c = contig_of_orf(B, oi);
     const u8* meta = B.meta + B.coff[c];
     const int start = B.o_start[oi], stop = B.o_stop[oi];
     const bool rev = B.o_frame[oi] < 0;
@@ -313,8 +306,14 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
         hold.e = eh;
         hold.neg = 0;
     }
-    // Orf.score (orfs.py:122-127)
-    Dec sc = dec_div(dec_one(), hold);
+    B.o_hold[oi] = hold;
+}
+// Stage 7c: Orf.score (orfs.py:122-127): weight = -(1/hold * start-codon weight * Decimal(str(weight_rbs))).  item = ORF
+PB_HDN void st_orf_finish(const Batch& B, i64 oi) {
+    if (oi >= B.no) return;
+    const int c = contig_of_orf(B, oi);
+    CStat* cs = B.cs + c;
+    Dec sc = dec_div(dec_one(), B.o_hold[oi]);
     int sw = B.o_sw[oi];
     if (sw >= 0) sc = dec_mul(sc, B.P.startw[sw]);
     sc = dec_mul(sc, cs->wrbs[B.o_rbs[oi]]);

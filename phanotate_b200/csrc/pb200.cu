@@ -51,6 +51,9 @@ PB_KERNEL(st_orf_lnx)
 PB_KERNEL(st_orf_powA)
 PB_KERNEL(st_orf_powF)
 PB_KERNEL(st_orf_prepare)
+PB_KERNEL(st_orf_finish)
+PB_KERNEL(st_ov_pbar)
+PB_KERNEL(st_ov_pow)
 PB_KERNEL(st_len_scatter)
 PB_KERNEL(st_ov_weight)
 PB_KERNEL(st_contig_stats)
@@ -84,6 +87,12 @@ __global__ void __launch_bounds__(PB_BLOCK) k_hold(const Batch B) {
         for (int j = 0; j < 18; j++) S[j * PB_BLOCK + t] = src[j];
         hold_run(B, oi, S, PB_BLOCK, t);
     }
+}
+__global__ void __launch_bounds__(PB_BLOCK) k_reach(const Batch B, i32 nc) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 c = warp; c < nc; c += nwarps) reach_contig(B, (int)c, lane, 32);
 }
 __global__ void k_pack_orfs(const Batch B, OrfRec* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.no; i += (i64)gridDim.x * blockDim.x) pack_orf(B, i, out);
@@ -275,6 +284,19 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         ctx->launches++;                                                                         \
         CK(cudaGetLastError());                                                                  \
     } while (0)
+#define PB_RUN_REACH(nc_)                                                                        \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = "reach";                                                                       \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        k_reach<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        cudaEventRecord(t_.b, ctx->stream);                                                      \
+        ctx->times.push_back(t_);                                                                \
+        ctx->launches++;                                                                         \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
 #define PB_RUN_HOLD(no_)                                                                         \
     do {                                                                                         \
         if ((no_) > 0) {                                                                         \
@@ -365,6 +387,11 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
     do {                                                               \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
         ctx->launches++;                                               \
+    } while (0)
+#define PB_RUN_REACH(nc_)                                                  \
+    do {                                                                   \
+        for (i32 c_ = 0; c_ < (nc_); c_++) reach_contig(B, c_, 0, 1);      \
+        ctx->launches++;                                                   \
     } while (0)
 #define PB_RUN_HOLD(no_)                                                   \
     do {                                                                   \

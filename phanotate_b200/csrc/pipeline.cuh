@@ -117,7 +117,8 @@ struct Batch {
     i32* ov_dst;
     Dec* ov_w;
     WInt* ov_wint;
-    u32* br_cnt;          // [nc+1]
+    u32* br_cnt;          // [nn+1] bridges starting at an interval-start node, then offsets
+    i32* n_reach;         // [nn] last covered base before the node
     i32* br_src;
     i32* br_dst;
     Dec* br_w;
@@ -139,6 +140,7 @@ struct Batch {
     EdgeRec* edges;
     // node-parallel fill / ORF scoring split
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
+    Dec* o_hold;          // [no] product over the codons (functions.py:286-298)
     Dec* o_x;             // [no] 1 - pstop
     SFx* o_lnx;           // [no] ln(1 - pstop), Q32.192
     Dec* o_A;             // [no*3] x ** pos_max[im]
