@@ -69,8 +69,9 @@ PB_HDNI Fx fx_mul(const Fx& a, const Fx& b) { return fx_mul_cols<4, 6>(a, b); }
 // still goes through, which relaxes the absolute accuracy needed here by 2^(24*rest)
 PB_HDNI Fx fx_mul_u(const Fx& p, const Fx& u, int rest) {
     // three variants only: instruction-cache footprint matters more than the last few skipped columns
-    if (rest <= 1) return fx_mul_cols<4, 5>(p, u);
-    if (rest <= 4) return fx_mul_cols<7, 5>(p, u);
+    // admissible cut per `rest` (0..7): 4,5,6,7,7,8,9,10
+    if (rest <= 2) return fx_mul_cols<4, 5>(p, u);
+    if (rest <= 5) return fx_mul_cols<7, 5>(p, u);
     return fx_mul_cols<9, 5>(p, u);
 }
 PB_HD double fx_to_double(const Fx& a) {
