@@ -69,23 +69,23 @@ PB_HD int contig_of_orf(const Batch& B, i64 oi) {
 PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
     if (oi >= B.no) return;
     const int c = contig_of_orf(B, oi);
-    const u8* s = B.seq + B.coff[c];
     const int L = B.cs[c].L;
     const int start = B.o_start[oi], stop = B.o_stop[oi];
     const bool rev = B.o_frame[oi] < 0;
     int x0 = rev ? stop - 1 : start - 1, x1 = rev ? start + 2 : stop + 2;   // extent of orf.seq (functions.py:206,219,234,246)
     if (x0 < 0) x0 = 0;
     if (x1 > L) x1 = L;
-    u32 cnt[4] = {0, 0, 0, 0};
-    for (int q = x0; q < x1; q++) {
-        int cd = base_code(lower(s[q]));
-        if (cd < 4) cnt[cd]++;
-    }
-    u32 na = cnt[0], nt = cnt[3], ng = cnt[2];
-    if (rev) {
-        na = cnt[3];
-        nt = cnt[0];
-        ng = cnt[1];
+    // letters of the ORF's own strand-oriented sequence (orfs.py:162-168): popcounts over the base masks
+    const i64 cb = B.coff[c];
+    u32 na, nt, ng;
+    if (!rev) {
+        na = count_bits(B.bA, cb + x0, cb + x1);
+        nt = count_bits(B.bT, cb + x0, cb + x1);
+        ng = count_bits(B.bG, cb + x0, cb + x1);
+    } else {
+        na = count_bits(B.bT, cb + x0, cb + x1);
+        nt = count_bits(B.bA, cb + x0, cb + x1);
+        ng = count_bits(B.bC, cb + x0, cb + x1);
     }
     Dec len = dec_from_u64((u64)(x1 - x0));
     Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);

@@ -138,6 +138,15 @@ struct Batch {
     i32 nedges;
     u32* ed_cnt;          // [nn+1] out-degree (all edge kinds) then exclusive offsets
     EdgeRec* edges;
+    // bit masks over the concatenated batch, one bit per base (word = 64 bases): codon classes and raw letters
+    u64* mS;
+    u64* ms;
+    u64* mT;
+    u64* mt;
+    u64* bA;
+    u64* bC;
+    u64* bG;
+    u64* bT;
     // node-parallel fill / ORF scoring split
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
     Dec* o_hold;          // [no] product over the codons (functions.py:286-298)
@@ -264,7 +273,7 @@ PB_HD void gc_class(int code, bool rev, int& imax, int& imin) {
 // Stage 1: per-base scan (functions.py:158-171 + codon classes of :196-215 + gc_frame_plot.py)
 // item = strip of SCAN_STRIP consecutive bases of the concatenated batch
 #define SCAN_STRIP 32
-PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1, u8* meta) {
+PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1, u8* meta, int bitoff, u32* mk) {
     CStat* cs = B.cs + c;
     const int n = i1 - i0;
     // ---- window sums Tz(j) = sum_{k=-19..20} gc0(j+3k), j = i0 .. i1+1
@@ -323,6 +332,9 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
             cls = B.P.codon_cls[code[k] * 16 + code[k + 1] * 4 + code[k + 2]];
         int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
         meta[i] = (u8)(cls | (tr << 3));
+        const u32 bit = 1u << (bitoff + k);
+        if (cls) mk[cls - 1] |= bit;                 // S, s, T, t
+        if (code[k] < 4) mk[4 + code[k]] |= bit;     // a, c, g, t
         // RBS background, both strands
         int sf, sr;
         bool clean = (i + 21 <= L);
@@ -365,6 +377,8 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
     i64 gend = g + SCAN_STRIP;
     if (gend > B.nb) gend = B.nb;
     int c = contig_of(B, g);
+    u32 mk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const i64 g0 = g;
     while (g < gend) {
         while (B.coff[c + 1] <= g) c++;
         i64 cb = B.coff[c];
@@ -372,140 +386,20 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
         int i0 = (int)(g - cb);
         i64 e = gend - cb;
         int i1 = (e < L) ? (int)e : L;
-        scan_range(B, c, B.seq + cb, L, i0, i1, B.meta + cb);
+        scan_range(B, c, B.seq + cb, L, i0, i1, B.meta + cb, (int)(g - g0), mk);
         g = cb + i1;
     }
+    ((u32*)B.mS)[strip] = mk[0];
+    ((u32*)B.ms)[strip] = mk[1];
+    ((u32*)B.mT)[strip] = mk[2];
+    ((u32*)B.mt)[strip] = mk[3];
+    ((u32*)B.bA)[strip] = mk[4];
+    ((u32*)B.bC)[strip] = mk[5];
+    ((u32*)B.bG)[strip] = mk[6];
+    ((u32*)B.bT)[strip] = mk[7];
 }
 
-// ------------------------------------------------------------------------------------------------
-// Six-frame scan as independent walks (functions.py:184-251).  p is 1-based.
-struct CView {
-    const u8* s;
-    const u8* meta;
-    int L;
-};
-PB_HD int cls_at(const CView& v, int p) { return (p >= 1 && p <= v.L - 2) ? (v.meta[p - 1] & 7) : CLS_NONE; }
-PB_HD int frame_end(int L, int f) { return L - ((L - (f - 1)) % 3); }   // functions.py:231
-PB_HD int codon_index(const CView& v, int p) {                           // -1 if any letter is not acgt
-    if (p < 1 || p > v.L - 2) return -1;
-    int a = base_code(lower(v.s[p - 1])), b = base_code(lower(v.s[p])), c = base_code(lower(v.s[p + 1]));
-    if (a > 3 || b > 3 || c > 3) return -1;
-    return a * 16 + b * 4 + c;
-}
-PB_HD bool is_fwd_start(const CView& v, int p) { return cls_at(v, p) == CLS_S || p <= 3; }
-PB_HD bool is_rev_start(const Batch& B, const CView& v, int p, int f) {
-    if (cls_at(v, p) == CLS_s) return true;
-    if (p == frame_end(v.L, f) - 2) {
-        int ci = codon_index(v, p);
-        return ci < 0 || !B.P.rev_start[ci];
-    }
-    return false;
-}
-// forward ORF starting at p: stop key and length.  limit>0 bounds the walk (validity only).
-PB_HD void fwd_orf_of_start(const CView& v, int p, int f, int& key, int& length, int& trig) {
-    int endf = frame_end(v.L, f);
-    for (int q = p; q <= v.L - 2; q += 3) {
-        if (cls_at(v, q) == CLS_T) {
-            key = q;
-            length = q + 2 - p + 1;
-            trig = q;
-            return;
-        }
-    }
-    key = endf - 2;
-    length = endf - p + 1;
-    trig = v.L + 2 * f;
-}
-// reverse ORF whose start codon begins at p (pushed value p+2): stop key (previous rev stop or f)
-PB_HD void rev_orf_of_start(const CView& v, int p, int f, int& key, int& length) {
-    key = f;
-    for (int q = p; q >= f; q -= 3) {
-        if (cls_at(v, q) == CLS_t) {
-            key = q;
-            break;
-        }
-    }
-    length = p + 2 - key + 1;
-}
-// forward family keyed at p (a T codon, or the frame's last codon): farthest pending start
-PB_HD int fwd_family_farthest(const CView& v, int p, int f) {
-    int far = -1;
-    for (int q = p - 3; q >= f; q -= 3) {
-        int c = cls_at(v, q);
-        if (c == CLS_T) break;
-        if (c == CLS_S || q <= 3) far = q;
-    }
-    return far;
-}
-// reverse family keyed at p (a t codon or the frame's first codon): farthest member and trigger
-PB_HD int rev_family_farthest(const Batch& B, const CView& v, int p, int f, int& trig) {
-    int far = -1;
-    trig = v.L + 2 * f + 1;
-    for (int q = p + 3; q <= v.L - 2; q += 3) {
-        if (cls_at(v, q) == CLS_t) {
-            trig = q;
-            return far;
-        }
-        if (is_rev_start(B, v, q, f)) far = q;
-    }
-    return far;
-}
-
-// Stage 2: mark which positions carry a start node (bit0; bit2 = reverse strand) and / or a
-// stop-key node (bit1; bit3 = reverse strand).  item = base position of the batch.
-PB_HDN void st_mark(const Batch& B, i64 g) {
-    if (g >= B.nb) return;
-    int c = contig_of(B, g);
-    i64 cb = B.coff[c];
-    CView v;
-    v.s = B.seq + cb;
-    v.meta = B.meta + cb;
-    v.L = (int)(B.coff[c + 1] - cb);
-    int p = (int)(g - cb) + 1;
-    u8 flag = 0;
-    if (v.L >= 9 && p <= v.L - 2) {
-        int f = (p - 1) % 3 + 1;
-        int cls = cls_at(v, p);
-        const int minlen = B.P.min_orf_len;
-        int endf = frame_end(v.L, f);
-        int nstart = 0;
-        if (cls == CLS_S || p <= 3) {
-            int key, len, trig;
-            fwd_orf_of_start(v, p, f, key, len, trig);
-            if (len >= minlen) {
-                flag |= 1;
-                nstart++;
-            }
-        }
-        if (is_rev_start(B, v, p, f)) {
-            int key, len;
-            rev_orf_of_start(v, p, f, key, len);
-            if (len >= minlen) {
-                flag |= 1 | 4;
-                nstart++;
-            }
-        }
-        int nstop = 0;
-        if (cls == CLS_T || p == endf - 2) {
-            int far = fwd_family_farthest(v, p, f);
-            if (far > 0 && p + 2 - far + 1 >= minlen) {
-                flag |= 2;
-                nstop++;
-            }
-        }
-        if (cls == CLS_t || p <= 3) {
-            int trig;
-            int far = rev_family_farthest(B, v, p, f, trig);
-            if (far > 0 && far + 2 - p + 1 >= minlen) {
-                flag |= 2 | 8;
-                nstop++;
-            }
-        }
-        if (nstart > 1 || nstop > 1) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_INTERNAL);
-    }
-    B.nflag[g] = flag;
-}
-
+#include "enum_fwd.inc"
 // Stage 3: per 64-base block counts (nodes in the low word, ORFs = start nodes in the high word)
 PB_HDN void st_count64(const Batch& B, i64 blk) {
     i64 g0 = blk * 64, g1 = g0 + 64;
@@ -547,119 +441,4 @@ PB_HDN void st_contig_offsets(const Batch& B, i64 c) {
     }
 }
 
-// Stage 4a: global position of every node.  item = base position of the batch
-PB_HDN void st_node_pos(const Batch& B, i64 g) {
-    if (g >= B.nb) return;
-    u8 flag = B.nflag[g];
-    if (!flag) return;
-    if (flag & 1) B.n_gpos[node_index(B, g, 0)] = ((u64)g << 1);
-    if (flag & 2) B.n_gpos[node_index(B, g, 1)] = ((u64)g << 1) | 1u;
-}
-// Stage 4b: fill node and ORF records; RBS training histogram; GC-frame training counts.  item = node
-PB_HDN void st_fill(const Batch& B, i64 node) {
-    if (node >= B.nn) return;
-    const i64 g = (i64)(B.n_gpos[node] >> 1);
-    const u8 flag = (B.n_gpos[node] & 1) ? (u8)(B.nflag[g] & (2 | 8)) : (u8)(B.nflag[g] & (1 | 4));
-    int c = contig_of(B, g);
-    i64 cb = B.coff[c];
-    CView v;
-    v.s = B.seq + cb;
-    v.meta = B.meta + cb;
-    v.L = (int)(B.coff[c + 1] - cb);
-    CStat* cs = B.cs + c;
-    int p = (int)(g - cb) + 1;
-    int f = (p - 1) % 3 + 1;
-    if (flag & 1) {
-        i32 ni = (i32)node;
-        i32 oi = orf_index(B, g);
-        bool rev = (flag & 4) != 0;
-        int key, len, trig = 0, rbs, sw;
-        if (!rev) {
-            fwd_orf_of_start(v, p, f, key, len, trig);
-            rbs = (p >= 21) ? rbs_score_scalar(v.s, v.L, p - 21, false) : 0;      // dna[start-21:start], functions.py:208-209
-            int ci = codon_index(v, p);
-            sw = (ci >= 0) ? B.P.sw_fwd[ci] : -1;
-        } else {
-            rev_orf_of_start(v, p, f, key, len);
-            int P2 = p + 2;                                                       // dna[start:start+21], functions.py:221-222
-            rbs = (P2 < v.L) ? rbs_score_scalar(v.s, v.L, P2, true) : 0;
-            int ci = codon_index(v, p);
-            sw = (ci >= 0) ? B.P.sw_rev[ci] : -1;
-        }
-        PB_ATOMIC_ADD(&cs->hist_tr[rbs], 1u);
-        B.n_pos[ni] = p;
-        B.n_kind[ni] = (u8)((rev ? K_RSTART : K_FSTART) | (f << 2));
-        B.n_orf[ni] = oi;
-        B.n_mate[ni] = node_index(B, cb + key - 1, 1);
-        B.n_trig[ni] = 0;
-        B.o_start[oi] = p;
-        B.o_stop[oi] = key;
-        B.o_frame[oi] = (signed char)(rev ? -f : f);
-        B.o_rbs[oi] = (u8)rbs;
-        B.o_sw[oi] = (signed char)sw;
-        B.o_node[oi] = ni;
-    }
-    if (flag & 2) {
-        i32 ni = (i32)node;
-        bool rev = (flag & 8) != 0;
-        const int minlen = B.P.min_orf_len;
-        int far, trig;
-        int atg = -1;                    // farthest valid member whose start codon is literally 'atg' (functions.py:266)
-        if (!rev) {
-            far = -1;
-            trig = (cls_at(v, p) == CLS_T) ? p : v.L + 2 * f;
-            for (int q = p - 3; q >= f; q -= 3) {
-                int cq = cls_at(v, q);
-                if (cq == CLS_T) break;
-                if (cq == CLS_S || q <= 3) {
-                    far = q;
-                    if (p + 2 - q + 1 >= minlen && codon_index(v, q) == 14) atg = q;   // a,t,g = 0*16+3*4+2
-                }
-            }
-        } else {
-            far = -1;
-            trig = v.L + 2 * f + 1;
-            for (int q = p + 3; q <= v.L - 2; q += 3) {
-                if (cls_at(v, q) == CLS_t) {
-                    trig = q;
-                    break;
-                }
-                if (is_rev_start(B, v, q, f)) {
-                    far = q;
-                    if (q + 2 - p + 1 >= minlen && codon_index(v, q) == 19) atg = q;   // 'cat' = 1*16+0*4+3
-                }
-            }
-        }
-        B.n_pos[ni] = p;
-        B.n_kind[ni] = (u8)((rev ? K_RSTOP : K_FSTOP) | (f << 2));
-        B.n_mate[ni] = node_index(B, cb + far - 1, 0);
-        B.n_orf[ni] = orf_index(B, cb + far - 1);
-        B.n_trig[ni] = trig;
-        if (atg > 0) {                   // functions.py:267-279
-            u32 cM[4] = {0, 0, 0, 0}, cm[4] = {0, 0, 0, 0};
-            if (!rev) {
-                int start = atg, stop = p;
-                int n = ((stop - start) / 8) * 3;
-                for (int b = start + n; b < stop - 36; b += 3) {
-                    int im, il;
-                    gc_class(v.meta[b - 1] >> 3, false, im, il);
-                    cM[im]++;
-                    cm[il]++;
-                }
-            } else {
-                int start = atg, stop = p;
-                int n = ((start - stop) / 8) * 3;
-                for (int b = start - n; b > stop + 36; b -= 3) {
-                    int im, il;
-                    gc_class(v.meta[b - 1] >> 3, true, im, il);
-                    cM[im]++;
-                    cm[il]++;
-                }
-            }
-            for (int k = 1; k < 4; k++) {
-                if (cM[k]) PB_ATOMIC_ADD(&cs->cmax[k], cM[k]);
-                if (cm[k]) PB_ATOMIC_ADD(&cs->cmin[k], cm[k]);
-            }
-        }
-    }
-}
+#include "enum_fill.inc"
