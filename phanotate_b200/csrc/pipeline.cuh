@@ -147,6 +147,8 @@ struct Batch {
     u64* bC;
     u64* bG;
     u64* bT;
+    u64* mNS;             // bit set where a start node sits
+    u64* mNK;             // bit set where a stop-key node sits
     // node-parallel fill / ORF scoring split
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
     Dec* o_hold;          // [no] product over the codons (functions.py:286-298)
@@ -236,6 +238,40 @@ PB_HDNI int rbs_score_scalar(const u8* s, int L, int i, bool rev) {
         }
     }
     return best;
+}
+PB_HD int rbs_group_max(int g, u32 mask);
+// one window through the 6-mer tables when it is complete and unambiguous, else the scalar form
+PB_HDNI int rbs_score_window(const u8* s, int L, int i, bool rev) {
+    if (i < 0 || i >= L) return 0;
+    if (i + 21 > L) return rbs_score_scalar(s, L, i, rev);
+    u32 idx = 0;
+    u32 gm = 0, gl = 0, gh = 0, gf = 0;
+    for (int k = 0; k < 21; k++) {
+        int cd = base_code(lower(s[i + k]));
+        if (cd > 3) return rbs_score_scalar(s, L, i, rev);
+        idx = ((idx << 2) | (u32)cd) & 4095u;
+        if (k >= 5) {
+            const int j = k - 5;                           // 6-mer starting at window offset j
+            if (!rev) {
+                const u32 m = TBL(rbs_end_mask)[idx];
+                if (j <= 2) gf |= m;
+                else if (j <= 4) gh |= m;
+                else if (j <= 10) gm |= m;
+                else if (j <= 12) gl |= m;
+            } else {
+                const u32 m = TBL(rbs_start_mask)[idx];
+                if (j >= 3 && j <= 4) gl |= m;
+                else if (j >= 5 && j <= 10) gm |= m;
+                else if (j >= 11 && j <= 12) gh |= m;
+                else if (j >= 13 && j <= 15) gf |= m;
+            }
+        }
+    }
+    int a = rbs_group_max(0, gm), b = rbs_group_max(1, gl), c = rbs_group_max(2, gh), d = rbs_group_max(3, gf);
+    int r = a > b ? a : b;
+    if (c > r) r = c;
+    if (d > r) r = d;
+    return r;
 }
 PB_HD int rbs_group_max(int g, u32 mask) {
     int lo, hi;
@@ -402,32 +438,21 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
 #include "enum_fwd.inc"
 // Stage 3: per 64-base block counts (nodes in the low word, ORFs = start nodes in the high word)
 PB_HDN void st_count64(const Batch& B, i64 blk) {
-    i64 g0 = blk * 64, g1 = g0 + 64;
-    if (g1 > B.nb) g1 = B.nb;
-    u32 nn = 0, no = 0;
-    for (i64 g = g0; g < g1; g++) {
-        u8 f = B.nflag[g];
-        nn += (f & 1) + ((f >> 1) & 1);
-        no += (f & 1);
-    }
-    B.rank[blk] = (u64)nn | ((u64)no << 32);
+    u32 ns = (u32)pb_popc64(B.mNS[blk]), nk = (u32)pb_popc64(B.mNK[blk]);
+    B.rank[blk] = (u64)(ns + nk) | ((u64)ns << 32);
 }
 // node index of (global position g, bit) after the exclusive scan of rank[]; start node sorts first
 PB_HD i32 node_index(const Batch& B, i64 g, int bit) {
-    i64 blk = g >> 6;
-    u32 n = (u32)B.rank[blk];
-    for (i64 q = blk << 6; q < g; q++) {
-        u8 f = B.nflag[q];
-        n += (f & 1) + ((f >> 1) & 1);
-    }
-    if (bit == 1) n += (B.nflag[g] & 1);
+    const i64 blk = g >> 6;
+    const u64 below = (1ull << (g & 63)) - 1ull;
+    u32 n = (u32)B.rank[blk] + (u32)pb_popc64(B.mNS[blk] & below) + (u32)pb_popc64(B.mNK[blk] & below);
+    if (bit == 1) n += (u32)((B.mNS[blk] >> (g & 63)) & 1ull);
     return (i32)n;
 }
 PB_HD i32 orf_index(const Batch& B, i64 g) {
-    i64 blk = g >> 6;
-    u32 n = (u32)(B.rank[blk] >> 32);
-    for (i64 q = blk << 6; q < g; q++) n += (B.nflag[q] & 1);
-    return (i32)n;
+    const i64 blk = g >> 6;
+    const u64 below = (1ull << (g & 63)) - 1ull;
+    return (i32)((u32)(B.rank[blk] >> 32) + (u32)pb_popc64(B.mNS[blk] & below));
 }
 PB_HDN void st_contig_offsets(const Batch& B, i64 c) {
     if (c > B.nc) return;
