@@ -164,6 +164,52 @@ PB_HDNI Dec dec_div(const Dec& a, const Dec& b, int prec = PB_PREC) {
     return dec_round8(Q, e, a.neg ^ b.neg, prec, inexact);
 }
 
+// a*b rounded half-even to W digits by ONE reciprocal multiplication (a has da digits, b has db):
+//   P = a*b;  k = digits(P) - W;  P/10^k = P * floor(2^256/10^k) / 2^256 + [0, 2^-30)
+// so quotient and rounding direction are known unless the top 32 fraction bits are within 2^-24 of
+// 0, 1/2 or 1 -- then, or for k outside 20..47, *ok = false and the caller uses the exact dec_mul.
+PB_HDNI Dec dec_mul_fast(const Dec& a, int da, const Dec& b, int db, int W, bool* ok) {
+    Dec r;
+    r.neg = a.neg ^ b.neg;
+    r.e = 0;
+    w_zero(r.c);
+    *ok = false;
+    Wide<8> P = w_mul(a.c, b.c);
+    int nd = da + db - 1;
+    if (nd >= PB_NPOW10 - 1) return r;
+    {
+        Wide<8> lim = w_pow10<8>(nd);
+        if (w_cmp(P, lim) >= 0) nd += 1;
+    }
+    const int k = nd - W;
+    if (k < 20 || k > 47 || P.w[7] != 0) return r;
+    Wide<6> R;
+#pragma unroll
+    for (int i = 0; i < 6; i++) R.w[i] = TBL(inv10_256)[k][i];
+    Wide<7> P7 = w_resize<7>(P);
+    Wide<13> Q = w_mul(P7, R);
+    if (Q.w[12] != 0) return r;
+    Wide<4> I;
+    I.w[0] = Q.w[8];
+    I.w[1] = Q.w[9];
+    I.w[2] = Q.w[10];
+    I.w[3] = Q.w[11];
+    const u32 fr = Q.w[7];
+    if (fr >= 0x7FFFFF00u && !(fr > 0x80000000u && fr < 0xFFFFFF00u)) return r;
+    if (fr > 0x80000000u) w_add_small(I, 1u);
+    Wide<4> hi = w_pow10<4>(W), lo = w_pow10<4>(W - 1);
+    i32 e = a.e + b.e + k;
+    if (w_cmp(I, hi) == 0) {
+        I = lo;
+        e += 1;
+    }
+    if (w_cmp(I, lo) < 0 || w_cmp(I, hi) >= 0) return r;
+    r.c = I;
+    r.e = e;
+    *ok = true;
+    return r;
+}
+
 // value exactly one?
 PB_HD bool dec_is_one_abs(const Dec& a) {
     if (a.e > 0 || a.e < -37) return false;
@@ -189,9 +235,24 @@ PB_HDNI Dec dec_powi(const Dec& x, u32 n, int prec = PB_PREC) {
     Dec r = x;
     int top = 31;
     while (!((n >> top) & 1)) top--;
+    const int dx = w_ndigits(x.c);
+    int dr = dx;                                   // digits of r: wprec once a product has been rounded
     for (int b = top - 1; b >= 0; b--) {
-        r = dec_mul(r, r, wprec);
-        if ((n >> b) & 1) r = dec_mul(r, x, wprec);
+        bool ok;
+        Dec t = dec_mul_fast(r, dr, r, dr, wprec, &ok);
+        if (!ok) {
+            t = dec_mul(r, r, wprec);
+            dr = w_ndigits(t.c);
+        } else dr = wprec;
+        r = t;
+        if ((n >> b) & 1) {
+            t = dec_mul_fast(r, dr, x, dx, wprec, &ok);
+            if (!ok) {
+                t = dec_mul(r, x, wprec);
+                dr = w_ndigits(t.c);
+            } else dr = wprec;
+            r = t;
+        }
     }
     i32 neg = (x.neg && (n & 1)) ? 1 : 0;
     return dec_round(r.c, r.e, neg, prec);

@@ -55,6 +55,134 @@ PB_HDNI void holdfac_prepare(const Dec& b, HoldFac& f) {
     f.btop[1] = t.w[1];
 }
 
+// one multiplication hold * b.  a = coefficient of hold (28 digits, three limbs), eh its exponent.
+// Returns false when the rounding cannot be decided from 32 fraction bits (caller runs the exact path).
+PB_HD bool hold_step_fast(u32& a0, u32& a1, u32& a2, i32& eh, const U4& c27, const U4& c28, const U4& misc) {
+    // which power of ten is dropped: a*b >= 10^55 <=> 28 digits are dropped
+    const u64 atop = ((u64)a2 << 34) | ((u64)a1 << 2) | (a0 >> 30);
+    const u64 btop = ((u64)misc.y << 32) | misc.x;
+#ifdef __CUDA_ARCH__
+    const u64 hi = __umul64hi(atop, btop);
+#else
+    const u64 hi = (u64)(((unsigned __int128)atop * btop) >> 64);
+#endif
+    const bool big = hi >= 0x06867a5a867f103bull;        // floor(10^55 / 2^124)
+    const u32 c0 = big ? c28.x : c27.x, c1 = big ? c28.y : c27.y, c2 = big ? c28.z : c27.z, c3 = big ? c28.w : c27.w;
+    // p = a * c, seven limbs, column by column
+    u32 p[7];
+    {
+        u64 acc;
+        u32 hi3;
+        u64 t;
+#define MAC(x, y)                  \
+    t = (u64)(x) * (y);            \
+    acc += t;                      \
+    hi3 += (acc < t) ? 1u : 0u;
+#define NEXT(k)                              \
+    p[k] = (u32)acc;                         \
+    acc = (acc >> 32) | ((u64)hi3 << 32);    \
+    hi3 = 0;
+        acc = 0;
+        hi3 = 0;
+        MAC(a0, c0) NEXT(0)
+        MAC(a0, c1) MAC(a1, c0) NEXT(1)
+        MAC(a0, c2) MAC(a1, c1) MAC(a2, c0) NEXT(2)
+        MAC(a0, c3) MAC(a1, c2) MAC(a2, c1) NEXT(3)
+        MAC(a1, c3) MAC(a2, c2) NEXT(4)
+        MAC(a2, c3) NEXT(5)
+        p[6] = (u32)acc;
+#undef MAC
+#undef NEXT
+    }
+    // integer part = p >> 124, fraction top 32 bits = bits 92..123
+    u32 i0 = (p[3] >> 28) | (p[4] << 4), i1 = (p[4] >> 28) | (p[5] << 4), i2 = (p[5] >> 28) | (p[6] << 4);
+    const u32 i3 = p[6] >> 28;
+    const u32 fr = (p[2] >> 28) | (p[3] << 4);
+    // 10^27 <= I < 10^28 must hold (otherwise the scale guess was off by one ulp: exact path)
+    const bool ge27 = (i2 > 0x033b2e3cu) || (i2 == 0x033b2e3cu && (i1 > 0x9fd0803cu || (i1 == 0x9fd0803cu && i0 >= 0xe8000000u)));
+    const bool lt28 = (i2 < 0x204fce5eu) || (i2 == 0x204fce5eu && (i1 < 0x3e250261u || (i1 == 0x3e250261u && i0 < 0x10000000u)));
+    if (i3 != 0 || !ge27 || !lt28) return false;
+    if (fr < 0x7FFFFF00u) {
+        // round down
+    } else if (fr > 0x80000000u && fr < 0xFFFFFF00u) {
+        i0 += 1;                                   // round up; carry
+        if (i0 == 0) {
+            i1 += 1;
+            if (i1 == 0) i2 += 1;
+        }
+        if (i2 == 0x204fce5eu && i1 == 0x3e250261u && i0 == 0x10000000u) {   // 10^28 -> 10^27, exponent + 1
+            i0 = 0xe8000000u;
+            i1 = 0x9fd0803cu;
+            i2 = 0x033b2e3cu;
+            eh += 1;
+        }
+    } else {
+        return false;
+    }
+    a0 = i0;
+    a1 = i1;
+    a2 = i2;
+    eh += (i32)misc.z + (big ? 28 : 27);
+    return true;
+}
+
+// a * b for 28-digit positive operands through hold_step_fast (b prepared in fb), else the generic multiply
+PB_HD Dec dec_mul28(const Dec& a, const Dec& b, const HoldFac& fb) {
+    if (fb.ok && a.c.w[3] == 0 && !a.neg && !b.neg) {
+        Wide<4> lo = w_pow10<4>(27);
+        if (w_cmp(a.c, lo) >= 0) {           // < 10^28 is implied by prec 28
+            u32 a0 = a.c.w[0], a1 = a.c.w[1], a2 = a.c.w[2];
+            i32 eh = a.e;
+            U4 c27, c28, misc;
+            c27.x = fb.c27[0]; c27.y = fb.c27[1]; c27.z = fb.c27[2]; c27.w = fb.c27[3];
+            c28.x = fb.c28[0]; c28.y = fb.c28[1]; c28.z = fb.c28[2]; c28.w = fb.c28[3];
+            misc.x = fb.btop[0]; misc.y = fb.btop[1]; misc.z = (u32)fb.e; misc.w = fb.ok;
+            if (hold_step_fast(a0, a1, a2, eh, c27, c28, misc)) {
+                Dec r;
+                r.c.w[0] = a0; r.c.w[1] = a1; r.c.w[2] = a2; r.c.w[3] = 0;
+                r.e = eh;
+                r.neg = 0;
+                return r;
+            }
+        }
+    }
+    return dec_mul(a, b);
+}
+// Decimal(a) / Decimal(b) for small non-negative integers (orfs.py:169-172: count / Decimal(len(seq))):
+// the General Decimal Arithmetic division with a one-limb divisor, magic = floor((2^64-1)/b)
+PB_HDNI Dec dec_div_u32(u32 a, u32 b, u64 magic, int prec) {
+    Dec r;
+    w_zero(r.c);
+    r.e = 0;
+    r.neg = 0;
+    if (a == 0) return r;
+    int Da = 1, Db = 1;
+    for (u32 t = a; t >= 10; t /= 10) Da++;
+    for (u32 t = b; t >= 10; t /= 10) Db++;
+    const int shift = Db - Da + prec + 1;
+    Wide<5> A = w_from_u64<5>(a);
+    w_mul_pow10(A, shift);
+    u32 rem = 0;
+#pragma unroll
+    for (int i = 4; i >= 0; i--) {
+        u64 x = ((u64)rem << 32) | A.w[i];
+        A.w[i] = div_u64_magic(x, b, magic, rem);
+    }
+    i32 e = -shift;
+    const bool inexact = rem != 0;
+    if (!inexact) {                                // exact: towards the ideal exponent 0
+        int sh = shift;
+        while (sh > 0) {
+            Wide<5> t = A;
+            u32 rm = w_div_p10(t, 1);
+            if (rm != 0) break;
+            A = t;
+            e += 1;
+            sh--;
+        }
+    }
+    return dec_round<5>(A, e, 0, prec, inexact);
+}
 PB_HD int contig_of_orf(const Batch& B, i64 oi) {
     int lo = 0, hi = B.nc;
     while (hi - lo > 1) {
@@ -87,9 +215,17 @@ PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
         nt = count_bits(B.bA, cb + x0, cb + x1);
         ng = count_bits(B.bC, cb + x0, cb + x1);
     }
-    Dec len = dec_from_u64((u64)(x1 - x0));
-    Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);
-    Dec pstop = pstop_formula(Pa, Pt, Pg);
+    const u32 len = (u32)(x1 - x0);
+    const u64 magic = ~0ull / len;
+    const Dec Pa = dec_div_u32(na, len, magic, PB_PREC), Pt = dec_div_u32(nt, len, magic, PB_PREC),
+              Pg = dec_div_u32(ng, len, magic, PB_PREC);
+    // Pt*Pa*Pa + Pt*Pg*Pa + Pt*Pa*Pg, left to right (orfs.py:173); Pa and Pg are the repeated multipliers
+    HoldFac fa, fg;
+    holdfac_prepare(Pa, fa);
+    holdfac_prepare(Pg, fg);
+    const Dec m1 = dec_mul28(Pt, Pa, fa), m2 = dec_mul28(Pt, Pg, fg);
+    const Dec t1 = dec_mul28(m1, Pa, fa), t2 = dec_mul28(m2, Pa, fa), t3 = dec_mul28(m1, Pg, fg);
+    Dec pstop = dec_add(dec_add(t1, t2), t3);
     B.o_pstop[oi] = pstop;
     B.o_x[oi] = dec_sub(dec_one(), pstop);
 }
@@ -177,77 +313,6 @@ PB_HDN void st_len_scatter(const Batch& B, i64 oi) {
     B.o_order[B.len_hist[HOLD_BINS - 1 - bin] + pos] = (i32)oi;
 }
 
-// one multiplication hold * b.  a = coefficient of hold (28 digits, three limbs), eh its exponent.
-// Returns false when the rounding cannot be decided from 32 fraction bits (caller runs the exact path).
-PB_HD bool hold_step_fast(u32& a0, u32& a1, u32& a2, i32& eh, const U4& c27, const U4& c28, const U4& misc) {
-    // which power of ten is dropped: a*b >= 10^55 <=> 28 digits are dropped
-    const u64 atop = ((u64)a2 << 34) | ((u64)a1 << 2) | (a0 >> 30);
-    const u64 btop = ((u64)misc.y << 32) | misc.x;
-#ifdef __CUDA_ARCH__
-    const u64 hi = __umul64hi(atop, btop);
-#else
-    const u64 hi = (u64)(((unsigned __int128)atop * btop) >> 64);
-#endif
-    const bool big = hi >= 0x06867a5a867f103bull;        // floor(10^55 / 2^124)
-    const u32 c0 = big ? c28.x : c27.x, c1 = big ? c28.y : c27.y, c2 = big ? c28.z : c27.z, c3 = big ? c28.w : c27.w;
-    // p = a * c, seven limbs, column by column
-    u32 p[7];
-    {
-        u64 acc;
-        u32 hi3;
-        u64 t;
-#define MAC(x, y)                  \
-    t = (u64)(x) * (y);            \
-    acc += t;                      \
-    hi3 += (acc < t) ? 1u : 0u;
-#define NEXT(k)                              \
-    p[k] = (u32)acc;                         \
-    acc = (acc >> 32) | ((u64)hi3 << 32);    \
-    hi3 = 0;
-        acc = 0;
-        hi3 = 0;
-        MAC(a0, c0) NEXT(0)
-        MAC(a0, c1) MAC(a1, c0) NEXT(1)
-        MAC(a0, c2) MAC(a1, c1) MAC(a2, c0) NEXT(2)
-        MAC(a0, c3) MAC(a1, c2) MAC(a2, c1) NEXT(3)
-        MAC(a1, c3) MAC(a2, c2) NEXT(4)
-        MAC(a2, c3) NEXT(5)
-        p[6] = (u32)acc;
-#undef MAC
-#undef NEXT
-    }
-    // integer part = p >> 124, fraction top 32 bits = bits 92..123
-    u32 i0 = (p[3] >> 28) | (p[4] << 4), i1 = (p[4] >> 28) | (p[5] << 4), i2 = (p[5] >> 28) | (p[6] << 4);
-    const u32 i3 = p[6] >> 28;
-    const u32 fr = (p[2] >> 28) | (p[3] << 4);
-    // 10^27 <= I < 10^28 must hold (otherwise the scale guess was off by one ulp: exact path)
-    const bool ge27 = (i2 > 0x033b2e3cu) || (i2 == 0x033b2e3cu && (i1 > 0x9fd0803cu || (i1 == 0x9fd0803cu && i0 >= 0xe8000000u)));
-    const bool lt28 = (i2 < 0x204fce5eu) || (i2 == 0x204fce5eu && (i1 < 0x3e250261u || (i1 == 0x3e250261u && i0 < 0x10000000u)));
-    if (i3 != 0 || !ge27 || !lt28) return false;
-    if (fr < 0x7FFFFF00u) {
-        // round down
-    } else if (fr > 0x80000000u && fr < 0xFFFFFF00u) {
-        i0 += 1;                                   // round up; carry
-        if (i0 == 0) {
-            i1 += 1;
-            if (i1 == 0) i2 += 1;
-        }
-        if (i2 == 0x204fce5eu && i1 == 0x3e250261u && i0 == 0x10000000u) {   // 10^28 -> 10^27, exponent + 1
-            i0 = 0xe8000000u;
-            i1 = 0x9fd0803cu;
-            i2 = 0x033b2e3cu;
-            eh += 1;
-        }
-    } else {
-        return false;
-    }
-    a0 = i0;
-    a1 = i1;
-    a2 = i2;
-    eh += (i32)misc.z + (big ? 28 : 27);
-    return true;
-}
-
 // Stage 7b+c: the per-codon product and Orf.score() of ORF oi.  S holds this ORF's six HoldFac as
 // 18 U4 words with stride BD (shared memory on the GPU: S[(k*3+v)*BD + t]).
 PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
@@ -264,8 +329,7 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
     bool infast = false;                     // hold currently lives in (a0,a1,a2,eh)
     int b = start;
     for (int it = 0; it < n; it++, b += step) {
-        const int code = meta[b - 1] >> 3;
-        const int k = TBL(gc_fac_index)[rev ? 1 : 0][code];
+        const int k = (meta[b - 1] >> (rev ? 3 : 0)) & 7;
         if (fastok) {
             if (!infast) {
                 if (it == 0) {               // 1 * f == f exactly

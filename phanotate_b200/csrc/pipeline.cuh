@@ -8,7 +8,7 @@
 // into /root/reference.
 //
 // HBM layout (structure of arrays, contigs concatenated):
-//   per base   : seq (input, 1 B), meta (1 B: codon class | GC-frame ordering), nflag (1 B)
+//   per base   : seq (input, 1 B), meta (1 B: GC-frame factor index fwd | rev), nflag (1 B), 10 bit masks (1.25 B)
 //   per 64 bp  : rank_nodes / rank_orfs (exclusive prefix counts -> node / ORF index of a position)
 //   per node   : position, kind, mate, ORF id, trigger, other_end, pstop index (sorted by contig, position)
 //   per ORF    : start, stop, frame, rbs score, start-codon weight id, pstop, weight (Dec), integer weight
@@ -367,7 +367,8 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         if (i + 2 < L && code[k] < 4 && code[k + 1] < 4 && code[k + 2] < 4)
             cls = B.P.codon_cls[code[k] * 16 + code[k + 1] * 4 + code[k + 2]];
         int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
-        meta[i] = (u8)(cls | (tr << 3));
+        // factor index of the codon starting here, forward strand in bits 0-2, reverse strand in bits 3-5
+        meta[i] = (u8)(TBL(gc_fac_index)[0][tr] | (TBL(gc_fac_index)[1][tr] << 3));
         const u32 bit = 1u << (bitoff + k);
         if (cls) mk[cls - 1] |= bit;                 // S, s, T, t
         if (code[k] < 4) mk[4 + code[k]] |= bit;     // a, c, g, t

@@ -179,120 +179,3 @@ PB_HDNI bool dec_to_wint(const Dec& d, WInt& out) {
     return ok;
 }
 
-// Stage 7: score one ORF.  item = ORF id
-PB_HDN void st_score_orf(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
-    const i32 ni = B.o_node[oi];
-    // contig of this ORF: binary search on corf
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (B.corf[mid] <= oi) lo = mid;
-        else hi = mid;
-    }
-    const int c = lo;
-    (void)ni;
-    CStat* cs = B.cs + c;
-    const i64 cb = B.coff[c];
-    const u8* s = B.seq + cb;
-    const u8* meta = B.meta + cb;
-    const int L = cs->L;
-    const int start = B.o_start[oi], stop = B.o_stop[oi];
-    const bool rev = B.o_frame[oi] < 0;
-    // extent of orf.seq in the forward text, 0-based half open (functions.py:206,219,234,246)
-    int x0, x1;
-    if (!rev) {
-        x0 = start - 1;
-        x1 = stop + 2;
-    } else {
-        x0 = stop - 1;
-        x1 = start + 2;
-    }
-    if (x0 < 0) x0 = 0;
-    if (x1 > L) x1 = L;
-    u32 cnt[4] = {0, 0, 0, 0};
-    for (int q = x0; q < x1; q++) {
-        int cd = base_code(lower(s[q]));
-        if (cd < 4) cnt[cd]++;
-    }
-    u32 na = cnt[0], nt = cnt[3], ng = cnt[2];
-    if (rev) {
-        na = cnt[3];
-        nt = cnt[0];
-        ng = cnt[1];
-    }
-    Dec len = dec_from_u64((u64)(x1 - x0));
-    Dec Pa = dec_div(dec_from_u64(na), len), Pt = dec_div(dec_from_u64(nt), len), Pg = dec_div(dec_from_u64(ng), len);
-    Dec pstop = pstop_formula(Pa, Pt, Pg);
-    B.o_pstop[oi] = pstop;
-    // factors ((1-pstop)**pos_max[i])**pos_min[j] for the six (i,j) classes, computed on first use
-    Dec x = dec_sub(dec_one(), pstop);
-    bool okall = true;
-    const bool xone = dec_is_one_abs(x);
-    SFx lnx;
-    w_zero(lnx.m);
-    lnx.neg = 0;
-    if (!xone) {
-        bool o1, o2;
-        Fx X = fx_from_dec(x, &o1);
-        lnx = fx_ln(X, &o2);
-        okall = okall && o1 && o2;
-    }
-    Dec A[4];
-    SFx lnA[4];
-    u8 haveA = 0, haveL = 0;
-    Dec F[16];
-    u32 haveF = 0;
-    Dec hold = dec_one();
-    const int step = rev ? -3 : 3;
-    for (int b = start; rev ? (b > stop) : (b < stop); b += step) {
-        int im, il;
-        gc_class(meta[b - 1] >> 3, rev, im, il);
-        int key = im * 4 + il;
-        if (!((haveF >> key) & 1u)) {
-            if (!((haveA >> im) & 1)) {
-                if (cs->max_one[im]) A[im] = x;                       // x ** Decimal(1) == x
-                else if (xone) {
-                    bool o;
-                    A[im] = dec_pow_fx(x, cs->fmax[im], 0, PB_PREC, &o);
-                } else {
-                    bool o;
-                    A[im] = dec_pow_ln(lnx, cs->fmax[im], PB_PREC, &o);
-                    okall = okall && o;
-                }
-                haveA |= (u8)(1 << im);
-            }
-            Dec f;
-            if (cs->min_one[il]) f = A[im];
-            else if (dec_is_one_abs(A[im])) {
-                bool o;
-                f = dec_pow_fx(A[im], cs->fmin[il], 0, PB_PREC, &o);
-            } else {
-                if (!((haveL >> im) & 1)) {
-                    bool o1, o2;
-                    Fx XA = fx_from_dec(A[im], &o1);
-                    lnA[im] = fx_ln(XA, &o2);
-                    okall = okall && o1 && o2;
-                    haveL |= (u8)(1 << im);
-                }
-                bool o;
-                f = dec_pow_ln(lnA[im], cs->fmin[il], PB_PREC, &o);
-                okall = okall && o;
-            }
-            F[key] = f;
-            haveF |= 1u << key;
-        }
-        hold = dec_mul(hold, F[key]);                                  // functions.py:293,298
-    }
-    // Orf.score (orfs.py:122-127)
-    Dec sc = dec_div(dec_one(), hold);
-    int sw = B.o_sw[oi];
-    if (sw >= 0) sc = dec_mul(sc, B.P.startw[sw]);
-    sc = dec_mul(sc, cs->wrbs[B.o_rbs[oi]]);
-    sc.neg ^= 1;
-    B.o_weight[oi] = sc;
-    WInt wi;
-    if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
-    B.o_wint[oi] = wi;
-    if (!okall) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
-}

@@ -139,6 +139,9 @@ void t_ln_rounded(int n, const u32* t_limbs, TDec* a_out, u32* ln_limbs, int* ln
         for (int j = 0; j < 7; j++) ln_limbs[i * 7 + j] = L.m.w[j];
     }
 }
+void t_div_u32(int n, const u32* a, const u32* b, TDec* o) {
+    for (int i = 0; i < n; i++) o[i] = out(dec_div_u32(a[i], b[i], ~0ull / b[i], 28));
+}
 void t_milli(int n, const TDec* a, u32* mag /* n x 8 */, int* okv) {
     for (int i = 0; i < n; i++) {
         Wide<8> m;

@@ -324,3 +324,19 @@ def test_ln_of_rounded_power_shortcut(lib):
             worst = max(worst, abs(got - want))
         print("ln-of-rounded worst", float(worst))
         assert worst < 2 ** 12, worst
+
+
+def test_small_integer_division_fast_path(lib):
+    """count / Decimal(len(seq)) (orfs.py:169-172) through the one-limb division: exact quotients keep the
+    ideal exponent, everything else is rounded half-even to 28 digits."""
+    rng = random.Random(31)
+    A = [rng.randrange(0, 6000) for _ in range(60000)] + [0, 1, 24, 3, 5, 1, 4095, 1000, 999999, 2 ** 31 - 1]
+    Bv = [rng.choice([rng.randrange(1, 6000), 96, 100, 125, 128, 300, 1024, 3000]) for _ in range(60000)] + \
+         [93, 3, 96, 6, 2, 7, 4096, 8, 1000000, 2 ** 31 - 1]
+    a = np.array(A, dtype=np.uint32)
+    b = np.array(Bv, dtype=np.uint32)
+    o = np.zeros(len(A), dtype=TDEC)
+    lib.t_div_u32(len(A), P(a), P(b), P(o))
+    getcontext().prec = 28
+    for x, y, g in zip(A, Bv, unpack(o)):
+        assert same(x / Decimal(y), g), (x, y, x / Decimal(y), g)
