@@ -151,15 +151,7 @@ PB_HDNI Dec dec_div(const Dec& a, const Dec& b, int prec = PB_PREC) {
     i32 e = a.e - b.e - shift;
     bool inexact = !w_is_zero(R);
     if (!inexact && shift > 0) {               // exact: move towards the ideal exponent a.e - b.e
-        int sh = shift;
-        while (sh > 0) {
-            Wide<8> t = Q;
-            u32 rem = w_div_p10(t, 1);
-            if (rem != 0) break;
-            Q = t;
-            e += 1;
-            sh--;
-        }
+        e += w_strip_zeros(Q, shift);
     }
     return dec_round8(Q, e, a.neg ^ b.neg, prec, inexact);
 }

@@ -171,15 +171,7 @@ PB_HDNI Dec dec_div_u32(u32 a, u32 b, u64 magic, int prec) {
     i32 e = -shift;
     const bool inexact = rem != 0;
     if (!inexact) {                                // exact: towards the ideal exponent 0
-        int sh = shift;
-        while (sh > 0) {
-            Wide<5> t = A;
-            u32 rm = w_div_p10(t, 1);
-            if (rm != 0) break;
-            A = t;
-            e += 1;
-            sh--;
-        }
+        e += w_strip_zeros(A, shift);
     }
     return dec_round<5>(A, e, 0, prec, inexact);
 }
@@ -291,24 +283,31 @@ PB_HDN void st_orf_powF(const Batch& B, i64 item) {
     B.o_fac[item] = f;
 }
 // S5: prepared factors, length bin, histogram for the counting sort.  item = ORF
-PB_HDN void st_orf_prepare(const Batch& B, i64 oi) {
+PB_HDN void st_orf_prepare(const Batch& B, i64 item) {
+    const i64 oi = item / 6;
     if (oi >= B.no) return;
-    u32 allok = 1;
-    for (int k = 0; k < 6; k++) {
-        HoldFac hf;
-        holdfac_prepare(B.o_fac[oi * 6 + k], hf);
-        allok &= hf.ok;
-        B.o_hf[oi * 6 + k] = hf;
+    const int k = (int)(item % 6);
+    HoldFac hf;
+    holdfac_prepare(B.o_fac[item], hf);
+    U4* dst = (U4*)(B.o_hf + item);            // three 16-byte stores
+    U4 v0, v1, v2;
+    v0.x = hf.c27[0]; v0.y = hf.c27[1]; v0.z = hf.c27[2]; v0.w = hf.c27[3];
+    v1.x = hf.c28[0]; v1.y = hf.c28[1]; v1.z = hf.c28[2]; v1.w = hf.c28[3];
+    v2.x = hf.btop[0]; v2.y = hf.btop[1]; v2.z = (u32)hf.e; v2.w = hf.ok;
+    dst[0] = v0;
+    dst[1] = v1;
+    dst[2] = v2;
+    if (k == 0) {
+        const bool rev = B.o_frame[oi] < 0;
+        int n = orf_steps(B.o_start[oi], B.o_stop[oi], rev);
+        int bin = n < HOLD_BINS - 1 ? n : HOLD_BINS - 1;
+        B.o_bin[oi] = (unsigned short)bin;
+        PB_ATOMIC_ADD(&B.len_hist[HOLD_BINS - 1 - bin], 1u);          // reversed: longest ORFs first
     }
-    const bool rev = B.o_frame[oi] < 0;
-    int n = orf_steps(B.o_start[oi], B.o_stop[oi], rev);
-    int bin = n < HOLD_BINS - 1 ? n : HOLD_BINS - 1;
-    B.o_bin[oi] = (unsigned short)(bin | (allok ? 0x8000 : 0));
-    PB_ATOMIC_ADD(&B.len_hist[HOLD_BINS - 1 - bin], 1u);              // reversed: longest ORFs first
 }
 PB_HDN void st_len_scatter(const Batch& B, i64 oi) {
     if (oi >= B.no) return;
-    int bin = B.o_bin[oi] & 0x7FFF;
+    int bin = B.o_bin[oi];
     u32 pos = PB_ATOMIC_ADD_RET(&B.len_cursor[HOLD_BINS - 1 - bin], 1u);
     B.o_order[B.len_hist[HOLD_BINS - 1 - bin] + pos] = (i32)oi;
 }
@@ -320,55 +319,54 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
     const u8* meta = B.meta + B.coff[c];
     const int start = B.o_start[oi], stop = B.o_stop[oi];
     const bool rev = B.o_frame[oi] < 0;
-    const bool fastok = (B.o_bin[oi] & 0x8000) != 0;
+    const int sh = rev ? 3 : 0;
     const int step = rev ? -3 : 3;
     const int n = orf_steps(start, stop, rev);
+    // the fast path needs all six factors to carry exactly 28 digits
+    bool fastok = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++) fastok = fastok && (S[(k * 3 + 2) * BD + t].w != 0);
     Dec hold = dec_one();
-    u32 a0 = 0, a1 = 0, a2 = 0;
-    i32 eh = 0;
-    bool infast = false;                     // hold currently lives in (a0,a1,a2,eh)
-    int b = start;
-    for (int it = 0; it < n; it++, b += step) {
-        const int k = (meta[b - 1] >> (rev ? 3 : 0)) & 7;
-        if (fastok) {
-            if (!infast) {
-                if (it == 0) {               // 1 * f == f exactly
-                    const Dec f = B.o_fac[(i64)oi * 6 + k];
-                    a0 = f.c.w[0];
-                    a1 = f.c.w[1];
-                    a2 = f.c.w[2];
-                    eh = f.e;
-                    infast = true;
-                    continue;
-                }
-            } else {
-                const U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
-                if (hold_step_fast(a0, a1, a2, eh, c27, c28, misc)) continue;
-                // undecidable from 32 fraction bits: exact multiplication, then back to the fast path
-                Dec h;
-                h.c.w[0] = a0;
-                h.c.w[1] = a1;
-                h.c.w[2] = a2;
-                h.c.w[3] = 0;
-                h.e = eh;
-                h.neg = 0;
-                h = dec_mul(h, B.o_fac[(i64)oi * 6 + k]);
-                a0 = h.c.w[0];
-                a1 = h.c.w[1];
-                a2 = h.c.w[2];
-                eh = h.e;
-                continue;
-            }
+    if (fastok && n > 0) {
+        // 1 * f == f exactly: the first step is a copy
+        int k = (meta[start - 1] >> sh) & 7;
+        const Dec f = B.o_fac[(i64)oi * 6 + k];
+        u32 a0 = f.c.w[0], a1 = f.c.w[1], a2 = f.c.w[2];
+        i32 eh = f.e;
+        int b = start + step;
+        int knext = (n > 1) ? ((meta[b - 1] >> sh) & 7) : 0;
+        for (int it = 1; it < n; it++) {
+            k = knext;
+            b += step;
+            if (it + 1 < n) knext = (meta[b - 1] >> sh) & 7;       // prefetch the next codon's class
+            const U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
+            if (hold_step_fast(a0, a1, a2, eh, c27, c28, misc)) continue;
+            // undecidable from 32 fraction bits: exact multiplication, then back to the fast path
+            Dec h;
+            h.c.w[0] = a0;
+            h.c.w[1] = a1;
+            h.c.w[2] = a2;
+            h.c.w[3] = 0;
+            h.e = eh;
+            h.neg = 0;
+            h = dec_mul(h, B.o_fac[(i64)oi * 6 + k]);
+            a0 = h.c.w[0];
+            a1 = h.c.w[1];
+            a2 = h.c.w[2];
+            eh = h.e;
         }
-        hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);             // functions.py:293,298 (generic path)
-    }
-    if (infast) {
         hold.c.w[0] = a0;
         hold.c.w[1] = a1;
         hold.c.w[2] = a2;
         hold.c.w[3] = 0;
         hold.e = eh;
         hold.neg = 0;
+    } else {
+        int b = start;
+        for (int it = 0; it < n; it++, b += step) {
+            const int k = (meta[b - 1] >> sh) & 7;
+            hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);         // functions.py:293,298 (generic path)
+        }
     }
     B.o_hold[oi] = hold;
 }

@@ -57,6 +57,8 @@ PB_KERNEL(st_ov_pow)
 PB_KERNEL(st_len_scatter)
 PB_KERNEL(st_ov_weight)
 PB_KERNEL(st_contig_stats)
+PB_KERNEL(st_gap_pow_int)
+PB_KERNEL(st_gap_pow_real)
 PB_KERNEL(st_gap_lut)
 PB_KERNEL(st_node_attrs)
 PB_KERNEL(st_ov_count)

@@ -345,17 +345,25 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         code[k] = (u8)cd;
     }
     if (bad) PB_ATOMIC_OR(&cs->err, (u32)ERR_CHAR);
-    // ---- 6-mer motif masks for 6-mers starting at i0+k (valid only when all six bases are acgt)
+    // ---- 6-mer motif masks for 6-mers starting at i0+k (valid only when all six bases are acgt), and the
+    //      length of the run of unambiguous letters ending at every position (rolling, one pass)
     unsigned short em[SCAN_STRIP + 16], sm[SCAN_STRIP + 16];
-    for (int k = 0; k < n + 15; k++) {
-        int idx = 0, ok = 1;
-        for (int t = 0; t < 6; t++) {
-            int cd = (k + t < ncode) ? code[k + t] : 5;
-            if (cd > 3) ok = 0;
-            idx = (idx << 2) | (cd & 3);
+    u8 runs[SCAN_STRIP + 21];
+    {
+        u32 idx = 0;
+        int run = 0;
+        for (int j = 0; j < ncode; j++) {
+            const int cd = code[j];
+            run = (cd < 4) ? (run < 255 ? run + 1 : 255) : 0;
+            runs[j] = (u8)run;
+            idx = ((idx << 2) | (u32)(cd & 3)) & 4095u;
+            if (j >= 5 && j - 5 < n + 15) {
+                const bool ok6 = run >= 6;
+                em[j - 5] = ok6 ? TBL(rbs_end_mask)[idx] : 0;
+                sm[j - 5] = ok6 ? TBL(rbs_start_mask)[idx] : 0;
+            }
         }
-        em[k] = ok ? TBL(rbs_end_mask)[idx] : 0;
-        sm[k] = ok ? TBL(rbs_start_mask)[idx] : 0;
+        for (int k = (ncode >= 5 ? ncode - 5 : 0); k < n + 15; k++) em[k] = sm[k] = 0;
     }
     u32 nAT = 0, nGC = 0;
     for (int k = 0; k < n; k++) {
@@ -374,13 +382,7 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         if (code[k] < 4) mk[4 + code[k]] |= bit;     // a, c, g, t
         // RBS background, both strands
         int sf, sr;
-        bool clean = (i + 21 <= L);
-        if (clean)
-            for (int t = 0; t < 21; t++)
-                if (code[k + t] > 3) {
-                    clean = false;
-                    break;
-                }
+        const bool clean = (i + 21 <= L) && runs[k + 20] >= 21;
         if (clean) {
             u32 gm = em[k + 5] | em[k + 6] | em[k + 7] | em[k + 8] | em[k + 9] | em[k + 10];
             u32 gl = em[k + 11] | em[k + 12];

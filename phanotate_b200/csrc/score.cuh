@@ -81,46 +81,55 @@ PB_HDN void st_contig_stats(const Batch& B, i64 c) {
     }
 }
 
-// score_gap for length <= 300 (functions.py:36-46): 1/g**Decimal(length/3) (+ 1/0.05 if 'diff')
-PB_HDN Dec gap_score_small(const CStat* cs, int len, bool* ok) {
-    Dec pw;
-    *ok = true;
-    if (len % 3 == 0) {
-        pw = dec_powi(cs->g, (u32)(len / 3));            // len >= 0 here
-    } else {
-        double y = (double)len / 3.0;                     // Python float, then Decimal(float) is exact
-        Fx Y = fx_from_double(fabs(y));
-        if (dec_is_one_abs(cs->g)) {
-            bool o;
-            pw = dec_pow_fx(cs->g, Y, y < 0, PB_PREC, &o);
-        } else {
-            SFx T;
-            T.m = fx_mul(cs->ln_g.m, Y);
-            T.neg = cs->ln_g.neg ^ (y < 0 ? 1 : 0);
-            bool o3, o4;
-            Fx V = fx_exp(T, &o3);
-            pw = fx_to_dec(V, PB_PREC, &o4);
-            *ok = o3 && o4;
-        }
-    }
-    return dec_div(dec_one(), pw);
-}
+// score_gap for length <= 300 (functions.py:36-46): 1/g**Decimal(length/3) (+ 1/0.05 if 'diff'), as three
+// small kernels: integer exponents (length % 3 == 0), real exponents, and the reciprocal / +20 / integer part.
 PB_HD Dec dec_twenty() {   // 1/Decimal('0.05') == Decimal('2E+1')
     Dec d = dec_from_u64(2);
     d.e = 1;
     return d;
 }
-// Stage 6: gap tables.  item = contig*GAPN + (len+2)
+// item = contig*101 + m, length = 3m
+PB_HDN void st_gap_pow_int(const Batch& B, i64 item) {
+    const i64 c = item / 101;
+    if (c >= B.nc) return;
+    const int m = (int)(item % 101);
+    const CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    B.gap_same[c * GAPN + (3 * m + 2)] = dec_powi(cs->g, (u32)m);
+}
+// item = contig*202 + j, length = 3*(j/2) - 2 + (j&1)  (the lengths in -2..299 that are not multiples of 3)
+PB_HDN void st_gap_pow_real(const Batch& B, i64 item) {
+    const i64 c = item / 202;
+    if (c >= B.nc) return;
+    const int j = (int)(item % 202);
+    const int len = 3 * (j >> 1) - 2 + (j & 1);
+    CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    const double y = (double)len / 3.0;                   // Python float; Decimal(float) is exact
+    const Fx Y = fx_from_double(fabs(y));
+    Dec pw;
+    bool ok = true;
+    if (dec_is_one_abs(cs->g)) pw = dec_pow_fx(cs->g, Y, y < 0, PB_PREC, &ok);
+    else {
+        SFx T;
+        T.m = fx_mul(cs->ln_g.m, Y);
+        T.neg = cs->ln_g.neg ^ (y < 0 ? 1 : 0);
+        bool o3, o4;
+        Fx V = fx_exp(T, &o3);
+        pw = fx_to_dec(V, PB_PREC, &o4);
+        ok = o3 && o4;
+    }
+    if (!ok) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+    B.gap_same[c * GAPN + (len + 2)] = pw;
+}
+// item = contig*GAPN + (len+2): gap_same holds g**(len/3) on entry
 PB_HDN void st_gap_lut(const Batch& B, i64 item) {
     i64 c = item / GAPN;
     if (c >= B.nc) return;
-    int len = (int)(item % GAPN) - 2;
     CStat* cs = B.cs + c;
     if (cs->L < 1) return;
-    bool ok;
-    Dec same = gap_score_small(cs, len, &ok);
+    Dec same = dec_div(dec_one(), B.gap_same[item]);
     Dec diff = dec_add(same, dec_twenty());
-    if (!ok) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
     B.gap_same[item] = same;
     B.gap_diff[item] = diff;
     Wide<2> m;

@@ -252,6 +252,23 @@ PB_HD void w_mul_pow10(Wide<N>& a, int k) {
     }
     if (k > 0) w_mul_small(a, TBL(p10_u32)[k]);
 }
+// Strip up to `maxz` trailing decimal zeros from a; returns how many were removed.  Chunked (8, 4, 2,
+// 1 digits) so that exact quotients like 1/4 = 0.25000... cost a handful of short divisions.
+template <int N>
+PB_HD int w_strip_zeros(Wide<N>& a, int maxz) {
+    int done = 0;
+#pragma unroll 1
+    for (int step = 8; step >= 1; step >>= 1) {
+        while (maxz - done >= step) {
+            Wide<N> t = a;
+            u32 rem = w_div_p10(t, step);
+            if (rem != 0) break;
+            a = t;
+            done += step;
+        }
+    }
+    return done;
+}
 // Drop the k lowest decimal digits of a with round-half-even.  *inexact is set when a non-zero
 // digit was dropped.  If `sticky_in` is non-zero the dropped part is treated as being followed by
 // further non-zero digits (used for division remainders).
