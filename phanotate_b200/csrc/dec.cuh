@@ -229,22 +229,26 @@ PB_HDNI Dec dec_powi(const Dec& x, u32 n, int prec = PB_PREC) {
     while (!((n >> top) & 1)) top--;
     const int dx = w_ndigits(x.c);
     int dr = dx;                                   // digits of r: wprec once a product has been rounded
-    for (int b = top - 1; b >= 0; b--) {
+    // square-and-multiply as ONE stream of products (r*r or r*x): lanes of a warp stay on the same
+    // instruction whatever the bits of their exponents are
+    int b = top - 1;
+    bool pending = false;
+    for (;;) {
+        const bool mulx = pending;
+        if (!mulx) {
+            if (b < 0) break;
+            pending = ((n >> b) & 1) != 0;
+            b--;
+        } else pending = false;
+        const Dec& other = mulx ? x : r;
+        const int dother = mulx ? dx : dr;
         bool ok;
-        Dec t = dec_mul_fast(r, dr, r, dr, wprec, &ok);
+        Dec t = dec_mul_fast(r, dr, other, dother, wprec, &ok);
         if (!ok) {
-            t = dec_mul(r, r, wprec);
+            t = dec_mul(r, other, wprec);
             dr = w_ndigits(t.c);
         } else dr = wprec;
         r = t;
-        if ((n >> b) & 1) {
-            t = dec_mul_fast(r, dr, x, dx, wprec, &ok);
-            if (!ok) {
-                t = dec_mul(r, x, wprec);
-                dr = w_ndigits(t.c);
-            } else dr = wprec;
-            r = t;
-        }
     }
     i32 neg = (x.neg && (n & 1)) ? 1 : 0;
     return dec_round(r.c, r.e, neg, prec);

@@ -12,15 +12,7 @@
 #include "dec2double.cuh"
 
 PB_HD bool kind_is_entry(int k) { return k == K_FSTART || k == K_RSTOP; }
-PB_HD int contig_of_node(const Batch& B, i32 ni) {
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (B.cnode[mid] <= ni) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
+PB_HD int contig_of_node(const Batch& B, i32 ni) { return B.n_contig[ni]; }
 
 // Stage 8: other_end[] and the pstop used for overlap averaging, per node, with the reference's
 // bare-position dict semantics at the six positions where two roles share a key (orfs.py:17-32,
@@ -591,14 +583,8 @@ struct NodeRec {
 };
 PB_HDN void pack_orf(const Batch& B, i64 oi, OrfRec* out) {
     if (oi >= B.no) return;
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (B.corf[mid] <= oi) lo = mid;
-        else hi = mid;
-    }
     OrfRec r;
-    r.contig = lo;
+    r.contig = B.o_contig[oi];
     r.start = B.o_start[oi];
     r.stop = B.o_stop[oi];
     r.frame = B.o_frame[oi];

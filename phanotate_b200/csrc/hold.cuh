@@ -175,15 +175,7 @@ PB_HDNI Dec dec_div_u32(u32 a, u32 b, u64 magic, int prec) {
     }
     return dec_round<5>(A, e, 0, prec, inexact);
 }
-PB_HD int contig_of_orf(const Batch& B, i64 oi) {
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (B.corf[mid] <= oi) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
+PB_HD int contig_of_orf(const Batch& B, i64 oi) { return B.o_contig[oi]; }
 // Stage 7a (split into small kernels: each keeps its instruction working set inside the I-cache).
 // S1: base composition -> pstop, x = 1 - pstop.  item = ORF
 PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
@@ -236,11 +228,13 @@ PB_HDN void st_orf_lnx(const Batch& B, i64 oi) {
     }
     B.o_lnx[oi] = lnx;
 }
-// S3: A_im = x ** pos_max[im] and ln(A_im).  item = ORF*3 + (im-1)
-PB_HDN void st_orf_powA(const Batch& B, i64 item) {
-    const i64 oi = item / 3;
-    if (oi >= B.no) return;
-    const int im = (int)(item % 3) + 1;
+// S3: A_im = x ** pos_max[im] and ln(A_im).  item = (im-1)*no + ORF: a warp works on one exponent index, so
+// the "exponent is exactly 1 -> plain copy" case (one of the three per contig) does not split warps
+PB_HDN void st_orf_powA(const Batch& B, i64 item_in) {
+    if (item_in >= (i64)B.no * 3) return;
+    const i64 oi = item_in % B.no;
+    const int im = (int)(item_in / B.no) + 1;
+    const i64 item = oi * 3 + (im - 1);
     const int c = contig_of_orf(B, oi);
     const CStat* cs = B.cs + c;
     const Dec x = B.o_x[oi];
@@ -264,11 +258,12 @@ PB_HDN void st_orf_powA(const Batch& B, i64 item) {
     B.o_A[item] = A;
     B.o_lnA[item] = lnA;
 }
-// S4: F_k = A_im ** pos_min[il].  item = ORF*6 + k
-PB_HDN void st_orf_powF(const Batch& B, i64 item) {
-    const i64 oi = item / 6;
-    if (oi >= B.no) return;
-    const int k = (int)(item % 6);
+// S4: F_k = A_im ** pos_min[il].  item = k*no + ORF (same reason)
+PB_HDN void st_orf_powF(const Batch& B, i64 item_in) {
+    if (item_in >= (i64)B.no * 6) return;
+    const i64 oi = item_in % B.no;
+    const int k = (int)(item_in / B.no);
+    const i64 item = oi * 6 + k;
     const int im = k / 2 + 1;
     const int il = (k % 2) + 1 + (((k % 2) + 1 >= im) ? 1 : 0);      // inverse of fac_index
     const int c = contig_of_orf(B, oi);

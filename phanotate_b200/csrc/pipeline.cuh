@@ -94,6 +94,8 @@ struct Batch {
     i32* cnode;           // [nc+1]
     i32* corf;            // [nc+1]
     i32* n_pos;
+    i32* n_contig;        // [nn] contig of the node
+    i32* o_contig;        // [no] contig of the ORF
     u8* n_kind;           // K_* | frame<<2
     i32* n_mate;
     i32* n_orf;
