@@ -35,10 +35,18 @@ PB_HD int orf_steps(int start, int stop, bool rev) { return rev ? (start - stop 
 PB_HDNI void holdfac_prepare(const Dec& b, HoldFac& f) {
     const u32 R27[6] = {0x524f8e02u, 0x7aa9a3eeu, 0xbaf51326u, 0x8f03f243u, 0xf3a68dbcu, 0x00000004u};   // 2^252/10^27
     const u32 R28[6] = {0x3b6e5b00u, 0x0c4429feu, 0xc5e54eb7u, 0x41806506u, 0x7ec3daf9u, 0x00000000u};   // 2^252/10^28
+    // a factor with fewer than 28 digits (e.g. 1 - pstop = 0.95968 exactly) is scaled to 28 digits: the
+    // rounded product with a 28-digit multiplicand only depends on its value
+    Wide<4> c4 = b.c;
     f.e = b.e;
+    int nd = w_ndigits(c4);
+    if (nd >= 1 && nd < 28) {
+        w_mul_pow10(c4, 28 - nd);
+        f.e -= 28 - nd;
+    }
     Wide<4> lo = w_pow10<4>(27), hi = w_pow10<4>(28);
-    f.ok = (w_cmp(b.c, lo) >= 0 && w_cmp(b.c, hi) < 0) ? 1u : 0u;
-    Wide<3> bc = w_resize<3>(b.c);
+    f.ok = (!b.neg && w_cmp(c4, lo) >= 0 && w_cmp(c4, hi) < 0) ? 1u : 0u;
+    Wide<3> bc = w_resize<3>(c4);
     Wide<6> r;
 #pragma unroll
     for (int i = 0; i < 6; i++) r.w[i] = R27[i];
@@ -50,7 +58,7 @@ PB_HDNI void holdfac_prepare(const Dec& b, HoldFac& f) {
     p = w_mul(bc, r);
 #pragma unroll
     for (int i = 0; i < 4; i++) f.c28[i] = p.w[i + 4];
-    Wide<4> t = w_shr(b.c, 30);
+    Wide<4> t = w_shr(c4, 30);
     f.btop[0] = t.w[0];
     f.btop[1] = t.w[1];
 }
@@ -322,20 +330,33 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
 #pragma unroll
     for (int k = 0; k < 6; k++) fastok = fastok && (S[(k * 3 + 2) * BD + t].w != 0);
     Dec hold = dec_one();
-    if (fastok && n > 0) {
-        // 1 * f == f exactly: the first step is a copy
-        int k = (meta[start - 1] >> sh) & 7;
-        const Dec f = B.o_fac[(i64)oi * 6 + k];
-        u32 a0 = f.c.w[0], a1 = f.c.w[1], a2 = f.c.w[2];
-        i32 eh = f.e;
-        int b = start + step;
-        int knext = (n > 1) ? ((meta[b - 1] >> sh) & 7) : 0;
-        for (int it = 1; it < n; it++) {
+    int it = 0, b = start;
+    // generic steps until the product carries 28 digits (normally just the first: 1 * f == f exactly)
+    const Wide<4> lo27 = w_pow10<4>(27);
+    while (it < n && !(fastok && hold.c.w[3] == 0 && w_cmp(hold.c, lo27) >= 0)) {
+        const int k = (meta[b - 1] >> sh) & 7;
+        hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);             // functions.py:293,298
+        it++;
+        b += step;
+    }
+    if (it < n) {
+        u32 a0 = hold.c.w[0], a1 = hold.c.w[1], a2 = hold.c.w[2];
+        i32 eh = hold.e;
+        // software pipeline: class of step it+1 and operands of step it are fetched one step ahead
+        int k = (meta[b - 1] >> sh) & 7;
+        U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
+        b += step;
+        int knext = (it + 1 < n) ? ((meta[b - 1] >> sh) & 7) : 0;
+        for (; it < n; it++) {
+            const int kcur = k;
+            const U4 d27 = c27, d28 = c28, dmisc = misc;
             k = knext;
+            c27 = S[(k * 3 + 0) * BD + t];
+            c28 = S[(k * 3 + 1) * BD + t];
+            misc = S[(k * 3 + 2) * BD + t];
             b += step;
-            if (it + 1 < n) knext = (meta[b - 1] >> sh) & 7;       // prefetch the next codon's class
-            const U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
-            if (hold_step_fast(a0, a1, a2, eh, c27, c28, misc)) continue;
+            if (it + 2 < n) knext = (meta[b - 1] >> sh) & 7;
+            if (hold_step_fast(a0, a1, a2, eh, d27, d28, dmisc)) continue;
             // undecidable from 32 fraction bits: exact multiplication, then back to the fast path
             Dec h;
             h.c.w[0] = a0;
@@ -344,7 +365,7 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
             h.c.w[3] = 0;
             h.e = eh;
             h.neg = 0;
-            h = dec_mul(h, B.o_fac[(i64)oi * 6 + k]);
+            h = dec_mul(h, B.o_fac[(i64)oi * 6 + kcur]);
             a0 = h.c.w[0];
             a1 = h.c.w[1];
             a2 = h.c.w[2];
@@ -356,12 +377,6 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
         hold.c.w[3] = 0;
         hold.e = eh;
         hold.neg = 0;
-    } else {
-        int b = start;
-        for (int it = 0; it < n; it++, b += step) {
-            const int k = (meta[b - 1] >> sh) & 7;
-            hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);         // functions.py:293,298 (generic path)
-        }
     }
     B.o_hold[oi] = hold;
 }
