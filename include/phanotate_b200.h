@@ -105,7 +105,12 @@ enum {
 
 enum {
     PB200_INPUT_DEVICE = 1,   /* flags of pb200_run: bases/offsets are device pointers */
-    PB200_REUSE_INPUT = 2     /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+    PB200_REUSE_INPUT = 2,    /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+    PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
+                                 pb200_run.  Default: the solve uses certified integer weights (exactly
+                                 trunc(weight*1000), edges.py:22) and the 28-digit Decimal weights are computed
+                                 for the called CDS, and for everything else when pb200_get_orfs /
+                                 pb200_build_edges ask for them.  Results are identical either way. */
 };
 
 typedef struct pb200_ctx pb200_ctx;
@@ -120,6 +125,12 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
 
 /* out[0..7] = n_contigs, n_bases, n_nodes, n_orfs, n_overlap_edges, n_bridge_edges, n_calls, n_edges */
 int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
+/* out[0] = ORFs whose weight went through the literal Decimal chain before the solve, out[1] = after
+ * it (called CDS), out[2] = overlap edges through the literal power; rest reserved */
+int pb200_stats(pb200_ctx* ctx, int64_t out[8]);
+/* the integer weight the solver used for every ORF edge: trunc(Orf.weight * 1000) (edges.py:22) as
+ * 8 little-endian 32-bit limbs, two's complement, per ORF */
+int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out);
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out);
 int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out);
 int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out);

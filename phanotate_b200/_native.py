@@ -36,6 +36,7 @@ assert PARAMS.itemsize == 4 + 32 + 192 + 4 + 32 + 8
 ERR_CHAR, ERR_RANGE, ERR_PARALLEL, ERR_OVERFLOW, ERR_NOPATH, ERR_INTERNAL, ERR_LOOKUP = 1, 2, 4, 8, 16, 32, 64
 INPUT_DEVICE = 1
 REUSE_INPUT = 2
+LITERAL = 4
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 
@@ -67,6 +68,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_last_error.restype = ctypes.c_char_p
     lib.pb200_run.argtypes = [vp, vp, i64p, i32, vp, ctypes.c_uint32]
     lib.pb200_sizes.argtypes = [vp, vp]
+    lib.pb200_stats.argtypes = [vp, vp]
+    lib.pb200_get_orf_int_weights.argtypes = [vp, vp]
     for f in ("pb200_get_calls", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_get_edges"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pb200_build_edges.argtypes = [vp]
@@ -88,7 +91,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
-EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_sizes", "pb200_get_calls",
+EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_sizes", "pb200_stats",
+           "pb200_get_orf_int_weights", "pb200_get_calls",
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_stage_times", "pb200_launch_count", "pb200_last_run_ms",
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes"]

@@ -131,9 +131,10 @@ PB_HDNI Fx fx_from_dec(const Dec& x, bool* ok) {
     return w_resize<FX_N>(s);
 }
 
-// exp(T) for signed T; result must be < 2^32.
-PB_HDNI Fx fx_exp(const SFx& T, bool* ok) {
+// exp(T) for signed T as P * 2^K with P in [1, 2) (Q32.192); |T| <= 700.
+PB_HDNI Fx fx_exp_core(const SFx& T, int* Kout, bool* ok) {
     *ok = true;
+    *Kout = 0;
     const Fx ln2 = fx_table(TBL(fx_ln2));
     Fx r;
     int K;
@@ -196,6 +197,14 @@ PB_HDNI Fx fx_exp(const SFx& T, bool* ok) {
     if (j1) p = fx_mul(p, fx_table(TBL(fx_e1)[j1]));
     if (j2) p = fx_mul(p, fx_table(TBL(fx_e2)[j2]));
     if (j3) p = fx_mul(p, fx_table(TBL(fx_e3)[j3]));
+    *Kout = K;
+    return p;
+}
+// exp(T) for signed T; result must be < 2^32.
+PB_HDNI Fx fx_exp(const SFx& T, bool* ok) {
+    int K;
+    Fx p = fx_exp_core(T, &K, ok);
+    if (!*ok) return fx_one();
     if (K > 0) {
         if (K >= 30) {
             *ok = false;

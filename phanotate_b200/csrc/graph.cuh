@@ -443,8 +443,8 @@ PB_HDN void st_backtrack(const Batch& B, i64 c64) {
     B.call_cnt[c] = (u32)n;
     cs->n_calls = n;
 }
-// call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them.  item = call
-PB_HDN void st_gather_calls(const Batch& B, i64 k) {
+// ORF of call k (calls are numbered contig by contig in path order).  item = call
+PB_HDN void st_call_orf(const Batch& B, i64 k) {
     if (k >= B.ncalls) return;
     int lo = 0, hi = B.nc;                 // contig of call k: call_cnt[lo] <= k < call_cnt[lo+1]
     while (hi - lo > 1) {
@@ -453,8 +453,13 @@ PB_HDN void st_gather_calls(const Batch& B, i64 k) {
         else hi = mid;
     }
     const int c = lo;
-    const i32 orf = B.call_tmp[B.corf[c] + (k - B.call_cnt[c])];
-    B.call_orf[k] = orf;
+    B.call_orf[k] = B.call_tmp[B.corf[c] + (k - B.call_cnt[c])];
+}
+// call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them.  item = call
+PB_HDN void st_gather_calls(const Batch& B, i64 k) {
+    if (k >= B.ncalls) return;
+    const i32 orf = B.call_orf[k];
+    const int c = B.o_contig[orf];
     CallRec r;
     const bool rev = B.o_frame[orf] < 0;
     r.contig = (i32)c;

@@ -184,6 +184,9 @@ PB_HDNI Dec dec_div_u32(u32 a, u32 b, u64 magic, int prec) {
     return dec_round<5>(A, e, 0, prec, inexact);
 }
 PB_HD int contig_of_orf(const Batch& B, i64 oi) { return B.o_contig[oi]; }
+// The literal chain (S2..S5, hold, finish) works on SLOTS: slot s stands for ORF lit_ids[s] (or ORF s
+// when lit_all); its scratch arrays (o_lnx, o_A, o_lnA, o_fac, o_hf, o_bin, o_hold) are indexed by slot.
+PB_HD i64 orf_of_slot(const Batch& B, i64 s) { return B.lit_all ? s : (i64)B.lit_ids[s]; }
 // Stage 7a (split into small kernels: each keeps its instruction working set inside the I-cache).
 // S1: base composition -> pstop, x = 1 - pstop.  item = ORF
 PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
@@ -222,8 +225,9 @@ PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
     B.o_x[oi] = dec_sub(dec_one(), pstop);
 }
 // S2: ln(1 - pstop).  item = ORF
-PB_HDN void st_orf_lnx(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
+PB_HDN void st_orf_lnx(const Batch& B, i64 sl) {
+    if (sl >= B.nlit) return;
+    const i64 oi = orf_of_slot(B, sl);
     const Dec x = B.o_x[oi];
     SFx lnx;
     w_zero(lnx.m);
@@ -234,21 +238,22 @@ PB_HDN void st_orf_lnx(const Batch& B, i64 oi) {
         lnx = fx_ln(X, &o2);
         if (!(o1 && o2)) PB_ATOMIC_OR(&B.cs[contig_of_orf(B, oi)].err, (u32)ERR_RANGE);
     }
-    B.o_lnx[oi] = lnx;
+    B.o_lnx[sl] = lnx;
 }
 // S3: A_im = x ** pos_max[im] and ln(A_im).  item = (im-1)*no + ORF: a warp works on one exponent index, so
 // the "exponent is exactly 1 -> plain copy" case (one of the three per contig) does not split warps
 PB_HDN void st_orf_powA(const Batch& B, i64 item_in) {
-    if (item_in >= (i64)B.no * 3) return;
-    const i64 oi = item_in % B.no;
-    const int im = (int)(item_in / B.no) + 1;
-    const i64 item = oi * 3 + (im - 1);
+    if (item_in >= (i64)B.nlit * 3) return;
+    const i64 sl = item_in % B.nlit;
+    const i64 oi = orf_of_slot(B, sl);
+    const int im = (int)(item_in / B.nlit) + 1;
+    const i64 item = sl * 3 + (im - 1);
     const int c = contig_of_orf(B, oi);
     const CStat* cs = B.cs + c;
     const Dec x = B.o_x[oi];
     const bool xone = dec_is_one_abs(x);
     Dec A;
-    SFx lnA = B.o_lnx[oi];
+    SFx lnA = B.o_lnx[sl];
     bool ok = true;
     if (cs->max_one[im]) {
         A = x;                                                        // x ** Decimal(1) == x
@@ -268,27 +273,29 @@ PB_HDN void st_orf_powA(const Batch& B, i64 item_in) {
 }
 // S4: F_k = A_im ** pos_min[il].  item = k*no + ORF (same reason)
 PB_HDN void st_orf_powF(const Batch& B, i64 item_in) {
-    if (item_in >= (i64)B.no * 6) return;
-    const i64 oi = item_in % B.no;
-    const int k = (int)(item_in / B.no);
-    const i64 item = oi * 6 + k;
+    if (item_in >= (i64)B.nlit * 6) return;
+    const i64 sl = item_in % B.nlit;
+    const i64 oi = orf_of_slot(B, sl);
+    const int k = (int)(item_in / B.nlit);
+    const i64 item = sl * 6 + k;
     const int im = k / 2 + 1;
     const int il = (k % 2) + 1 + (((k % 2) + 1 >= im) ? 1 : 0);      // inverse of fac_index
     const int c = contig_of_orf(B, oi);
     const CStat* cs = B.cs + c;
-    const Dec A = B.o_A[oi * 3 + (im - 1)];
+    const Dec A = B.o_A[sl * 3 + (im - 1)];
     Dec f;
     bool ok = true;
     if (cs->min_one[il]) f = A;
     else if (dec_is_one_abs(A)) f = dec_pow_fx(A, cs->fmin[il], 0, PB_PREC, &ok);
-    else f = dec_pow_ln(B.o_lnA[oi * 3 + (im - 1)], cs->fmin[il], PB_PREC, &ok);
+    else f = dec_pow_ln(B.o_lnA[sl * 3 + (im - 1)], cs->fmin[il], PB_PREC, &ok);
     if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
     B.o_fac[item] = f;
 }
 // S5: prepared factors, length bin, histogram for the counting sort.  item = ORF
 PB_HDN void st_orf_prepare(const Batch& B, i64 item) {
-    const i64 oi = item / 6;
-    if (oi >= B.no) return;
+    const i64 sl = item / 6;
+    if (sl >= B.nlit) return;
+    const i64 oi = orf_of_slot(B, sl);
     const int k = (int)(item % 6);
     HoldFac hf;
     holdfac_prepare(B.o_fac[item], hf);
@@ -304,20 +311,21 @@ PB_HDN void st_orf_prepare(const Batch& B, i64 item) {
         const bool rev = B.o_frame[oi] < 0;
         int n = orf_steps(B.o_start[oi], B.o_stop[oi], rev);
         int bin = n < HOLD_BINS - 1 ? n : HOLD_BINS - 1;
-        B.o_bin[oi] = (unsigned short)bin;
+        B.o_bin[sl] = (unsigned short)bin;
         PB_ATOMIC_ADD(&B.len_hist[HOLD_BINS - 1 - bin], 1u);          // reversed: longest ORFs first
     }
 }
-PB_HDN void st_len_scatter(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
-    int bin = B.o_bin[oi];
+PB_HDN void st_len_scatter(const Batch& B, i64 sl) {
+    if (sl >= B.nlit) return;
+    int bin = B.o_bin[sl];
     u32 pos = PB_ATOMIC_ADD_RET(&B.len_cursor[HOLD_BINS - 1 - bin], 1u);
-    B.o_order[B.len_hist[HOLD_BINS - 1 - bin] + pos] = (i32)oi;
+    B.o_order[B.len_hist[HOLD_BINS - 1 - bin] + pos] = (i32)sl;
 }
 
-// Stage 7b+c: the per-codon product and Orf.score() of ORF oi.  S holds this ORF's six HoldFac as
+// Stage 7b+c: the per-codon product of the ORF in slot sl.  S holds its six HoldFac as
 // 18 U4 words with stride BD (shared memory on the GPU: S[(k*3+v)*BD + t]).
-PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
+PB_HDN void hold_run(const Batch& B, i32 sl, const U4* S, int BD, int t) {
+    const i64 oi = orf_of_slot(B, sl);
     const int c = contig_of_orf(B, oi);
     const u8* meta = B.meta + B.coff[c];
     const int start = B.o_start[oi], stop = B.o_stop[oi];
@@ -335,7 +343,7 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
     const Wide<4> lo27 = w_pow10<4>(27);
     while (it < n && !(fastok && hold.c.w[3] == 0 && w_cmp(hold.c, lo27) >= 0)) {
         const int k = (meta[b - 1] >> sh) & 7;
-        hold = dec_mul(hold, B.o_fac[(i64)oi * 6 + k]);             // functions.py:293,298
+        hold = dec_mul(hold, B.o_fac[(i64)sl * 6 + k]);             // functions.py:293,298
         it++;
         b += step;
     }
@@ -365,7 +373,7 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
             h.c.w[3] = 0;
             h.e = eh;
             h.neg = 0;
-            h = dec_mul(h, B.o_fac[(i64)oi * 6 + kcur]);
+            h = dec_mul(h, B.o_fac[(i64)sl * 6 + kcur]);
             a0 = h.c.w[0];
             a1 = h.c.w[1];
             a2 = h.c.w[2];
@@ -378,14 +386,15 @@ PB_HDN void hold_run(const Batch& B, i32 oi, const U4* S, int BD, int t) {
         hold.e = eh;
         hold.neg = 0;
     }
-    B.o_hold[oi] = hold;
+    B.o_hold[sl] = hold;
 }
 // Stage 7c: Orf.score (orfs.py:122-127): weight = -(1/hold * start-codon weight * Decimal(str(weight_rbs))).  item = ORF
-PB_HDN void st_orf_finish(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
+PB_HDN void st_orf_finish(const Batch& B, i64 sl) {
+    if (sl >= B.nlit) return;
+    const i64 oi = orf_of_slot(B, sl);
     const int c = contig_of_orf(B, oi);
     CStat* cs = B.cs + c;
-    Dec sc = dec_div(dec_one(), B.o_hold[oi]);
+    Dec sc = dec_div(dec_one(), B.o_hold[sl]);
     int sw = B.o_sw[oi];
     if (sw >= 0) sc = dec_mul(sc, B.P.startw[sw]);
     sc = dec_mul(sc, cs->wrbs[B.o_rbs[oi]]);
@@ -394,4 +403,5 @@ PB_HDN void st_orf_finish(const Batch& B, i64 oi) {
     WInt wi;
     if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
     B.o_wint[oi] = wi;
+    B.o_lit[oi] = 1;
 }

@@ -12,6 +12,7 @@
 
 #include "../../include/phanotate_b200.h"
 #include "graph.cuh"
+#include "fast.cuh"
 
 static_assert(sizeof(pb200_dec) == sizeof(Dec), "Dec layout");
 static_assert(sizeof(pb200_call) == sizeof(CallRec), "CallRec layout");
@@ -19,7 +20,7 @@ static_assert(sizeof(pb200_edge) == sizeof(EdgeRec), "EdgeRec layout");
 static_assert(sizeof(pb200_orf) == sizeof(OrfRec), "OrfRec layout");
 static_assert(sizeof(pb200_node) == sizeof(NodeRec), "NodeRec layout");
 
-#define NPHASE 8
+#define NPHASE 12
 
 #ifndef PB_HOSTSIM
 // ================================================================================================
@@ -67,6 +68,11 @@ PB_KERNEL(st_br_count)
 PB_KERNEL(st_br_fill)
 PB_KERNEL(st_backtrack)
 PB_KERNEL(st_gather_calls)
+PB_KERNEL(st_call_orf)
+PB_KERNEL(st_fast_tables)
+PB_KERNEL(st_orf_fast)
+PB_KERNEL(st_lit_calls)
+PB_KERNEL(st_lit_rest)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 
@@ -82,12 +88,12 @@ __global__ void __launch_bounds__(PB_BLOCK) k_solve(const Batch B, i32 nc) {
 __global__ void __launch_bounds__(PB_BLOCK) k_hold(const Batch B) {
     __shared__ U4 S[18 * PB_BLOCK];
     const int t = threadIdx.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + t; i < B.no; i += (i64)gridDim.x * blockDim.x) {
-        const i32 oi = B.o_order[i];
-        const U4* src = (const U4*)(B.o_hf + (i64)oi * 6);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + t; i < B.nlit; i += (i64)gridDim.x * blockDim.x) {
+        const i32 sl = B.o_order[i];
+        const U4* src = (const U4*)(B.o_hf + (i64)sl * 6);
 #pragma unroll
         for (int j = 0; j < 18; j++) S[j * PB_BLOCK + t] = src[j];
-        hold_run(B, oi, S, PB_BLOCK, t);
+        hold_run(B, sl, S, PB_BLOCK, t);
     }
 }
 __global__ void __launch_bounds__(PB_BLOCK) k_reach(const Batch B, i32 nc) {
@@ -477,6 +483,52 @@ static int make_params(pb200_ctx* ctx, const pb200_params* in, Params* P) {
     return 0;
 }
 
+// The literal chain (hold.cuh) over the first nlit entries of B.lit_ids (or over every ORF when B.lit_all):
+// the six Decimal factors per ORF, the per-codon product replayed multiplication by multiplication, Orf.score().
+#define ALN(x) (((size_t)(x) + 255) & ~(size_t)255)
+static int literal_chain(pb200_ctx* ctx, i32 nlit) {
+    Batch& B = ctx->B;
+    B.nlit = nlit;
+    if (nlit <= 0) return 0;
+    const size_t m = (size_t)nlit + 1;
+    PB_PHASE(8, ALN(m * 6 * sizeof(Dec)) + ALN(m * 6 * sizeof(HoldFac)) + ALN(m * sizeof(Dec)) + ALN(m * sizeof(SFx)) +
+                    ALN(m * 3 * sizeof(Dec)) + ALN(m * 3 * sizeof(SFx)) + ALN(m * 2) + ALN(m * 4) + 2 * ALN((HOLD_BINS + 1) * 4) + 4096);
+    B.o_fac = PB_ALLOC(8, Dec, m * 6);
+    B.o_hf = PB_ALLOC(8, HoldFac, m * 6);
+    B.o_hold = PB_ALLOC(8, Dec, m);
+    B.o_lnx = PB_ALLOC(8, SFx, m);
+    B.o_A = PB_ALLOC(8, Dec, m * 3);
+    B.o_lnA = PB_ALLOC(8, SFx, m * 3);
+    B.o_bin = PB_ALLOC(8, unsigned short, m);
+    B.o_order = PB_ALLOC(8, i32, m);
+    B.len_hist = PB_ALLOC(8, u32, HOLD_BINS + 1);
+    B.len_cursor = PB_ALLOC(8, u32, HOLD_BINS + 1);
+    PB_ZERO(B.len_hist, (HOLD_BINS + 1) * 4);
+    PB_ZERO(B.len_cursor, (HOLD_BINS + 1) * 4);
+    PB_RUN(st_orf_lnx, nlit);
+    PB_RUN(st_orf_powA, (i64)nlit * 3);
+    PB_RUN(st_orf_powF, (i64)nlit * 6);
+    PB_RUN(st_orf_prepare, (i64)nlit * 6);
+    PB_SCAN32(B.len_hist, HOLD_BINS);
+    PB_RUN(st_len_scatter, nlit);
+    PB_RUN_HOLD(nlit);
+    PB_RUN(st_orf_finish, nlit);
+    return 0;
+}
+#undef ALN
+// Decimal weight of every ORF that still lacks one (after a certified run; pb200_get_orfs, pb200_build_edges)
+static int ensure_literal_orfs(pb200_ctx* ctx) {
+    Batch& B = ctx->B;
+    if (B.lit_all || B.lit_done || B.no < 1) return 0;
+    PB_ZERO(B.lit_cnt + 1, 4);
+    PB_RUN(st_lit_rest, B.no);
+    u32 cnt;
+    PB_FETCH(&cnt, B.lit_cnt + 1, 4);
+    if (literal_chain(ctx, (i32)cnt)) return -1;
+    B.lit_done = 1;
+    return 0;
+}
+
 static int run_pipeline(pb200_ctx* ctx) {
     Batch& B = ctx->B;
 #include "driver.inc"
@@ -540,6 +592,7 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     int rc = make_params(ctx, params, &B.P);
     if (rc) return rc;
     B.nc = n_contigs;
+    B.flags = (i32)flags;
 #ifndef PB_HOSTSIM
     CK(cudaSetDevice(ctx->device));
     ctx->times.clear();
@@ -660,6 +713,22 @@ int pb200_sizes(pb200_ctx* ctx, int64_t out[8]) {
     return 0;
 }
 
+int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
+    if (!ctx || !ctx->have) return -2;
+    const Batch& B = ctx->B;
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[0] = B.lit_all ? B.no : B.n_lit_pre;
+    out[1] = B.lit_all ? 0 : B.n_lit_post;
+    out[2] = B.novlit;
+    return 0;
+}
+
+int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out) {
+    if (!ctx || !ctx->have) return -2;
+    if (ctx->B.no > 0) PB_TO_HOST(out, ctx->B.o_wint, (size_t)ctx->B.no * sizeof(WInt));
+    return 0;
+}
+
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out) {
     if (!ctx || !ctx->have) return -2;
     if (ctx->B.ncalls > 0) PB_TO_HOST(out, ctx->B.calls, (size_t)ctx->B.ncalls * sizeof(CallRec));
@@ -704,6 +773,7 @@ int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out) {
     if (!ctx || !ctx->have) return -2;
     Batch& B = ctx->B;
     if (B.no < 1) return 0;
+    if (ensure_literal_orfs(ctx)) return -1;
     PB_PHASE(6, (size_t)B.no * sizeof(OrfRec) + 1024);
     OrfRec* tmp = PB_ALLOC(6, OrfRec, B.no);
 #ifndef PB_HOSTSIM
@@ -737,6 +807,7 @@ int pb200_build_edges(pb200_ctx* ctx) {
     Batch& B = ctx->B;
     B.nedges = 0;
     if (B.nn < 1) return 0;
+    if (ensure_literal_orfs(ctx)) return -1;
     PB_PHASE(7, ((size_t)B.nn + 2) * 4 + 1024);
     B.ed_cnt = PB_ALLOC(7, u32, (size_t)B.nn + 1);
     PB_RUN(st_edge_count, B.nn);

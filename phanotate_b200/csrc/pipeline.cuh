@@ -57,7 +57,8 @@ struct CStat {
     Fx fmax[4], fmin[4];
     u8 max_one[4], min_one[4];
     i32 n_calls;
-    i32 pad;
+    i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
+    Fx fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
 };
 
@@ -151,6 +152,8 @@ struct Batch {
     u64* bT;
     u64* mNS;             // bit set where a start node sits
     u64* mNK;             // bit set where a stop-key node sits
+    u64* cF[5];           // bit set where the forward codon starting here has GC-frame factor index k (k = 5: the rest)
+    u64* cR[5];           // same for the reverse strand
     // node-parallel fill / ORF scoring split
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
     Dec* o_hold;          // [no] product over the codons (functions.py:286-298)
@@ -166,6 +169,18 @@ struct Batch {
     i32* o_order;         // [no] ORF ids sorted by codon count, longest first
     i32* ov_src;          // [nov]
     u8* ov_diff;          // [nov]
+    // certified integer weights (fast.cuh): ORFs / overlap edges whose 28-digit Decimal weight is still owed
+    i32 nlit;             // entries of lit_ids the literal chain works on
+    i32 lit_all;          // literal chain over every ORF (ids = slot)
+    i32* lit_ids;         // [<= no] ORF ids; NULL when lit_all
+    u32* lit_cnt;         // [4] device counters: 0 = ORFs sent to the literal chain before the solve, 1 = after, 2 = overlap edges
+    u8* o_lit;            // [no] 1 once o_weight / o_wint hold the literal 28-digit result
+    Fx* sw_fx;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
+    Fx* wr_fx;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
+    i32* ovlit_ids;       // [<= nov] overlap edges routed to the literal power
+    i32 novlit;
+    i32 n_lit_pre, n_lit_post;   // statistics of the last run
+    i32 lit_done;         // every ORF has its literal weight (lazy completion ran)
 };
 
 #ifdef __CUDA_ARCH__
@@ -378,8 +393,11 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
             cls = B.P.codon_cls[code[k] * 16 + code[k + 1] * 4 + code[k + 2]];
         int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
         // factor index of the codon starting here, forward strand in bits 0-2, reverse strand in bits 3-5
-        meta[i] = (u8)(TBL(gc_fac_index)[0][tr] | (TBL(gc_fac_index)[1][tr] << 3));
+        const int kf = TBL(gc_fac_index)[0][tr], kr = TBL(gc_fac_index)[1][tr];
+        meta[i] = (u8)(kf | (kr << 3));
         const u32 bit = 1u << (bitoff + k);
+        if (kf < 5) mk[8 + kf] |= bit;
+        if (kr < 5) mk[13 + kr] |= bit;
         if (cls) mk[cls - 1] |= bit;                 // S, s, T, t
         if (code[k] < 4) mk[4 + code[k]] |= bit;     // a, c, g, t
         // RBS background, both strands
@@ -418,7 +436,8 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
     i64 gend = g + SCAN_STRIP;
     if (gend > B.nb) gend = B.nb;
     int c = contig_of(B, g);
-    u32 mk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 mk[18];
+    for (int k = 0; k < 18; k++) mk[k] = 0;
     const i64 g0 = g;
     while (g < gend) {
         while (B.coff[c + 1] <= g) c++;
@@ -438,6 +457,10 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
     ((u32*)B.bC)[strip] = mk[5];
     ((u32*)B.bG)[strip] = mk[6];
     ((u32*)B.bT)[strip] = mk[7];
+    for (int k = 0; k < 5; k++) {
+        ((u32*)B.cF[k])[strip] = mk[8 + k];
+        ((u32*)B.cR[k])[strip] = mk[13 + k];
+    }
 }
 
 #include "enum_fwd.inc"

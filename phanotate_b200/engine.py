@@ -79,6 +79,9 @@ class Result:
         self.contigs = np.zeros(self.n_contigs, dtype=N.CONTIG)
         engine._ck(engine.lib.pb200_get_contigs(engine.ctx, self.contigs.ctypes.data))
         self._orfs = self._nodes = self._edges = None
+        st = np.zeros(8, dtype=np.int64)
+        engine._ck(engine.lib.pb200_stats(engine.ctx, st.ctypes.data))
+        self.n_literal_presolve, self.n_literal_postsolve, self.n_literal_overlaps = (int(v) for v in st[:3])
         self.launches = int(engine.lib.pb200_launch_count(engine.ctx))
         self.stage_ms = engine._stage_times()
 
@@ -106,6 +109,18 @@ class Result:
             self._edges = np.zeros(int(sz[7]), dtype=N.EDGE)
             self._e._ck(self._e.lib.pb200_get_edges(self._e.ctx, self._edges.ctypes.data))
         return self._edges
+
+    def orf_int_weights(self):
+        """trunc(Orf.weight*1000) per ORF as Python ints -- what the solver used (request before .orfs)."""
+        raw = np.zeros((self.n_orfs, 8), dtype=np.uint32)
+        self._e._ck(self._e.lib.pb200_get_orf_int_weights(self._e.ctx, raw.ctypes.data))
+        out = []
+        for row in raw:
+            v = 0
+            for k in range(7, -1, -1):
+                v = (v << 32) | int(row[k])
+            out.append(v - (1 << 256) if v >> 255 else v)
+        return out
 
     def fetch_all(self):
         self.orfs, self.nodes, self.edges
@@ -171,18 +186,22 @@ class Engine:
             out[k] = out.get(k, 0.0) + float(ms[i])
         return out
 
-    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True):
+    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False):
         """bases: uint8 array of concatenated contigs, offsets: int64[n+1].
 
         resident=True reuses the batch the previous call uploaded (inputs already in HBM).
         fetch=False skips copying the result tables to the host (returns None).
+        literal=True replays the reference's Decimal arithmetic for every ORF and overlap edge inside the
+        run (PB200_LITERAL); by default the solve runs on certified integer weights and Decimal weights are
+        produced for the calls, and lazily for the ORF table / edge dump.  Results are identical.
         """
         if params is None:
             params = make_params()
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
-                                    params.ctypes.data, N.REUSE_INPUT if resident else 0))
+                                    params.ctypes.data,
+                                    (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0)))
         return Result(self, names) if fetch else None
 
     def last_run_ms(self) -> float:
@@ -199,9 +218,9 @@ class Engine:
     def unpin(self, arr: np.ndarray):
         return self.lib.pb200_unpin_host(arr.ctypes.data) == 0
 
-    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None) -> Result:
+    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False) -> Result:
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         offs = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum([len(s) for s in seqs], out=offs[1:])
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
-        return self.run_packed(bases, offs, params, names)
+        return self.run_packed(bases, offs, params, names, literal=literal)

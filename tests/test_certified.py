@@ -1,0 +1,106 @@
+"""The certified integer weights (csrc/fast.cuh) against the literal Decimal chain.
+
+The solve only needs trunc(weight*1000) per edge (edges.py:22).  By default pb200_run decides that
+integer from a closed form with a rigorous error bound and replays the reference's Decimal
+arithmetic only where it is owed; PB200_LITERAL replays it for everything.  These tests check, on
+the host build of the same stage functions, that both modes give identical integers, calls and
+Decimal weights, and (with the oracle) that the error bound used by the filter really holds."""
+import decimal
+import os
+import subprocess
+from decimal import Decimal
+
+import pytest
+
+from phanotate_b200 import _native as N
+from phanotate_b200 import engine
+from helpers import STRESS, golden_text, seq_of
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HOSTSIM = os.path.join(ROOT, "tests", "native", "pb200_hostsim.so")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    src = os.path.join(ROOT, "phanotate_b200", "csrc")
+    deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "phanotate_b200.h")]
+    if not os.path.exists(HOSTSIM) or any(os.path.getmtime(d) > os.path.getmtime(HOSTSIM) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-DPB_HOSTSIM", "-shared", "-fPIC",
+                               "-o", HOSTSIM, os.path.join(src, "pb200.cu")])
+    e = engine.Engine(0, lib_path=HOSTSIM)
+    yield e
+    e.close()
+
+
+def _calls(res, k):
+    return "".join("%d\t%d\t%s\t%s\n" % r for r in res.call_rows(k))
+
+
+def _both(sim, seqs):
+    fast = sim.run(seqs)
+    wf = fast.orf_int_weights()                       # before .orfs triggers the lazy literal completion
+    lit = sim.run(seqs, literal=True)
+    return fast, wf, lit, lit.orf_int_weights()
+
+
+@pytest.mark.parametrize("name", ["phiX174", "lambda", "T4", "synth4_0", "synth4_1"])
+def test_certified_integers_equal_literal(sim, name):
+    fast, wf, lit, wl = _both(sim, [seq_of(name)])
+    assert wf == wl
+    assert _calls(fast, 0) == _calls(lit, 0) == golden_text(name, "calls.tsv")
+    assert [str(N.dec_to_decimal(r["weight"])) for r in fast.calls] == [str(N.dec_to_decimal(r["weight"])) for r in lit.calls]
+    assert lit.n_literal_presolve == lit.n_orfs
+    # the filter must actually filter: almost every ORF is decided without the literal chain
+    assert fast.n_literal_presolve <= max(2, fast.n_orfs // 20)
+    assert fast.n_literal_presolve + fast.n_literal_postsolve >= fast.n_calls
+
+
+def test_certified_stress_batch(sim):
+    seqs = [seq_of(n) for n in STRESS]
+    fast, wf, lit, wl = _both(sim, seqs)
+    assert wf == wl
+    for k, name in enumerate(STRESS):
+        assert _calls(fast, k) == golden_text(name, "calls.tsv"), name
+
+
+def test_integer_is_trunc_of_weight_times_1000(sim):
+    res = sim.run([seq_of("lambda")])
+    wf = res.orf_int_weights()
+    for w, o in zip(wf, res.orfs):                    # .orfs completes the Decimal weights lazily
+        d = N.dec_to_decimal(o["weight"])
+        with decimal.localcontext() as ctx:
+            ctx.prec = 80
+            assert w == int(d * 1000)                 # edges.py:22; int() truncates toward zero
+
+
+def test_closed_form_error_bound_holds_on_reference_weights():
+    """|W_ref / W_closed_form - 1| <= (2.51 n + 1.51) 1e-27 (fast.cuh header), checked with the oracle's
+    literal weights at 90 digits on phiX174 and lambda."""
+    from oracle import phanotate_oracle as O
+    worst = Decimal(0)
+    for name in ("phiX174", "lambda"):
+        orfs = O.get_orfs(seq_of(name))
+        T, pm, pn = orfs.T, orfs.pos_max, orfs.pos_min
+        sc = O.normalise_starts(O.DEFAULT_STARTS)
+        for o in orfs.iter_orfs():
+            fwd = o.frame > 0
+            rng = range(o.start, o.stop, 3 if fwd else -3)
+            cnt = {}
+            for base in rng:
+                a, b, c = int(T[base]), int(T[base + 1]), int(T[base + 2])
+                if not fwd:
+                    a, c = c, a
+                k = (O.max_idx(a, b, c), O.min_idx(a, b, c))
+                cnt[k] = cnt.get(k, 0) + 1
+            x = 1 - o.pstop                            # the literal 28-digit value
+            with decimal.localcontext() as ctx:
+                ctx.prec = 90
+                E = sum(Decimal(v) * pm[k[0]] * pn[k[1]] for k, v in cnt.items())
+                S = (-(E * x.ln())).exp()
+                if o.codon in sc:
+                    S *= sc[o.codon]
+                S *= Decimal(str(o.weight_rbs))
+                rel = abs((-o.weight) / S - 1)
+                bound = (Decimal("2.51") * len(rng) + Decimal("1.51")) * Decimal("1e-27")
+                worst = max(worst, rel / bound)
+    assert worst < Decimal("0.25")                    # observed: 0.03

@@ -72,3 +72,20 @@ def test_invalid_letter_sets_keyerror_bit(eng):
     with pytest.raises(KeyError):
         res.check(0)
     assert calls_text(res, 1) == golden_text("phiX174", "calls.tsv")
+
+
+def test_certified_integers_equal_literal_on_gpu(eng):
+    """Default mode (certified integer weights, fast.cuh) vs PB200_LITERAL on 48 synthetic 50-kb contigs + fixtures:
+    the integers the solver sees, the calls and the Decimal weights of the calls are identical."""
+    from phanotate_b200 import synth
+    seqs = [synth.synth4_contig(k) for k in range(48)] + [seq_of(n).encode() for n in ("T4", "lambda", "phiX174")]
+    fast = eng.run(seqs)
+    wf = fast.orf_int_weights()
+    lit = eng.run(seqs, literal=True)
+    wl = lit.orf_int_weights()
+    assert wf == wl
+    assert fast.n_literal_presolve < fast.n_orfs // 20 and lit.n_literal_presolve == lit.n_orfs
+    assert np.array_equal(fast.calls, lit.calls)
+    assert int((fast.contigs["err"] != 0).sum()) == 0
+    # lazy completion gives the same ORF table as the literal run
+    assert np.array_equal(fast.orfs, lit.orfs)
