@@ -131,6 +131,9 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]);
 /* the integer weight the solver used for every ORF edge: trunc(Orf.weight * 1000) (edges.py:22) as
  * 8 little-endian 32-bit limbs, two's complement, per ORF */
 int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out);
+/* the same for every overlap edge (n_overlap_edges entries, in edge order): trunc(score_overlap * 1000),
+ * INT64_MAX where it needs more than 62 bits (the solver then uses the wide value) */
+int pb200_get_overlap_int_weights(pb200_ctx* ctx, int64_t* out);
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out);
 int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out);
 int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out);

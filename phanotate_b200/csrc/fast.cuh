@@ -160,3 +160,143 @@ PB_HDN void st_lit_rest(const Batch& B, i64 oi) {
         B.o_lit[oi] = 2;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Overlap edges (functions.py:26-34,140-141,386): weight = 1/o**len (+20 if 'diff'), o = 1 - ave([o1,o2]).
+// Closed form in double-double arithmetic (two IEEE doubles, ~2^-104 per operation):
+//     W_true = (1 - (o1+o2)/2) ** -len  (+ 20)
+// Roundings of the reference, each of relative size <= 0.5e-27 of its result:
+//     o1+o2, /2, 1-pbar      -> |o_ref - o_true| <= 1.001e-27, i.e. <= 2.01e-27 relative for o >= 0.5,
+//                               amplified by len <= 502 in the power                 -> 1.01e-24
+//     _mpd_qpow_int at 33 digits (<= 16 products) + rounding to 28, 1/x, + 20          -> 1.52e-27
+// total <= 1.02e-24 < 2^-79.6; the double-double evaluation adds < 2^-87.  The integer
+// trunc(W*1000) is accepted when W*1000 (1 +- 2^-79) does not straddle an integer; else the literal
+// chain (st_ov_pbar/pow/weight) computes it.
+struct DD {
+    double hi, lo;
+};
+PB_HD double pb_fma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+PB_HD DD dd_two_sum(double a, double b) {
+    DD r;
+    r.hi = a + b;
+    const double bb = r.hi - a;
+    r.lo = (a - (r.hi - bb)) + (b - bb);
+    return r;
+}
+PB_HD DD dd_quick(double a, double b) {      // |a| >= |b|
+    DD r;
+    r.hi = a + b;
+    r.lo = b - (r.hi - a);
+    return r;
+}
+PB_HD DD dd_add(const DD& a, const DD& b) {
+    DD s = dd_two_sum(a.hi, b.hi);
+    const DD t = dd_two_sum(a.lo, b.lo);
+    s.lo += t.hi;
+    s = dd_quick(s.hi, s.lo);
+    s.lo += t.lo;
+    return dd_quick(s.hi, s.lo);
+}
+PB_HD DD dd_mul(const DD& a, const DD& b) {
+    const double p = a.hi * b.hi;
+    double e = pb_fma(a.hi, b.hi, -p);
+    e = pb_fma(a.hi, b.lo, e);
+    e = pb_fma(a.lo, b.hi, e);
+    return dd_quick(p, e);
+}
+PB_HD DD dd_mul_d(const DD& a, double b) {
+    const double p = a.hi * b;
+    double e = pb_fma(a.hi, b, -p);
+    e = pb_fma(a.lo, b, e);
+    return dd_quick(p, e);
+}
+PB_HD DD dd_from_d(double v) {
+    DD r;
+    r.hi = v;
+    r.lo = 0.0;
+    return r;
+}
+PB_HD DD dd_recip(const DD& b) {             // 1/b with two correction steps
+    const double q1 = 1.0 / b.hi;
+    DD t = dd_mul_d(b, q1);
+    t.hi = -t.hi;
+    t.lo = -t.lo;
+    DD r = dd_add(dd_from_d(1.0), t);
+    const double q2 = r.hi / b.hi;
+    t = dd_mul_d(b, q2);
+    t.hi = -t.hi;
+    t.lo = -t.lo;
+    r = dd_add(r, t);
+    const double q3 = r.hi / b.hi;
+    DD q = dd_quick(q1, q2);
+    return dd_add(q, dd_from_d(q3));
+}
+// non-negative Dec with a coefficient below 2^96 and exponent in (-PB_NP10DD, 0] -> DD
+PB_HD bool dd_from_dec(const Dec& d, DD& out) {
+    out = dd_from_d(0.0);
+    if (dec_is_zero(d)) return true;
+    if (d.neg || d.c.w[3] != 0 || d.e > 0 || -d.e >= PB_NP10DD) return false;
+    const double a = (double)d.c.w[2] * 18446744073709551616.0, b = (double)d.c.w[1] * 4294967296.0, c = (double)d.c.w[0];
+    DD s = dd_two_sum(a, b);
+    const DD t = dd_two_sum(s.hi, c);
+    const DD cc = dd_quick(t.hi, s.lo + t.lo);          // exact: the coefficient has at most 96 bits
+    DD p;
+    p.hi = TBL(p10neg_dd)[-d.e][0];
+    p.lo = TBL(p10neg_dd)[-d.e][1];
+    out = dd_mul(cc, p);
+    return true;
+}
+
+// Certified integer weight of overlap edge k, or a slot in the literal list.  item = overlap edge
+PB_HDN void st_ov_fast(const Batch& B, i64 k) {
+    if (k >= B.nov) return;
+    const i32 x = B.ov_src[k], e = B.ov_dst[k];
+    const int c = contig_of_node(B, x);
+    const int len = B.n_pos[x] - B.n_pos[e] + 3;
+    DD o1, o2;
+    bool fast = dd_from_dec(node_o(B, c, e), o1) && dd_from_dec(node_o(B, c, x), o2) && len >= 1 && len <= 502;
+    i64 I = 0;
+    if (fast) {
+        DD pbar = dd_add(o1, o2);
+        pbar.hi *= 0.5;
+        pbar.lo *= 0.5;
+        pbar.hi = -pbar.hi;
+        pbar.lo = -pbar.lo;
+        const DD o = dd_add(dd_from_d(1.0), pbar);
+        if (!(o.hi >= 0.5 && o.hi <= 1.0)) fast = false;
+        else {
+            int top = 31;
+            while (!((u32)len >> top)) top--;
+            DD r = o;
+            for (int b = top - 1; b >= 0; b--) {
+                r = dd_mul(r, r);
+                if ((len >> b) & 1) r = dd_mul(r, o);
+            }
+            DD w = dd_mul_d(dd_recip(r), 1000.0);
+            if (B.ov_diff[k]) w = dd_add(w, dd_from_d(20000.0));
+            if (!(w.hi >= 1.0 && w.hi < 4.0e18)) fast = false;
+            else {
+                const double ih = floor(w.hi), il = floor(w.lo);
+                double f = (w.hi - ih) + (w.lo - il);
+                I = (i64)ih + (i64)il;
+                if (f >= 1.0) {
+                    I += 1;
+                    f -= 1.0;
+                }
+                const double thr = w.hi * 1.6543612251060553e-24 + 8.8817841970012523e-16;   // 2^-79, 2^-50
+                if (!(f >= thr && f <= 1.0 - thr)) fast = false;
+            }
+        }
+    }
+    if (fast) B.ov_w64[k] = I;
+    else {
+        const u32 pos = PB_ATOMIC_ADD_RET(&B.lit_cnt[2], 1u);
+        B.ovlit_ids[pos] = (i32)k;
+    }
+}

@@ -120,29 +120,38 @@ PB_HDN void st_ov_fill(const Batch& B, i64 ni) {
 //   pow:    o ** Decimal(r-l+3), a 33-digit square-and-multiply (functions.py:30)
 //   weight: 1/score (+ 1/0.05 if 'diff'), integer weight (functions.py:31-34)
 // item = overlap edge
-PB_HDN void st_ov_pbar(const Batch& B, i64 k) {
-    if (k >= B.nov) return;
+// The chain works on SLOTS: slot sl stands for edge ovlit_ids[sl] (or edge sl when ov_all); ov_w[] is per slot.
+PB_HD i64 edge_of_slot(const Batch& B, i64 sl) { return B.ov_all ? sl : (i64)B.ovlit_ids[sl]; }
+PB_HDN void st_ov_pbar(const Batch& B, i64 sl) {
+    if (sl >= B.novlit) return;
+    const i64 k = edge_of_slot(B, sl);
     const i32 x = B.ov_src[k], e = B.ov_dst[k];
     const int c = contig_of_node(B, x);
     Dec t = dec_add(dec_from_u64(0), node_o(B, c, e));
     t = dec_add(t, node_o(B, c, x));
     Dec pbar = dec_div(t, dec_from_u64(2));
-    B.ov_w[k] = dec_sub(dec_one(), pbar);
+    B.ov_w[sl] = dec_sub(dec_one(), pbar);
 }
-PB_HDN void st_ov_pow(const Batch& B, i64 k) {
-    if (k >= B.nov) return;
+PB_HDN void st_ov_pow(const Batch& B, i64 sl) {
+    if (sl >= B.novlit) return;
+    const i64 k = edge_of_slot(B, sl);
     const i32 x = B.ov_src[k], e = B.ov_dst[k];
-    B.ov_w[k] = dec_powi(B.ov_w[k], (u32)(B.n_pos[x] - B.n_pos[e] + 3));
+    B.ov_w[sl] = dec_powi(B.ov_w[sl], (u32)(B.n_pos[x] - B.n_pos[e] + 3));
 }
-PB_HDN void st_ov_weight(const Batch& B, i64 k) {
-    if (k >= B.nov) return;
+PB_HDN void st_ov_weight(const Batch& B, i64 sl) {
+    if (sl >= B.novlit) return;
+    const i64 k = edge_of_slot(B, sl);
     const int c = contig_of_node(B, B.ov_src[k]);
-    Dec sc = dec_div(dec_one(), B.ov_w[k]);
+    Dec sc = dec_div(dec_one(), B.ov_w[sl]);
     if (B.ov_diff[k]) sc = dec_add(sc, dec_twenty());
-    B.ov_w[k] = sc;
+    B.ov_w[sl] = sc;
     WInt wi;
     if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
     B.ov_wint[k] = wi;
+    bool small = (wi.w[1] >> 30) == 0;               // 0 <= weight < 2^62 (overlap weights are positive)
+#pragma unroll
+    for (int i = 2; i < WN; i++) small = small && wi.w[i] == 0;
+    B.ov_w64[k] = small ? (i64)(((u64)wi.w[1] << 32) | wi.w[0]) : OV_W64_WIDE;
 }
 
 // Stage 11: bridges over uncovered runs longer than 500 bp (functions.py:320-354).
@@ -368,7 +377,9 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
             // overlap edges (backwards)
             for (u32 k = B.ov_cnt[u] + lane; k < B.ov_cnt[u + 1]; k += NL) {
                 WInt cand = Du;
-                w_add(cand, B.ov_wint[k]);
+                const i64 w64 = B.ov_w64[k];
+                if (w64 != OV_W64_WIDE) w_add(cand, wint_from_i64(w64));
+                else w_add(cand, B.ov_wint[k]);
                 i32 v = B.ov_dst[k];
                 if (relax(B, S, v, cand, u) && v < rewind) rewind = v;
             }

@@ -73,6 +73,7 @@ PB_KERNEL(st_fast_tables)
 PB_KERNEL(st_orf_fast)
 PB_KERNEL(st_lit_calls)
 PB_KERNEL(st_lit_rest)
+PB_KERNEL(st_ov_fast)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 
@@ -516,6 +517,24 @@ static int literal_chain(pb200_ctx* ctx, i32 nlit) {
     return 0;
 }
 #undef ALN
+// score_overlap replayed in Decimal arithmetic over the first n entries of B.ovlit_ids (or every edge when B.ov_all)
+static int overlap_chain(pb200_ctx* ctx, i32 n) {
+    Batch& B = ctx->B;
+    B.novlit = n;
+    if (n <= 0) return 0;
+    PB_PHASE(10, ((size_t)n + 1) * sizeof(Dec) + 1024);
+    B.ov_w = PB_ALLOC(10, Dec, (size_t)n + 1);
+    PB_RUN(st_ov_pbar, n);
+    PB_RUN(st_ov_pow, n);
+    PB_RUN(st_ov_weight, n);
+    return 0;
+}
+static int ensure_literal_overlaps(pb200_ctx* ctx) {
+    Batch& B = ctx->B;
+    if (B.ov_all || B.nov < 1) return 0;
+    B.ov_all = 1;
+    return overlap_chain(ctx, B.nov);
+}
 // Decimal weight of every ORF that still lacks one (after a certified run; pb200_get_orfs, pb200_build_edges)
 static int ensure_literal_orfs(pb200_ctx* ctx) {
     Batch& B = ctx->B;
@@ -719,13 +738,19 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
     for (int i = 0; i < 8; i++) out[i] = 0;
     out[0] = B.lit_all ? B.no : B.n_lit_pre;
     out[1] = B.lit_all ? 0 : B.n_lit_post;
-    out[2] = B.novlit;
+    out[2] = (B.flags & PB200_LITERAL) ? B.nov : B.n_ovlit;
     return 0;
 }
 
 int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out) {
     if (!ctx || !ctx->have) return -2;
     if (ctx->B.no > 0) PB_TO_HOST(out, ctx->B.o_wint, (size_t)ctx->B.no * sizeof(WInt));
+    return 0;
+}
+
+int pb200_get_overlap_int_weights(pb200_ctx* ctx, int64_t* out) {
+    if (!ctx || !ctx->have) return -2;
+    if (ctx->B.nov > 0) PB_TO_HOST(out, ctx->B.ov_w64, (size_t)ctx->B.nov * 8);
     return 0;
 }
 
@@ -808,6 +833,7 @@ int pb200_build_edges(pb200_ctx* ctx) {
     B.nedges = 0;
     if (B.nn < 1) return 0;
     if (ensure_literal_orfs(ctx)) return -1;
+    if (ensure_literal_overlaps(ctx)) return -1;
     PB_PHASE(7, ((size_t)B.nn + 2) * 4 + 1024);
     B.ed_cnt = PB_ALLOC(7, u32, (size_t)B.nn + 1);
     PB_RUN(st_edge_count, B.nn);

@@ -32,6 +32,7 @@ enum {
 #define GAPN 303          // gap lengths -2..300 (functions.py:36-46)
 #define WN 8              // limbs of the exact distances (256 bit)
 typedef Wide<WN> WInt;    // two's complement
+#define OV_W64_WIDE ((i64)0x7FFFFFFFFFFFFFFFll)      /* ov_w64 marker: the weight is in ov_wint[] */
 
 struct Params {
     u8 codon_cls[64];     // CLS_* with the reference's elif priority applied (functions.py:198-215)
@@ -178,8 +179,10 @@ struct Batch {
     Fx* sw_fx;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
     Fx* wr_fx;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
     i32* ovlit_ids;       // [<= nov] overlap edges routed to the literal power
+    i64* ov_w64;          // [nov] integer weight of the overlap edge, or OV_W64_WIDE -> ov_wint[]
+    i32 ov_all;           // literal overlap chain over every edge (slot = edge), ov_w[] indexed by edge
     i32 novlit;
-    i32 n_lit_pre, n_lit_post;   // statistics of the last run
+    i32 n_lit_pre, n_lit_post, n_ovlit;   // statistics of the last run
     i32 lit_done;         // every ORF has its literal weight (lazy completion ran)
 };
 

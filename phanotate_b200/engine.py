@@ -122,6 +122,12 @@ class Result:
             out.append(v - (1 << 256) if v >> 255 else v)
         return out
 
+    def overlap_int_weights(self):
+        """trunc(score_overlap*1000) per overlap edge (int64; INT64_MAX marks a wider value)."""
+        out = np.zeros(self.n_overlaps, dtype=np.int64)
+        self._e._ck(self._e.lib.pb200_get_overlap_int_weights(self._e.ctx, out.ctypes.data))
+        return out
+
     def fetch_all(self):
         self.orfs, self.nodes, self.edges
         return self

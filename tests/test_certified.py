@@ -10,6 +10,7 @@ import os
 import subprocess
 from decimal import Decimal
 
+import numpy as np
 import pytest
 
 from phanotate_b200 import _native as N
@@ -39,7 +40,10 @@ def _calls(res, k):
 def _both(sim, seqs):
     fast = sim.run(seqs)
     wf = fast.orf_int_weights()                       # before .orfs triggers the lazy literal completion
+    ovf = fast.overlap_int_weights()
     lit = sim.run(seqs, literal=True)
+    assert np.array_equal(ovf, lit.overlap_int_weights())
+    assert lit.n_literal_overlaps == lit.n_overlaps and fast.n_literal_overlaps <= max(2, fast.n_overlaps // 50)
     return fast, wf, lit, lit.orf_int_weights()
 
 

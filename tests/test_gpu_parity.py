@@ -81,7 +81,10 @@ def test_certified_integers_equal_literal_on_gpu(eng):
     seqs = [synth.synth4_contig(k) for k in range(48)] + [seq_of(n).encode() for n in ("T4", "lambda", "phiX174")]
     fast = eng.run(seqs)
     wf = fast.orf_int_weights()
+    ovf = fast.overlap_int_weights()
     lit = eng.run(seqs, literal=True)
+    assert np.array_equal(ovf, lit.overlap_int_weights())
+    assert fast.n_literal_overlaps < fast.n_overlaps // 50
     wl = lit.orf_int_weights()
     assert wf == wl
     assert fast.n_literal_presolve < fast.n_orfs // 20 and lit.n_literal_presolve == lit.n_orfs
