@@ -14,9 +14,13 @@
 //     factor  F_k = (x ** pos_max) ** pos_min   two Decimal powers, <= 1 ulp each, pos_min <= 1  -> 2.001e-27
 //     product hold *= F_k                       half an ulp per step                              -> 0.5e-27
 //     1/hold, * startw, * weight_rbs            half an ulp each                                  -> 1.5e-27
-// so |W_ref / W_true - 1| <= (2.51 n + 1.51) * 1e-27 for n codon steps (tests/test_filter_bound.py
-// measures the actual ratio on the golden ORF tables: <= 4 % of the bound).  We use (3n + 8) * 2^-89
-// (2^-89 = 1.6e-27), which also swallows the ~2^-170 relative error of the Q32.192 evaluation.
+// so |W_ref / W(x) - 1| <= (2.51 n + 1.51) * 1e-27 for n codon steps (tests/test_certified.py measures the
+// actual ratio on the golden ORF tables: <= 4 % of the bound).  x itself is not needed as a Decimal either:
+//     pstop_true = Pt Pa (Pa + 2 Pg) = nt na (na + 2 ng) / len^3             (orfs.py:162-173, exact rational)
+//     pstop_ref  = pstop_true (1 +- 3.51e-27)    three quotients, five products, two sums, half an ulp each
+//     x_ref      = x_true (1 +- 4.01e-27)        for x >= 1/2, incl. the rounding of 1 - pstop
+// and W = C x^-E with E <= n turns that into another 4.01 n e-27: total (6.52 n + 1.51) e-27.  We use
+// (7n + 8) * 2^-89 (2^-89 = 1.6e-27), which also swallows the ~2^-170 relative error of the Q32.192 evaluation.
 #pragma once
 #include "graph.cuh"
 
@@ -73,10 +77,46 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
     const bool rev = B.o_frame[oi] < 0;
     const int n = orf_steps(start, stop, rev);
     bool fast = cs->fast_ok && n > 0 && n < 100000;
-    const Dec x = B.o_x[oi];
     Wide<10> big;
     w_zero(big);
-    if (fast && (dec_is_one_abs(x) || dec_is_zero(x) || x.neg)) fast = false;
+    // x_true = 1 - pstop_true, pstop_true = Pt Pa (Pa + 2 Pg) = nt na (na + 2 ng) / len^3 exactly (orfs.py:162-173)
+    u32 na, nt, ng, len;
+    orf_base_counts(B, oi, na, nt, ng, len);
+    {
+        U4 cn;
+        cn.x = na;
+        cn.y = nt;
+        cn.z = ng;
+        cn.w = len;
+        B.o_cnt[oi] = cn;
+    }
+    Fx X;
+    w_zero(X);
+    if (len < 1 || len >= (1u << 17)) fast = false;
+    if (fast) {
+        const u64 num = (u64)nt * na * ((u64)na + 2ull * ng), den = (u64)len * len * len;
+        if (num == 0 || num >= den) fast = false;
+        else {
+            Wide<9> N, Q;
+            Wide<2> D, Rm;
+            w_zero(N);
+            N.w[6] = (u32)num;
+            N.w[7] = (u32)(num >> 32);
+            D.w[0] = (u32)den;
+            D.w[1] = (u32)(den >> 32);
+            w_divmod<9, 2>(N, D, Q, Rm);                       // floor(num * 2^192 / den) < 2^192
+            X = fx_one();
+            const Fx q = w_resize<FX_N>(Q);
+            w_sub(X, q);
+            if (!w_is_zero(Rm)) {                               // round the quotient up so that X <= x_true < X + 2^-192
+                Fx ulp;
+                w_zero(ulp);
+                ulp.w[0] = 1;
+                w_sub(X, ulp);
+            }
+            if (!(X.w[6] == 0 && (X.w[5] >> 31))) fast = false; // certified for 1/2 <= x < 1 only
+        }
+    }
     if (fast) {
         // codon counts per factor class over [start, stop) (forward) / (stop, start] (reverse), functions.py:289-298
         const i64 cb = B.coff[c];
@@ -93,8 +133,7 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
             w_mul_small(t, nk[k]);
             w_add(E, t);
         }
-        bool o1, o2, o3;
-        const Fx X = fx_from_dec(x, &o1);
+        bool o1 = true, o2, o3;
         const SFx lnx = fx_ln(X, &o2);
         SFx T;
         T.m = fx_mul(lnx.m, E);
@@ -120,7 +159,7 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
         I.w[3] = big.w[9];
         const u64 fr = ((u64)big.w[5] << 32) | big.w[4];       // top 64 bits of the fraction
         const int bl = w_bitlen(I) + 1;                        // |weight|*1000 < 2^bl
-        const u64 en = 3ull * (u64)n + 8ull;
+        const u64 en = 7ull * (u64)n + 8ull;
         u64 errU;                                              // error bound in units of 2^-64: en * 2^(bl-89) * 2^64
         if (bl > 68) fast = false;
         else {
@@ -166,11 +205,12 @@ PB_HDN void st_lit_rest(const Batch& B, i64 oi) {
 // Closed form in double-double arithmetic (two IEEE doubles, ~2^-104 per operation):
 //     W_true = (1 - (o1+o2)/2) ** -len  (+ 20)
 // Roundings of the reference, each of relative size <= 0.5e-27 of its result:
-//     o1+o2, /2, 1-pbar      -> |o_ref - o_true| <= 1.001e-27, i.e. <= 2.01e-27 relative for o >= 0.5,
-//                               amplified by len <= 502 in the power                 -> 1.01e-24
+//     o1, o2 themselves      -> pstop_ref = pstop_true (1 +- 3.51e-27) (above), pbar <= 1/2
+//     o1+o2, /2, 1-pbar      -> |o_ref - o_true| <= 1.001e-27 + 1.76e-27, i.e. <= 5.52e-27 relative for
+//                               o >= 0.5, amplified by len <= 502 in the power          -> 2.77e-24
 //     _mpd_qpow_int at 33 digits (<= 16 products) + rounding to 28, 1/x, + 20          -> 1.52e-27
-// total <= 1.02e-24 < 2^-79.6; the double-double evaluation adds < 2^-87.  The integer
-// trunc(W*1000) is accepted when W*1000 (1 +- 2^-79) does not straddle an integer; else the literal
+// total <= 2.78e-24 < 2^-78.2; the double-double evaluation adds < 2^-87.  The integer
+// trunc(W*1000) is accepted when W*1000 (1 +- 2^-78) does not straddle an integer; else the literal
 // chain (st_ov_pbar/pow/weight) computes it.
 struct DD {
     double hi, lo;
@@ -253,6 +293,20 @@ PB_HD bool dd_from_dec(const Dec& d, DD& out) {
     return true;
 }
 
+// pstop of the ORF behind node n as the exact rational nt na (na + 2 ng) / len^3 (counts left by st_orf_fast),
+// or the contig's Decimal pstop for a node without an ORF (functions.py:373-385)
+PB_HD bool dd_node_pstop(const Batch& B, int c, i32 n, DD& out) {
+    const i32 oi = B.n_oidx[n];
+    if (oi < 0) return dd_from_dec(B.cs[c].pstop, out);
+    const U4 cn = B.o_cnt[oi];
+    if (cn.w < 1 || cn.w >= (1u << 17)) return false;
+    const double num = (double)cn.y * (double)cn.x * ((double)cn.x + 2.0 * (double)cn.z);   // < 2^53: exact
+    const double den = (double)cn.w * (double)cn.w * (double)cn.w;                             // < 2^51: exact
+    const double q1 = num / den;
+    const double r = pb_fma(-q1, den, num);                                                    // exact remainder
+    out = dd_quick(q1, r / den);
+    return true;
+}
 // Certified integer weight of overlap edge k, or a slot in the literal list.  item = overlap edge
 PB_HDN void st_ov_fast(const Batch& B, i64 k) {
     if (k >= B.nov) return;
@@ -260,7 +314,7 @@ PB_HDN void st_ov_fast(const Batch& B, i64 k) {
     const int c = contig_of_node(B, x);
     const int len = B.n_pos[x] - B.n_pos[e] + 3;
     DD o1, o2;
-    bool fast = dd_from_dec(node_o(B, c, e), o1) && dd_from_dec(node_o(B, c, x), o2) && len >= 1 && len <= 502;
+    bool fast = dd_node_pstop(B, c, e, o1) && dd_node_pstop(B, c, x, o2) && len >= 1 && len <= 502;
     i64 I = 0;
     if (fast) {
         DD pbar = dd_add(o1, o2);
@@ -289,7 +343,7 @@ PB_HDN void st_ov_fast(const Batch& B, i64 k) {
                     I += 1;
                     f -= 1.0;
                 }
-                const double thr = w.hi * 1.6543612251060553e-24 + 8.8817841970012523e-16;   // 2^-79, 2^-50
+                const double thr = w.hi * 3.3087224502121107e-24 + 8.8817841970012523e-16;   // 2^-78, 2^-50
                 if (!(f >= thr && f <= 1.0 - thr)) fast = false;
             }
         }

@@ -74,7 +74,14 @@ PB_HD int overlap_kind(const Batch& B, i32 e, i32 x) {     // 0 none, 1 'same', 
     if (ke == K_FSTART && kx == K_RSTART) return (ro < l && r < lo) ? 2 : 0;
     return 0;
 }
-PB_HD Dec node_o(const Batch& B, int c, i32 n) { return B.n_oidx[n] < 0 ? B.cs[c].pstop : B.o_pstop[B.n_oidx[n]]; }
+// the pstop a node contributes to ave([o1,o2]) (functions.py:373-385); an ORF whose Decimal pstop has not been
+// materialised yet (certified run) gets it computed on the spot
+PB_HD Dec node_o(const Batch& B, int c, i32 n) {
+    const i32 oi = B.n_oidx[n];
+    if (oi < 0) return B.cs[c].pstop;
+    if (B.o_lit[oi] == 1) return B.o_pstop[oi];
+    return orf_pstop_dec(B, oi);
+}
 // score_overlap(r-l+3, dir, ave([o1,o2]))  (functions.py:26-34,140-141,386)
 PB_HDN Dec overlap_score(const Batch& B, int c, i32 e, i32 x, bool diff) {
     Dec t = dec_add(dec_from_u64(0), node_o(B, c, e));

@@ -20,13 +20,6 @@ struct HoldFac {      // one factor b (28 digits) prepared for the fast multiply
     i32 e;            // exponent of b
     u32 ok;           // 1 if b has exactly 28 digits (fast path usable)
 };
-#ifdef __CUDACC__
-typedef uint4 U4;
-#else
-struct U4 {
-    u32 x, y, z, w;
-};
-#endif
 #define HOLD_BINS 2048
 
 PB_HD int fac_index(int imax, int imin) { return (imax - 1) * 2 + (imin - 1) - (imin > imax ? 1 : 0); }
@@ -188,9 +181,8 @@ PB_HD int contig_of_orf(const Batch& B, i64 oi) { return B.o_contig[oi]; }
 // when lit_all); its scratch arrays (o_lnx, o_A, o_lnA, o_fac, o_hf, o_bin, o_hold) are indexed by slot.
 PB_HD i64 orf_of_slot(const Batch& B, i64 s) { return B.lit_all ? s : (i64)B.lit_ids[s]; }
 // Stage 7a (split into small kernels: each keeps its instruction working set inside the I-cache).
-// S1: base composition -> pstop, x = 1 - pstop.  item = ORF
-PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
-    if (oi >= B.no) return;
+// letters of the ORF's own strand-oriented sequence (orfs.py:162-168): popcounts over the base masks
+PB_HD void orf_base_counts(const Batch& B, i64 oi, u32& na, u32& nt, u32& ng, u32& len) {
     const int c = contig_of_orf(B, oi);
     const int L = B.cs[c].L;
     const int start = B.o_start[oi], stop = B.o_stop[oi];
@@ -198,9 +190,7 @@ PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
     int x0 = rev ? stop - 1 : start - 1, x1 = rev ? start + 2 : stop + 2;   // extent of orf.seq (functions.py:206,219,234,246)
     if (x0 < 0) x0 = 0;
     if (x1 > L) x1 = L;
-    // letters of the ORF's own strand-oriented sequence (orfs.py:162-168): popcounts over the base masks
     const i64 cb = B.coff[c];
-    u32 na, nt, ng;
     if (!rev) {
         na = count_bits(B.bA, cb + x0, cb + x1);
         nt = count_bits(B.bT, cb + x0, cb + x1);
@@ -210,7 +200,12 @@ PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
         nt = count_bits(B.bA, cb + x0, cb + x1);
         ng = count_bits(B.bC, cb + x0, cb + x1);
     }
-    const u32 len = (u32)(x1 - x0);
+    len = (u32)(x1 - x0);
+}
+// Orf.p_stop (orfs.py:162-173) in Decimal arithmetic, every operation rounded to 28 digits
+PB_HDNI Dec orf_pstop_dec(const Batch& B, i64 oi) {
+    u32 na, nt, ng, len;
+    orf_base_counts(B, oi, na, nt, ng, len);
     const u64 magic = ~0ull / len;
     const Dec Pa = dec_div_u32(na, len, magic, PB_PREC), Pt = dec_div_u32(nt, len, magic, PB_PREC),
               Pg = dec_div_u32(ng, len, magic, PB_PREC);
@@ -220,7 +215,13 @@ PB_HDN void st_orf_pstop(const Batch& B, i64 oi) {
     holdfac_prepare(Pg, fg);
     const Dec m1 = dec_mul28(Pt, Pa, fa), m2 = dec_mul28(Pt, Pg, fg);
     const Dec t1 = dec_mul28(m1, Pa, fa), t2 = dec_mul28(m2, Pa, fa), t3 = dec_mul28(m1, Pg, fg);
-    Dec pstop = dec_add(dec_add(t1, t2), t3);
+    return dec_add(dec_add(t1, t2), t3);
+}
+// S1: base composition -> pstop, x = 1 - pstop.  item = slot
+PB_HDN void st_orf_pstop(const Batch& B, i64 sl) {
+    if (sl >= B.nlit) return;
+    const i64 oi = orf_of_slot(B, sl);
+    const Dec pstop = orf_pstop_dec(B, oi);
     B.o_pstop[oi] = pstop;
     B.o_x[oi] = dec_sub(dec_one(), pstop);
 }

@@ -506,6 +506,7 @@ static int literal_chain(pb200_ctx* ctx, i32 nlit) {
     B.len_cursor = PB_ALLOC(8, u32, HOLD_BINS + 1);
     PB_ZERO(B.len_hist, (HOLD_BINS + 1) * 4);
     PB_ZERO(B.len_cursor, (HOLD_BINS + 1) * 4);
+    PB_RUN(st_orf_pstop, nlit);
     PB_RUN(st_orf_lnx, nlit);
     PB_RUN(st_orf_powA, (i64)nlit * 3);
     PB_RUN(st_orf_powF, (i64)nlit * 6);

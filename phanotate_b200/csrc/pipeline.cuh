@@ -34,6 +34,14 @@ enum {
 typedef Wide<WN> WInt;    // two's complement
 #define OV_W64_WIDE ((i64)0x7FFFFFFFFFFFFFFFll)      /* ov_w64 marker: the weight is in ov_wint[] */
 
+#ifdef __CUDACC__
+typedef uint4 U4;
+#else
+struct U4 {
+    u32 x, y, z, w;
+};
+#endif
+
 struct Params {
     u8 codon_cls[64];     // CLS_* with the reference's elif priority applied (functions.py:198-215)
     u8 rev_start[64];     // rev_comp(codon) in start_codons
@@ -175,7 +183,8 @@ struct Batch {
     i32 lit_all;          // literal chain over every ORF (ids = slot)
     i32* lit_ids;         // [<= no] ORF ids; NULL when lit_all
     u32* lit_cnt;         // [4] device counters: 0 = ORFs sent to the literal chain before the solve, 1 = after, 2 = overlap edges
-    u8* o_lit;            // [no] 1 once o_weight / o_wint hold the literal 28-digit result
+    u8* o_lit;            // [no] 1 once o_pstop / o_weight / o_wint hold the literal 28-digit results
+    U4* o_cnt;            // [no] (#a, #t, #g, length) of the ORF's own strand-oriented sequence (certified runs)
     Fx* sw_fx;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
     Fx* wr_fx;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
     i32* ovlit_ids;       // [<= nov] overlap edges routed to the literal power

@@ -81,9 +81,10 @@ def test_closed_form_error_bound_holds_on_reference_weights():
     """|W_ref / W_closed_form - 1| <= (2.51 n + 1.51) 1e-27 (fast.cuh header), checked with the oracle's
     literal weights at 90 digits on phiX174 and lambda."""
     from oracle import phanotate_oracle as O
-    worst = Decimal(0)
+    worst = worst_x = Decimal(0)
     for name in ("phiX174", "lambda"):
-        orfs = O.get_orfs(seq_of(name))
+        dna = seq_of(name).lower()
+        orfs = O.get_orfs(dna)
         T, pm, pn = orfs.T, orfs.pos_max, orfs.pos_min
         sc = O.normalise_starts(O.DEFAULT_STARTS)
         for o in orfs.iter_orfs():
@@ -97,6 +98,15 @@ def test_closed_form_error_bound_holds_on_reference_weights():
                 k = (O.max_idx(a, b, c), O.min_idx(a, b, c))
                 cnt[k] = cnt.get(k, 0) + 1
             x = 1 - o.pstop                            # the literal 28-digit value
+            # second bound: x_ref against the exact rational 1 - nt na (na + 2 ng) / len^3 (fast.cuh header)
+            lo, hi = (o.start - 1, o.stop + 2) if fwd else (o.stop - 1, o.start + 2)
+            lo, hi = max(lo, 0), min(hi, len(dna))
+            sub = dna[lo:hi] if fwd else O.rev_comp(dna[lo:hi])
+            na, nt, ng, ln = sub.count("a"), sub.count("t"), sub.count("g"), len(sub)
+            with decimal.localcontext() as ctx:
+                ctx.prec = 90
+                xt = 1 - Decimal(nt * na * (na + 2 * ng)) / Decimal(ln) ** 3
+                worst_x = max(worst_x, abs(x / xt - 1) / Decimal("4.01e-27"))
             with decimal.localcontext() as ctx:
                 ctx.prec = 90
                 E = sum(Decimal(v) * pm[k[0]] * pn[k[1]] for k, v in cnt.items())
@@ -108,3 +118,4 @@ def test_closed_form_error_bound_holds_on_reference_weights():
                 bound = (Decimal("2.51") * len(rng) + Decimal("1.51")) * Decimal("1e-27")
                 worst = max(worst, rel / bound)
     assert worst < Decimal("0.25")                    # observed: 0.03
+    assert worst_x < Decimal("0.5")
