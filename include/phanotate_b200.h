@@ -106,6 +106,7 @@ enum {
 enum {
     PB200_INPUT_DEVICE = 1,   /* flags of pb200_run: bases/offsets are device pointers */
     PB200_REUSE_INPUT = 2,    /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+    PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly
                                  trunc(weight*1000), edges.py:22) and the 28-digit Decimal weights are computed

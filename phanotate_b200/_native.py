@@ -37,6 +37,7 @@ ERR_CHAR, ERR_RANGE, ERR_PARALLEL, ERR_OVERFLOW, ERR_NOPATH, ERR_INTERNAL, ERR_L
 INPUT_DEVICE = 1
 REUSE_INPUT = 2
 LITERAL = 4
+SCAN_REFERENCE = 8
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 

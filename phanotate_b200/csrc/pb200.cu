@@ -77,6 +77,7 @@ PB_KERNEL(st_ov_fast)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 
+#include "scan_tile.cuh"
 // one warp per contig
 __global__ void __launch_bounds__(PB_BLOCK) k_solve(const Batch B, i32 nc) {
     const int lane = threadIdx.x & 31;
@@ -280,6 +281,24 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             CK(cudaGetLastError());                                                              \
         }                                                                                        \
     } while (0)
+#define PB_RUN_SCAN()                                                                            \
+    do {                                                                                         \
+        if (B.flags & PB200_SCAN_REFERENCE) PB_RUN(st_scan, (B.nb + SCAN_STRIP - 1) / SCAN_STRIP); \
+        else {                                                                                   \
+            StageTime t_;                                                                        \
+            t_.name = "scan_tiles";                                                              \
+            t_.a = ev_get(ctx);                                                                  \
+            t_.b = ev_get(ctx);                                                                  \
+            const i64 ntiles_ = (B.nb + ST_T - 1) / ST_T;                                        \
+            const int tpb_ = 32;                                                                 \
+            cudaEventRecord(t_.a, ctx->stream);                                                  \
+            k_scan_tiles<<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, 0, ctx->stream>>>(B, ntiles_, tpb_); \
+            cudaEventRecord(t_.b, ctx->stream);                                                  \
+            ctx->times.push_back(t_);                                                            \
+            ctx->launches++;                                                                     \
+            CK(cudaGetLastError());                                                              \
+        }                                                                                        \
+    } while (0)
 #define PB_RUN_SOLVE(nc_)                                                                        \
     do {                                                                                         \
         StageTime t_;                                                                            \
@@ -392,6 +411,7 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
         for (i64 i_ = 0; i_ < n_; i_++) stage(B, i_);     \
         ctx->launches++;                                  \
     } while (0)
+#define PB_RUN_SCAN() PB_RUN(st_scan, (B.nb + SCAN_STRIP - 1) / SCAN_STRIP)
 #define PB_RUN_SOLVE(nc_)                                              \
     do {                                                               \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \

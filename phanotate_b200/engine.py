@@ -192,7 +192,7 @@ class Engine:
             out[k] = out.get(k, 0.0) + float(ms[i])
         return out
 
-    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False):
+    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False, flags=0):
         """bases: uint8 array of concatenated contigs, offsets: int64[n+1].
 
         resident=True reuses the batch the previous call uploaded (inputs already in HBM).
@@ -207,7 +207,7 @@ class Engine:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                     params.ctypes.data,
-                                    (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0)))
+                                    (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) | int(flags)))
         return Result(self, names) if fetch else None
 
     def last_run_ms(self) -> float:
@@ -224,9 +224,9 @@ class Engine:
     def unpin(self, arr: np.ndarray):
         return self.lib.pb200_unpin_host(arr.ctypes.data) == 0
 
-    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False) -> Result:
+    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False, flags=0) -> Result:
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         offs = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum([len(s) for s in seqs], out=offs[1:])
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
-        return self.run_packed(bases, offs, params, names, literal=literal)
+        return self.run_packed(bases, offs, params, names, literal=literal, flags=flags)

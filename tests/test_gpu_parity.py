@@ -92,3 +92,19 @@ def test_certified_integers_equal_literal_on_gpu(eng):
     assert int((fast.contigs["err"] != 0).sum()) == 0
     # lazy completion gives the same ORF table as the literal run
     assert np.array_equal(fast.orfs, lit.orfs)
+
+
+def test_tiled_scan_equals_reference_scan(eng):
+    """The block-cooperative scan kernel (scan_tile.cuh) against the per-strip statement of the stage
+    (PB200_SCAN_REFERENCE): contig statistics incl. the RBS background histogram, every ORF, every call.
+    The batch mixes 50-kb contigs, the fixtures and the 64 stress contigs (tiny, IUPAC, N runs), so tiles
+    with one and with many contig segments are both exercised."""
+    from phanotate_b200 import synth
+    seqs = ([synth.synth4_contig(k) for k in range(8)] + [seq_of(n).encode() for n in STRESS] +
+            [seq_of(n).encode() for n in ("T4", "phiX174", "lambda")] + [seq_of(n).encode() for n in STRESS[:20]])
+    a = eng.run(seqs)
+    b = eng.run(seqs, flags=N.SCAN_REFERENCE)
+    assert np.array_equal(a.contigs, b.contigs)
+    assert np.array_equal(a.calls, b.calls)
+    assert np.array_equal(a.orfs, b.orfs)
+    assert np.array_equal(a.nodes, b.nodes)
