@@ -58,6 +58,20 @@ __device__ __forceinline__ void scan_flush(const Batch& B, ScanSmem& S, int cur_
     }
 }
 
+// the 16 raw letters of staging chunk `tid` (positions 16*tid .. 16*tid+15 of [tg0-64, tg0+2048+64)) of a tile
+__device__ __forceinline__ uint4 scan_load_chunk(const Batch& B, i64 tg0, int tid, bool wide) {
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    const i64 g0 = tg0 - ST_HL + 16 * (i64)tid;
+    if (tid >= ST_NS / 16 || g0 + 16 <= 0 || g0 >= B.nb) return raw;
+    if (wide && g0 >= 0 && g0 + 16 <= B.nb) return *(const uint4*)(B.seq + g0);
+    u32 w[4] = {0u, 0u, 0u, 0u};
+    for (int b = 0; b < 16; b++) {
+        const i64 g = g0 + b;
+        if (g >= 0 && g < B.nb) w[b >> 2] |= (u32)B.seq[g] << (8 * (b & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(ST_NT) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block) {
     __shared__ __align__(16) ScanSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,51 +115,61 @@ __global__ void __launch_bounds__(ST_NT) k_scan_tiles(const Batch B, i64 ntiles,
         }
     }
     __syncthreads();
-    int cur_c = -1;
+    int cur_c = -1;                                  // contig of the block's accumulators
     const i64 t0 = (i64)blockIdx.x * tiles_per_block;
     const i64 t1 = (t0 + tiles_per_block < ntiles) ? t0 + tiles_per_block : ntiles;
     const int pb = ST_HL + 8 * tid;                  // staging index of this thread's first base
+    const bool wide = (((size_t)B.seq) & 15) == 0;   // 16-byte loads of the letters (tile starts are multiples of 2048)
+    int c = contig_of(B, t0 * ST_T);                 // walking contig cursor with its bounds: tiles are consecutive
+    i64 cb = B.coff[c], ce = B.coff[c + 1];
+    uint4 raw_next = scan_load_chunk(B, t0 * ST_T, tid, wide);
     for (i64 tile = t0; tile < t1; tile++) {
         const i64 tg0 = tile * ST_T;
         const i64 tg1 = (tg0 + ST_T < B.nb) ? tg0 + ST_T : B.nb;
         const i64 gb = tg0 + 8 * tid;                // this thread's bases: gb .. gb+7
         u32 meta_lo = 0, meta_hi = 0;
         u64 acc_cls = 0, acc_cd = 0, acc_kf = 0, acc_kr = 0;
-        int c_first = cur_c;                          // tiles are consecutive: the contig of tg0 is cur_c or a later one
-        if (c_first < 0) c_first = contig_of(B, tg0);
-        else
-            while (B.coff[c_first + 1] <= tg0) c_first++;
-        for (int c = c_first; c < B.nc && B.coff[c] < tg1; c++) {
-            const i64 cb = B.coff[c], ce = B.coff[c + 1];
+        const uint4 raw = raw_next;
+        if (tile + 1 < t1) raw_next = scan_load_chunk(B, tg0 + ST_T, tid, wide);   // in flight during this tile's phases
+        while (ce <= tg0 && c + 1 < B.nc) {           // (skips empty contigs too)
+            c++;
+            cb = ce;
+            ce = B.coff[c + 1];
+        }
+        for (;;) {
             const i64 seg_lo = cb > tg0 ? cb : tg0, seg_hi = ce < tg1 ? ce : tg1;
-            if (seg_hi <= seg_lo) continue;
+            if (seg_hi > seg_lo) {
             if (c != cur_c) {
                 scan_flush(B, S, cur_c, tid);        // phase D of the previous segment ended with a barrier
                 cur_c = c;
             }
             __syncthreads();
-            // ---- A: stage codes and bit planes of [tg0-64, tg0+2048+64)
-            {
+            // ---- A: codes and bit planes of [tg0-64, tg0+2048+64) from the raw letters, 16 positions per thread
+            if (tid < ST_NS / 16 + 8) {
+                const i64 g0 = tg0 - ST_HL + 16 * (i64)tid;
+                const u32 rw[4] = {raw.x, raw.y, raw.z, raw.w};
+                u32 cw[4] = {0u, 0u, 0u, 0u};
+                u32 gcbits = 0, okbits = 0;
                 bool bad = false;
-                for (int p = tid; p < ST_NS + 128; p += ST_NT) {
-                    const i64 g = tg0 - ST_HL + p;
-                    int cd = 6, gcb = 0;
-                    if (p < ST_NS && g >= cb && g < ce) {
-                        const int v = S.chlut[B.seq[g]];
-                        cd = v & 7;
-                        gcb = v >> 3;
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const i64 g = g0 + b;
+                    u32 cd = 6;
+                    if (tid < ST_NS / 16 && g >= cb && g < ce) {
+                        const u32 v = S.chlut[(rw[b >> 2] >> (8 * (b & 3))) & 0xFFu];
+                        cd = v & 7u;
+                        gcbits |= (v >> 3) << b;
                         if (cd == 5) {
                             if (g >= seg_lo && g < seg_hi) bad = true;
                             cd = 4;
                         }
+                        okbits |= (cd < 4 ? 1u : 0u) << b;
                     }
-                    if (p < ST_NS + 16) S.code[p] = (u8)cd;
-                    const u32 bg = __ballot_sync(0xFFFFFFFFu, gcb != 0), bo = __ballot_sync(0xFFFFFFFFu, cd < 4);
-                    if (lane == 0) {
-                        S.gcw[p >> 5] = bg;
-                        S.okw[p >> 5] = bo;
-                    }
+                    cw[b >> 2] |= cd << (8 * (b & 3));
                 }
+                if (tid <= ST_NS / 16) *(uint4*)(S.code + 16 * tid) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                ((unsigned short*)S.gcw)[tid] = (unsigned short)gcbits;
+                ((unsigned short*)S.okw)[tid] = (unsigned short)okbits;
                 if (bad) atomicOr(&B.cs[c].err, (u32)ERR_CHAR);
             }
             __syncthreads();
@@ -299,6 +323,11 @@ __global__ void __launch_bounds__(ST_NT) k_scan_tiles(const Batch B, i64 ntiles,
                 }
             }
             __syncthreads();
+            }
+            if (ce >= tg1 || c + 1 >= B.nc) break;    // the tile ends inside this contig (or it is the last one)
+            c++;
+            cb = ce;
+            ce = B.coff[c + 1];
         }
         // ---- outputs of the tile
         if (gb + 8 <= B.nb) {
