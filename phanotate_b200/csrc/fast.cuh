@@ -20,7 +20,8 @@
 //     pstop_ref  = pstop_true (1 +- 3.51e-27)    three quotients, five products, two sums, half an ulp each
 //     x_ref      = x_true (1 +- 4.01e-27)        for x >= 1/2, incl. the rounding of 1 - pstop
 // and W = C x^-E with E <= n turns that into another 4.01 n e-27: total (6.52 n + 1.51) e-27.  We use
-// (7n + 8) * 2^-89 (2^-89 = 1.6e-27), which also swallows the ~2^-170 relative error of the Q32.192 evaluation.
+// (7n + 8) * 2^-89 (2^-89 = 1.6e-27) plus 2^-90 for the double-double evaluation of the closed form
+// (ddmath.cuh: < 2^-92).  The fast path is taken for 0 < pstop <= 1/8 and |weight|*1000 < 2^68.
 #pragma once
 #include "graph.cuh"
 
@@ -39,32 +40,27 @@ PB_HD void count_frame_bits5(u64* const* M, i64 g0, i64 g1, int rg, u32* n) {
     }
 }
 
-// Per-contig / global fixed-point constants of the closed form.  item = contig*28 + r (RBS bin);
+// Per-contig / global double-double constants of the closed form.  item = contig*28 + r (RBS bin);
 // items 0..8 of contig 0 also convert the start-codon weights (index 8 = no start codon -> 1000).
 PB_HDN void st_fast_tables(const Batch& B, i64 item) {
     const i64 c = item / 28;
     if (c >= B.nc) return;
     const int r = (int)(item % 28);
     CStat* cs = B.cs + c;
-    bool ok;
-    Fx v = fx_from_dec(cs->wrbs[r], &ok);
-    if (!ok || v.w[6] >= (1u << 20)) {
+    DD v;
+    if (!dd_from_dec(cs->wrbs[r], v) || !(v.hi < 1.0e9)) {
         cs->fast_ok = 0;               // (benign race: every writer stores 0)
-        w_zero(v);
+        v = dd_from_d(0.0);
     }
-    B.wr_fx[item] = v;
+    B.wr_dd[item] = v;
     if (c == 0 && r < 9) {
-        Fx s;
-        w_zero(s);
-        s.w[6] = 1000;
+        DD s = dd_from_d(1000.0);
         if (r < 8) {
-            Dec d = B.P.startw[r];
-            d.e += 3;
-            bool o2;
-            s = fx_from_dec(d, &o2);
-            if (!o2 || d.neg || s.w[6] >= (1u << 11)) w_zero(s);     // zero = "not usable": the ORF goes literal
+            DD w;
+            if (dd_from_dec(B.P.startw[r], w) && w.hi <= 1.0e6) s = dd_mul_d(w, 1000.0);
+            else s = dd_from_d(0.0);   // zero = "not usable": the ORF goes literal
         }
-        B.sw_fx[r] = s;
+        B.sw_dd[r] = s;
     }
 }
 
@@ -77,8 +73,6 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
     const bool rev = B.o_frame[oi] < 0;
     const int n = orf_steps(start, stop, rev);
     bool fast = cs->fast_ok && n > 0 && n < 100000;
-    Wide<10> big;
-    w_zero(big);
     // x_true = 1 - pstop_true, pstop_true = Pt Pa (Pa + 2 Pg) = nt na (na + 2 ng) / len^3 exactly (orfs.py:162-173)
     u32 na, nt, ng, len;
     orf_base_counts(B, oi, na, nt, ng, len);
@@ -90,86 +84,67 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
         cn.w = len;
         B.o_cnt[oi] = cn;
     }
-    Fx X;
-    w_zero(X);
+    DD V = dd_from_d(0.0);              // |weight| * 1000
     if (len < 1 || len >= (1u << 17)) fast = false;
     if (fast) {
-        const u64 num = (u64)nt * na * ((u64)na + 2ull * ng), den = (u64)len * len * len;
-        if (num == 0 || num >= den) fast = false;
+        const double num = (double)nt * (double)na * ((double)na + 2.0 * (double)ng);   // < 2^53: exact
+        const double den = (double)len * (double)len * (double)len;                      // < 2^51: exact
+        if (!(num > 0.0 && num * 8.0 <= den)) fast = false;                             // certified for 0 < pstop <= 1/8
         else {
-            Wide<9> N, Q;
-            Wide<2> D, Rm;
-            w_zero(N);
-            N.w[6] = (u32)num;
-            N.w[7] = (u32)(num >> 32);
-            D.w[0] = (u32)den;
-            D.w[1] = (u32)(den >> 32);
-            w_divmod<9, 2>(N, D, Q, Rm);                       // floor(num * 2^192 / den) < 2^192
-            X = fx_one();
-            const Fx q = w_resize<FX_N>(Q);
-            w_sub(X, q);
-            if (!w_is_zero(Rm)) {                               // round the quotient up so that X <= x_true < X + 2^-192
-                Fx ulp;
-                w_zero(ulp);
-                ulp.w[0] = 1;
-                w_sub(X, ulp);
-            }
-            if (!(X.w[6] == 0 && (X.w[5] >> 31))) fast = false; // certified for 1/2 <= x < 1 only
-        }
-    }
-    if (fast) {
-        // codon counts per factor class over [start, stop) (forward) / (stop, start] (reverse), functions.py:289-298
-        const i64 cb = B.coff[c];
-        const i64 g0 = rev ? cb + stop : cb + start - 1, g1 = rev ? cb + start : cb + stop - 1;
-        u32 nk[6];
-        count_frame_bits5(rev ? B.cR : B.cF, g0, g1, (int)((cb + start - 1) % 3), nk);
-        nk[5] = (u32)n - (nk[0] + nk[1] + nk[2] + nk[3] + nk[4]);
-        if (nk[5] > (u32)n) fast = false;
-        Fx E;
-        w_zero(E);
+            const double q1 = num / den;
+            const DD p = dd_quick(q1, pb_fma(-q1, den, num) / den);
+            const DD Lx = dd_neglog1m(p);                                               // -ln(1 - pstop) > 0
+            // codon counts per factor class over [start, stop) (forward) / (stop, start] (reverse), functions.py:289-298
+            const i64 cb = B.coff[c];
+            const i64 g0 = rev ? cb + stop : cb + start - 1, g1 = rev ? cb + start : cb + stop - 1;
+            u32 nk[6];
+            count_frame_bits5(rev ? B.cR : B.cF, g0, g1, (int)((cb + start - 1) % 3), nk);
+            nk[5] = (u32)n - (nk[0] + nk[1] + nk[2] + nk[3] + nk[4]);
+            if (nk[5] > (u32)n) fast = false;
+            DD E = dd_from_d(0.0);
 #pragma unroll 1
-        for (int k = 0; k < 6; k++) {
-            Fx t = cs->fe[k];
-            w_mul_small(t, nk[k]);
-            w_add(E, t);
-        }
-        bool o1 = true, o2, o3;
-        const SFx lnx = fx_ln(X, &o2);
-        SFx T;
-        T.m = fx_mul(lnx.m, E);
-        T.neg = 0;                                             // exp(-E ln x), ln x < 0
-        if (!o1 || !o2 || !lnx.neg || fx_to_double(T.m) > 60.0) fast = false;
-        if (fast) {
-            int K;
-            const Fx P = fx_exp_core(T, &K, &o3);
+            for (int k = 0; k < 6; k++) E = dd_add(E, dd_mul_d(cs->fe[k], (double)nk[k]));
+            const DD T = dd_mul(E, Lx);                                                 // weight = C * exp(T)
             const int sw = B.o_sw[oi];
-            const Fx SW = B.sw_fx[sw < 0 ? 8 : sw];
-            if (!o3 || K < 0 || K > 90 || w_is_zero(SW)) fast = false;
-            else {
-                const Fx Mv = fx_mul(fx_mul(P, SW), B.wr_fx[(i64)c * 28 + B.o_rbs[oi]]);
-                big = w_shl(w_resize<10>(Mv), K);              // |weight| * 1000 in Q128.192
+            const DD SW = B.sw_dd[sw < 0 ? 8 : sw];
+            if (!(T.hi >= 0.0 && T.hi < 60.0) || !(SW.hi > 0.0)) fast = false;
+            if (fast) {
+                int K;
+                const DD P = dd_exp_split(T, &K);
+                const DD Mv = dd_mul(dd_mul(P, SW), B.wr_dd[(i64)c * 28 + B.o_rbs[oi]]);
+                V.hi = ldexp(Mv.hi, K);
+                V.lo = ldexp(Mv.lo, K);
             }
         }
     }
+    if (fast && !(V.hi >= 0.0 && V.hi < 2.9e20)) fast = false;                          // < 2^68
     if (fast) {
-        Wide<4> I;
-        I.w[0] = big.w[6];
-        I.w[1] = big.w[7];
-        I.w[2] = big.w[8];
-        I.w[3] = big.w[9];
-        const u64 fr = ((u64)big.w[5] << 32) | big.w[4];       // top 64 bits of the fraction
-        const int bl = w_bitlen(I) + 1;                        // |weight|*1000 < 2^bl
-        const u64 en = 7ull * (u64)n + 8ull;
-        u64 errU;                                              // error bound in units of 2^-64: en * 2^(bl-89) * 2^64
-        if (bl > 68) fast = false;
-        else {
-            errU = (bl >= 25) ? (en << (bl - 25)) : ((en >> (25 - bl)) + 1);
-            errU += 2;
-            if (errU >> 62) fast = false;
-            else if (fr < errU || fr > ~errU) fast = false;
+        // integer part and fraction of hi + lo
+        const double ih = floor(V.hi), il = floor(V.lo);
+        double f = (V.hi - ih) + (V.lo - il);                                           // in [0, 2)
+        i64 adj = (i64)il;
+        if (f >= 1.0) {
+            f -= 1.0;
+            adj += 1;
         }
+        const double top = floor(ih * 2.3283064365386963e-10);                          // ih / 2^32, exact
+        const u64 low = (u64)(ih - top * 4294967296.0), t64 = (u64)top;                 // ih = t64 * 2^32 + low, t64 < 2^36
+        u64 lo64 = (t64 << 32) + low, hi64 = t64 >> 32;
+        const u64 old = lo64;
+        lo64 += (u64)adj;
+        if (adj >= 0) hi64 += (lo64 < old) ? 1u : 0u;
+        else hi64 -= (lo64 > old) ? 1u : 0u;
+        // relative error bound (7n + 8) 2^-89 of the reference's roundings + 2^-90 for the evaluation, absolute 2^-36 for f
+        const double thr = V.hi * (((double)(7 * n + 8) + 0.5) * 1.6155871338926322e-27) + 1.4551915228366852e-11;
+        if (!(thr < 0.25 && f >= thr && f <= 1.0 - thr) || (hi64 >> 8)) fast = false;
         if (fast) {
-            B.o_wint[oi] = wint_from_mag(w_resize<WN>(I), !w_is_zero(I));
+            Wide<WN> I;
+            w_zero(I);
+            I.w[0] = (u32)lo64;
+            I.w[1] = (u32)(lo64 >> 32);
+            I.w[2] = (u32)hi64;
+            I.w[3] = (u32)(hi64 >> 32);
+            B.o_wint[oi] = wint_from_mag(I, !w_is_zero(I));
             B.o_lit[oi] = 0;
         }
     }
@@ -212,87 +187,6 @@ PB_HDN void st_lit_rest(const Batch& B, i64 oi) {
 // total <= 2.78e-24 < 2^-78.2; the double-double evaluation adds < 2^-87.  The integer
 // trunc(W*1000) is accepted when W*1000 (1 +- 2^-78) does not straddle an integer; else the literal
 // chain (st_ov_pbar/pow/weight) computes it.
-struct DD {
-    double hi, lo;
-};
-PB_HD double pb_fma(double a, double b, double c) {
-#ifdef __CUDA_ARCH__
-    return __fma_rn(a, b, c);
-#else
-    return fma(a, b, c);
-#endif
-}
-PB_HD DD dd_two_sum(double a, double b) {
-    DD r;
-    r.hi = a + b;
-    const double bb = r.hi - a;
-    r.lo = (a - (r.hi - bb)) + (b - bb);
-    return r;
-}
-PB_HD DD dd_quick(double a, double b) {      // |a| >= |b|
-    DD r;
-    r.hi = a + b;
-    r.lo = b - (r.hi - a);
-    return r;
-}
-PB_HD DD dd_add(const DD& a, const DD& b) {
-    DD s = dd_two_sum(a.hi, b.hi);
-    const DD t = dd_two_sum(a.lo, b.lo);
-    s.lo += t.hi;
-    s = dd_quick(s.hi, s.lo);
-    s.lo += t.lo;
-    return dd_quick(s.hi, s.lo);
-}
-PB_HD DD dd_mul(const DD& a, const DD& b) {
-    const double p = a.hi * b.hi;
-    double e = pb_fma(a.hi, b.hi, -p);
-    e = pb_fma(a.hi, b.lo, e);
-    e = pb_fma(a.lo, b.hi, e);
-    return dd_quick(p, e);
-}
-PB_HD DD dd_mul_d(const DD& a, double b) {
-    const double p = a.hi * b;
-    double e = pb_fma(a.hi, b, -p);
-    e = pb_fma(a.lo, b, e);
-    return dd_quick(p, e);
-}
-PB_HD DD dd_from_d(double v) {
-    DD r;
-    r.hi = v;
-    r.lo = 0.0;
-    return r;
-}
-PB_HD DD dd_recip(const DD& b) {             // 1/b with two correction steps
-    const double q1 = 1.0 / b.hi;
-    DD t = dd_mul_d(b, q1);
-    t.hi = -t.hi;
-    t.lo = -t.lo;
-    DD r = dd_add(dd_from_d(1.0), t);
-    const double q2 = r.hi / b.hi;
-    t = dd_mul_d(b, q2);
-    t.hi = -t.hi;
-    t.lo = -t.lo;
-    r = dd_add(r, t);
-    const double q3 = r.hi / b.hi;
-    DD q = dd_quick(q1, q2);
-    return dd_add(q, dd_from_d(q3));
-}
-// non-negative Dec with a coefficient below 2^96 and exponent in (-PB_NP10DD, 0] -> DD
-PB_HD bool dd_from_dec(const Dec& d, DD& out) {
-    out = dd_from_d(0.0);
-    if (dec_is_zero(d)) return true;
-    if (d.neg || d.c.w[3] != 0 || d.e > 0 || -d.e >= PB_NP10DD) return false;
-    const double a = (double)d.c.w[2] * 18446744073709551616.0, b = (double)d.c.w[1] * 4294967296.0, c = (double)d.c.w[0];
-    DD s = dd_two_sum(a, b);
-    const DD t = dd_two_sum(s.hi, c);
-    const DD cc = dd_quick(t.hi, s.lo + t.lo);          // exact: the coefficient has at most 96 bits
-    DD p;
-    p.hi = TBL(p10neg_dd)[-d.e][0];
-    p.lo = TBL(p10neg_dd)[-d.e][1];
-    out = dd_mul(cc, p);
-    return true;
-}
-
 // pstop of the ORF behind node n as the exact rational nt na (na + 2 ng) / len^3 (counts left by st_orf_fast),
 // or the contig's Decimal pstop for a node without an ORF (functions.py:373-385)
 PB_HD bool dd_node_pstop(const Batch& B, int c, i32 n, DD& out) {

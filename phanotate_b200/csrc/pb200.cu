@@ -206,6 +206,7 @@ struct pb200_ctx {
     size_t evused = 0;
     int launches = 0;
     int sm_count = 148;
+    bool scan_attr_set = false;
     cudaEvent_t run_a = nullptr, run_b = nullptr;
 };
 static int buf_ensure(pb200_ctx* ctx, DevBuf& b, size_t bytes) {
@@ -291,6 +292,10 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             t_.b = ev_get(ctx);                                                                  \
             const i64 ntiles_ = (B.nb + ST_T - 1) / ST_T;                                        \
             const int tpb_ = 32;                                                                 \
+            if (!ctx->scan_attr_set) {                                                           \
+                cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+                ctx->scan_attr_set = true;                                                       \
+            }                                                                                    \
             cudaEventRecord(t_.a, ctx->stream);                                                  \
             k_scan_tiles<<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, 0, ctx->stream>>>(B, ntiles_, tpb_); \
             cudaEventRecord(t_.b, ctx->stream);                                                  \

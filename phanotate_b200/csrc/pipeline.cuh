@@ -16,6 +16,7 @@
 #pragma once
 #include "fxpow.cuh"
 #include "frepr.cuh"
+#include "ddmath.cuh"
 
 // ------------------------------------------------------------------------------------------------
 enum { CLS_NONE = 0, CLS_S = 1, CLS_s = 2, CLS_T = 3, CLS_t = 4 };
@@ -67,7 +68,7 @@ struct CStat {
     u8 max_one[4], min_one[4];
     i32 n_calls;
     i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
-    Fx fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
+    DD fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
 };
 
@@ -185,8 +186,8 @@ struct Batch {
     u32* lit_cnt;         // [4] device counters: 0 = ORFs sent to the literal chain before the solve, 1 = after, 2 = overlap edges
     u8* o_lit;            // [no] 1 once o_pstop / o_weight / o_wint hold the literal 28-digit results
     U4* o_cnt;            // [no] (#a, #t, #g, length) of the ORF's own strand-oriented sequence (certified runs)
-    Fx* sw_fx;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
-    Fx* wr_fx;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
+    DD* sw_dd;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
+    DD* wr_dd;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
     i32* ovlit_ids;       // [<= nov] overlap edges routed to the literal power
     i64* ov_w64;          // [nov] integer weight of the overlap edge, or OV_W64_WIDE -> ov_wint[]
     i32 ov_all;           // literal overlap chain over every edge (slot = edge), ov_w[] indexed by edge

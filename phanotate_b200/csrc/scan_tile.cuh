@@ -72,7 +72,7 @@ __device__ __forceinline__ uint4 scan_load_chunk(const Batch& B, i64 tg0, int ti
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(ST_NT) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block) {
+__global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block) {
     __shared__ __align__(16) ScanSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += ST_NT) {

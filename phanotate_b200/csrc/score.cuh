@@ -79,11 +79,13 @@ PB_HDN void st_contig_stats(const Batch& B, i64 c) {
         cs->fmin[k] = fx_from_dec(cs->pos_min[k], &o2);
         if (!o1 || !o2) cs->err |= ERR_RANGE;
     }
+    cs->fast_ok = (cs->err & ERR_RANGE) ? 0 : 1;
     for (int k = 0; k < 6; k++) {
         const int im = k / 2 + 1, il = (k % 2) + 1 + (((k % 2) + 1 >= im) ? 1 : 0);
-        cs->fe[k] = fx_mul(cs->fmax[im], cs->fmin[il]);
+        DD a, b;
+        if (!dd_from_dec(cs->pos_max[im], a) || !dd_from_dec(cs->pos_min[il], b)) cs->fast_ok = 0;
+        cs->fe[k] = dd_mul(a, b);
     }
-    cs->fast_ok = (cs->err & ERR_RANGE) ? 0 : 1;
 }
 
 // score_gap for length <= 300 (functions.py:36-46): 1/g**Decimal(length/3) (+ 1/0.05 if 'diff'), as three
