@@ -50,7 +50,7 @@ typedef struct pb200_call {     /* one CDS row of Locus.tabular (locus.py:39-56)
     int32_t left;               /* entry node position              (phanotate.py:72-74) */
     int32_t right;              /* exit node position + 2           (locus.py:30)        */
     int32_t strand;             /* +1 / -1 = sign(left.frame)                             */
-    pb200_dec weight;           /* graph.weight(Edge(left,right)) = Orf.weight           */
+    pb200_dec weight;           /* graph.weight(Edge(left,right)) = Orf.weight (see PB200_CALL_WEIGHTS) */
     double score;               /* float(weight), what '%E' prints  (phanotate.py:75-76) */
 } pb200_call;
 
@@ -106,6 +106,9 @@ enum {
 enum {
     PB200_INPUT_DEVICE = 1,   /* flags of pb200_run: bases/offsets are device pointers */
     PB200_REUSE_INPUT = 2,    /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+    PB200_CALL_WEIGHTS = 16,  /* also fill pb200_call.weight with the 28-digit Decimal of every call (otherwise it is
+                                 filled only where the Decimal chain ran anyway and is 0 elsewhere; pb200_call.score,
+                                 the float that Locus.tabular prints with '%E', is always exact) */
     PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly

@@ -35,7 +35,7 @@ def main(argv=None):
         c = res.contigs[k]
         from phanotate_b200 import _native as N
         for r in res.calls[c["call_off"]:c["call_off"] + c["n_calls"]]:
-            weight = N.dec_to_decimal(r["weight"])
+            weight = float(r["score"])                             # '%E' % Decimal goes through float() as well
             strand = 1 if r["strand"] > 0 else -1
             pairs = [[int(r["left"]), int(r["right"]) - 2]]       # add_feature adds the 2 back (locus.py:30)
             feature = locus.add_feature('CDS', strand, pairs, {'note': ['score:%E' % weight]})

@@ -38,6 +38,7 @@ INPUT_DEVICE = 1
 REUSE_INPUT = 2
 LITERAL = 4
 SCAN_REFERENCE = 8
+CALL_WEIGHTS = 16
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 

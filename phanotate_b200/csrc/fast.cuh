@@ -145,6 +145,7 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
             I.w[2] = (u32)hi64;
             I.w[3] = (u32)(hi64 >> 32);
             B.o_wint[oi] = wint_from_mag(I, !w_is_zero(I));
+            B.o_v[oi] = V;
             B.o_lit[oi] = 0;
         }
     }
@@ -155,10 +156,35 @@ PB_HDN void st_orf_fast(const Batch& B, i64 oi) {
     }
 }
 
-// ORFs on the path whose Decimal weight is still owed.  item = call
+// float(Orf.weight) (what '%E' prints, phanotate.py:75-76) from the closed form: W = V/1000 = hi + lo is within
+// rel = (7n + 8.5) 2^-89 + 2^-100 of the reference's Decimal, so hi is ITS nearest double as soon as
+// |lo| + rel |hi| stays clear of half an ulp of hi (a quarter below a power of two).  Fails ~2^-26 of the time.
+PB_HD bool certified_score(const DD& V, int n, double* score) {
+    if (!(V.hi > 0.0)) return false;
+    const DD W = dd_mul(V, dd_table(TBL(p10neg_dd)[3]));
+    const double hi = W.hi, alo = fabs(W.lo);
+    int ex;
+    const double m = frexp(hi, &ex);                              // hi = m 2^ex, m in [0.5, 1): ulp = 2^(ex-53)
+    if (ex < -900 || ex > 900) return false;
+    const double half = ldexp(1.0, ex - 54), room = (m == 0.5) ? 0.5 * half : half;
+    const double rel = ((double)(7 * n + 8) + 0.5) * 1.6155871338926322e-27 + 7.8886090522101181e-31;
+    if (!(alo + hi * rel * 1.0000001 < room * 0.9999999)) return false;
+    *score = -hi;
+    return true;
+}
+// Calls whose score cannot be certified (or every call when PB200_CALL_WEIGHTS asks for the Decimal weights)
+// go through the literal chain after the solve.  item = call
 PB_HDN void st_lit_calls(const Batch& B, i64 k) {
     if (k >= B.ncalls) return;
     const i32 oi = B.call_orf[k];
+    if (B.o_lit[oi] == 0 && !(B.flags & PB200_CALL_WEIGHTS)) {
+        const bool rev = B.o_frame[oi] < 0;
+        double sc;
+        if (certified_score(B.o_v[oi], orf_steps(B.o_start[oi], B.o_stop[oi], rev), &sc)) {
+            B.call_score[k] = sc;
+            return;
+        }
+    }
     if (B.o_lit[oi] == 0) {
         const u32 pos = PB_ATOMIC_ADD_RET(&B.lit_cnt[1], 1u);
         B.lit_ids[pos] = oi;

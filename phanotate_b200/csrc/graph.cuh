@@ -484,10 +484,17 @@ PB_HDN void st_gather_calls(const Batch& B, i64 k) {
     r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
     r.right = (rev ? B.o_start[orf] : B.o_stop[orf]) + 2;     // right = exit node position + 2
     r.strand = rev ? -1 : 1;
-    r.weight = B.o_weight[orf];
-    bool ok;
-    r.score = dec_to_double(r.weight, &ok);
-    if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
+    if (B.o_lit[orf] == 1) {
+        r.weight = B.o_weight[orf];
+        bool ok;
+        r.score = dec_to_double(r.weight, &ok);
+        if (!ok) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_RANGE);
+    } else {                               // certified score, Decimal weight not materialised (no PB200_CALL_WEIGHTS)
+        w_zero(r.weight.c);
+        r.weight.e = 0;
+        r.weight.neg = 0;
+        r.score = B.call_score[k];
+    }
     B.calls[k] = r;
 }
 

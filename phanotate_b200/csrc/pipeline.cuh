@@ -186,6 +186,8 @@ struct Batch {
     u32* lit_cnt;         // [4] device counters: 0 = ORFs sent to the literal chain before the solve, 1 = after, 2 = overlap edges
     u8* o_lit;            // [no] 1 once o_pstop / o_weight / o_wint hold the literal 28-digit results
     U4* o_cnt;            // [no] (#a, #t, #g, length) of the ORF's own strand-oriented sequence (certified runs)
+    DD* o_v;              // [no] |weight| * 1000 from the closed form (certified runs)
+    double* call_score;   // [ncalls] certified float(weight) of a call whose Decimal weight was not materialised
     DD* sw_dd;            // [9] 1000 * start-codon weight (index 8: no start codon -> 1000)
     DD* wr_dd;            // [nc*28] Decimal(str(weight_rbs)) per contig and RBS bin
     i32* ovlit_ids;       // [<= nov] overlap edges routed to the literal power

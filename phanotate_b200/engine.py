@@ -192,14 +192,17 @@ class Engine:
             out[k] = out.get(k, 0.0) + float(ms[i])
         return out
 
-    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False, flags=0):
+    def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False, flags=0,
+                   call_weights=False):
         """bases: uint8 array of concatenated contigs, offsets: int64[n+1].
 
         resident=True reuses the batch the previous call uploaded (inputs already in HBM).
         fetch=False skips copying the result tables to the host (returns None).
         literal=True replays the reference's Decimal arithmetic for every ORF and overlap edge inside the
         run (PB200_LITERAL); by default the solve runs on certified integer weights and Decimal weights are
-        produced for the calls, and lazily for the ORF table / edge dump.  Results are identical.
+        produced lazily for the ORF table / edge dump.  Results are identical.
+        call_weights=True also fills the Decimal `weight` column of the call rows (PB200_CALL_WEIGHTS); the
+        float `score` column -- what the tabular output prints -- is always exact.
         """
         if params is None:
             params = make_params()
@@ -207,7 +210,8 @@ class Engine:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                     params.ctypes.data,
-                                    (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) | int(flags)))
+                                    (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) |
+                                    (N.CALL_WEIGHTS if call_weights else 0) | int(flags)))
         return Result(self, names) if fetch else None
 
     def last_run_ms(self) -> float:
@@ -224,9 +228,10 @@ class Engine:
     def unpin(self, arr: np.ndarray):
         return self.lib.pb200_unpin_host(arr.ctypes.data) == 0
 
-    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False, flags=0) -> Result:
+    def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False, flags=0,
+            call_weights=False) -> Result:
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         offs = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum([len(s) for s in seqs], out=offs[1:])
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
-        return self.run_packed(bases, offs, params, names, literal=literal, flags=flags)
+        return self.run_packed(bases, offs, params, names, literal=literal, flags=flags, call_weights=call_weights)

@@ -52,11 +52,14 @@ def test_certified_integers_equal_literal(sim, name):
     fast, wf, lit, wl = _both(sim, [seq_of(name)])
     assert wf == wl
     assert _calls(fast, 0) == _calls(lit, 0) == golden_text(name, "calls.tsv")
-    assert [str(N.dec_to_decimal(r["weight"])) for r in fast.calls] == [str(N.dec_to_decimal(r["weight"])) for r in lit.calls]
+    assert [float(r["score"]) for r in fast.calls] == [float(r["score"]) for r in lit.calls]      # certified scores
+    withw = sim.run([seq_of(name)], call_weights=True)
+    assert [str(N.dec_to_decimal(r["weight"])) for r in withw.calls] == [str(N.dec_to_decimal(r["weight"])) for r in lit.calls]
+    assert withw.n_literal_presolve + withw.n_literal_postsolve >= withw.n_calls
     assert lit.n_literal_presolve == lit.n_orfs
     # the filter must actually filter: almost every ORF is decided without the literal chain
     assert fast.n_literal_presolve <= max(2, fast.n_orfs // 20)
-    assert fast.n_literal_presolve + fast.n_literal_postsolve >= fast.n_calls
+    assert fast.n_literal_postsolve <= 2                  # scores are certified too: no Decimal chain after the solve
 
 
 def test_certified_stress_batch(sim):

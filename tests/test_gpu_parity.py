@@ -88,7 +88,11 @@ def test_certified_integers_equal_literal_on_gpu(eng):
     wl = lit.orf_int_weights()
     assert wf == wl
     assert fast.n_literal_presolve < fast.n_orfs // 20 and lit.n_literal_presolve == lit.n_orfs
-    assert np.array_equal(fast.calls, lit.calls)
+    for col in ("contig", "left", "right", "strand", "score"):
+        assert np.array_equal(fast.calls[col], lit.calls[col]), col
+    assert fast.n_literal_postsolve < 4
+    assert np.array_equal(eng.run(seqs, call_weights=True).calls, lit.calls)
+    fast = eng.run(seqs)
     assert int((fast.contigs["err"] != 0).sum()) == 0
     # lazy completion gives the same ORF table as the literal run
     assert np.array_equal(fast.orfs, lit.orfs)
