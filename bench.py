@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--length", type=int, default=50000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="contigs in the cpu_baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lanes", type=int, default=4, help="contexts of the pipelined engine used for the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -176,7 +177,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from phanotate_b200.engine import Engine, make_params
+    from phanotate_b200.engine import Engine, PipelinedEngine, make_params
     from phanotate_b200 import _native as N
     eng = Engine(local)
     params = make_params()
@@ -227,16 +228,30 @@ def main():
     sizes = eng.sizes()
     ncalls = sizes[6]
 
-    # ---- end to end through the public API with pinned host buffers (`e2e`)
+    # ---- end to end through the public API with pinned host buffers (`e2e`): PipelinedEngine cuts the batch into
+    #      `lanes` groups of contigs so that the copies of one group overlap the kernels of the others
+    peng = PipelinedEngine(local, lanes=args.lanes)
+
+    def gather_host_calls(res):
+        if dist is None:
+            return
+        from phanotate_b200.dist import gather_call_tables
+        raw = torch.from_numpy(res.calls.view(np.uint8).reshape(-1)).cuda() if res.n_calls else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        gather_call_tables(raw, res.n_calls, dist, rank, world)
+        if rank == 0:
+            torch.cuda.synchronize()
+
+    res = peng.run_packed(bases, offs, params)                     # warm-up: sizes the lanes' device buffers
     barrier()
     t1 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        res = eng.run_packed(bases, offs, params)                  # H2D bases+offsets, kernels, D2H calls+contig table
+        res = peng.run_packed(bases, offs, params)                 # H2D bases+offsets, kernels, D2H calls+contig table
         d2h = res.calls.nbytes + res.contigs.nbytes
-        gather_calls()
+        gather_host_calls(res)
     barrier()
     wall_e2e = time.perf_counter() - t1
+    peng.close()
     errs = int((res.contigs["err"] != 0).sum())
 
     if dist is not None:

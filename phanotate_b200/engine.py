@@ -235,3 +235,94 @@ class Engine:
         np.cumsum([len(s) for s in seqs], out=offs[1:])
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
         return self.run_packed(bases, offs, params, names, literal=literal, flags=flags, call_weights=call_weights)
+
+
+class MergedResult:
+    """Call and contig tables of a batch that ran as several groups (PipelinedEngine): same columns as Result,
+    contig ids and table offsets renumbered to the whole batch.  The per-group Results stay reachable for
+    the lazily fetched ORF / node / edge tables (`group_of(contig)`)."""
+
+    def __init__(self, parts, first_contig):
+        self.parts, self.first_contig = parts, list(first_contig)
+        calls, contigs = [], []
+        call_off = node_off = orf_off = 0
+        for r, c0 in zip(parts, self.first_contig):
+            cl = r.calls.copy()
+            cl["contig"] += c0
+            ct = r.contigs.copy()
+            ct["call_off"] += call_off
+            ct["node_off"] += node_off
+            ct["orf_off"] += orf_off
+            calls.append(cl)
+            contigs.append(ct)
+            call_off += r.n_calls
+            node_off += r.n_nodes
+            orf_off += r.n_orfs
+        self.calls = np.concatenate(calls) if calls else np.zeros(0, dtype=N.CALL)
+        self.contigs = np.concatenate(contigs) if contigs else np.zeros(0, dtype=N.CONTIG)
+        self.n_contigs, self.n_calls = len(self.contigs), len(self.calls)
+        self.n_bases = sum(r.n_bases for r in parts)
+        self.n_nodes, self.n_orfs = node_off, orf_off
+        self.n_overlaps = sum(r.n_overlaps for r in parts)
+        self.n_bridges = sum(r.n_bridges for r in parts)
+        self.launches = sum(r.launches for r in parts)
+        self.n_literal_presolve = sum(r.n_literal_presolve for r in parts)
+        self.n_literal_postsolve = sum(r.n_literal_postsolve for r in parts)
+        self.n_literal_overlaps = sum(r.n_literal_overlaps for r in parts)
+
+    def group_of(self, contig: int):
+        """(Result of the group holding `contig`, its index inside that group)"""
+        g = int(np.searchsorted(self.first_contig, contig, side="right")) - 1
+        return self.parts[g], contig - self.first_contig[g]
+
+    check = Result.check
+    call_rows = Result.call_rows
+
+
+class PipelinedEngine:
+    """Several contexts (streams) on one GPU, one host thread each.  A batch is cut into consecutive groups of
+    contigs; while one group's kernels run, the next group's letters are copied in and the previous group's
+    call table is copied out, so a run from pinned host buffers costs little more than the kernels alone.
+    Contigs are independent (phanotate.py:40-56), so grouping does not change any result."""
+
+    def __init__(self, device: int = 0, lanes: int = 4, lib_path: str | None = None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.engines = [Engine(device, lib_path) for _ in range(max(1, lanes))]
+        self.pool = ThreadPoolExecutor(len(self.engines))
+        self.device = device
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.pool.shutdown(wait=True)
+
+    def pin(self, arr):
+        return self.engines[0].pin(arr)
+
+    def unpin(self, arr):
+        return self.engines[0].unpin(arr)
+
+    def run_packed(self, bases, offsets, params=None, **kw):
+        if params is None:
+            params = make_params()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        lanes = min(len(self.engines), max(n, 1))
+        # consecutive groups of about equal size in bases
+        cuts = [0]
+        for k in range(1, lanes):
+            c = int(np.searchsorted(offsets, offsets[-1] * k // lanes, side="left"))
+            cuts.append(min(max(c, cuts[-1]), n))
+        cuts.append(n)
+
+        def work(k):
+            a, b = cuts[k], cuts[k + 1]
+            if b <= a:
+                return None
+            sub_off = offsets[a:b + 1] - offsets[a]
+            return self.engines[k].run_packed(bases[offsets[a]:offsets[b]], sub_off, params, **kw)
+
+        parts = list(self.pool.map(work, range(lanes)))
+        keep = [(r, cuts[k]) for k, r in enumerate(parts) if r is not None]
+        return MergedResult([r for r, _ in keep], [c for _, c in keep])

@@ -39,3 +39,18 @@ def md5(text: str) -> str:
 
 
 STRESS = sorted((k for k in INDEX if k.startswith("stress")), key=lambda s: int(s[6:]))
+
+
+ROOT = os.path.abspath(os.path.join(HERE, ".."))
+HOSTSIM = os.path.join(HERE, "native", "pb200_hostsim.so")
+
+
+def hostsim_path() -> str:
+    """Host build of the SAME stage functions the kernels run (tests only; see pb200.cu header); rebuilt when stale."""
+    import subprocess
+    src = os.path.join(ROOT, "phanotate_b200", "csrc")
+    deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "phanotate_b200.h")]
+    if not os.path.exists(HOSTSIM) or any(os.path.getmtime(d) > os.path.getmtime(HOSTSIM) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-DPB_HOSTSIM", "-shared", "-fPIC",
+                               "-o", HOSTSIM, os.path.join(src, "pb200.cu")])
+    return HOSTSIM

@@ -54,11 +54,8 @@ def test_start_codon_weights_match_reference_normalisation():
 @pytest.fixture(scope="module")
 def sim():
     """Host build of the SAME stage functions the kernels run (tests only; see pb200.cu header)."""
-    src = os.path.join(ROOT, "phanotate_b200", "csrc")
-    deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "phanotate_b200.h")]
-    if not os.path.exists(HOSTSIM) or any(os.path.getmtime(d) > os.path.getmtime(HOSTSIM) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-DPB_HOSTSIM", "-shared", "-fPIC",
-                               "-o", HOSTSIM, os.path.join(src, "pb200.cu")])
+    from helpers import hostsim_path
+    hostsim_path()
     e = engine.Engine(0, lib_path=HOSTSIM)
     yield e
     e.close()

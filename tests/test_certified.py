@@ -23,11 +23,8 @@ HOSTSIM = os.path.join(ROOT, "tests", "native", "pb200_hostsim.so")
 
 @pytest.fixture(scope="module")
 def sim():
-    src = os.path.join(ROOT, "phanotate_b200", "csrc")
-    deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "phanotate_b200.h")]
-    if not os.path.exists(HOSTSIM) or any(os.path.getmtime(d) > os.path.getmtime(HOSTSIM) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-DPB_HOSTSIM", "-shared", "-fPIC",
-                               "-o", HOSTSIM, os.path.join(src, "pb200.cu")])
+    from helpers import hostsim_path
+    hostsim_path()
     e = engine.Engine(0, lib_path=HOSTSIM)
     yield e
     e.close()

@@ -77,9 +77,8 @@ def _check(name):
 def sim_engine():
     import fastpathz
     from phanotate_modules import functions
-    if not os.path.exists(HOSTSIM):
-        pytest.skip("host build missing (tests/test_abi_host.py builds it)")
-    e = Engine(0, lib_path=HOSTSIM)
+    from helpers import hostsim_path
+    e = Engine(0, lib_path=hostsim_path())
     functions.set_engine(e)
     fastpathz._engine = e
     yield e
@@ -167,3 +166,27 @@ def test_call_table_gather_world_size_2_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_pipelined_engine_equals_single_context():
+    """PipelinedEngine (several contexts, groups of contigs) returns the same call / contig tables as one batch."""
+    import numpy as np
+    from helpers import STRESS, golden_text, seq_of
+    from phanotate_b200 import engine
+    from helpers import hostsim_path
+    hostsim_path()
+    names = ["phiX174"] + STRESS[:12] + ["lambda"] + STRESS[12:24]
+    seqs = [seq_of(n).encode() for n in names]
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    pe = engine.PipelinedEngine(0, lanes=3, lib_path=HOSTSIM)
+    e = engine.Engine(0, lib_path=HOSTSIM)
+    m, s = pe.run_packed(bases, offs), e.run_packed(bases, offs)
+    assert np.array_equal(m.calls, s.calls) and np.array_equal(m.contigs, s.contigs)
+    for k, n in enumerate(names):
+        assert "".join("%d\t%d\t%s\t%s\n" % r for r in m.call_rows(k)) == golden_text(n, "calls.tsv")
+    r, j = m.group_of(len(names) - 1)
+    assert int(r.contigs[j]["length"]) == len(seqs[-1])
+    pe.close()
+    e.close()
