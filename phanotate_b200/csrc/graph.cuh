@@ -626,6 +626,39 @@ PB_HDN void pack_orf(const Batch& B, i64 oi, OrfRec* out) {
     r.weight = B.o_weight[oi];
     out[oi] = r;
 }
+struct ContigRec {        // = pb200_contig
+    i32 length;
+    u32 err;
+    i32 node_off, n_nodes, orf_off, n_orfs, call_off, n_calls, n_ties, reserved;
+    Dec pstop, pos_max[4], pos_min[4];
+    double background_rbs[28], training_rbs[28];
+};
+PB_HDN void pack_contig(const Batch& B, i64 c, ContigRec* out) {
+    if (c >= B.nc) return;
+    const CStat* cs = B.cs + c;
+    ContigRec r;
+    r.length = cs->L;
+    r.err = cs->err;
+    r.node_off = B.cnode[c];
+    r.n_nodes = B.cnode[c + 1] - B.cnode[c];
+    r.orf_off = B.corf[c];
+    r.n_orfs = B.corf[c + 1] - B.corf[c];
+    r.call_off = (i32)B.call_cnt[c];
+    r.n_calls = (i32)(B.call_cnt[c + 1] - B.call_cnt[c]);
+    r.n_ties = (i32)cs->n_ties;
+    r.reserved = 0;
+    r.pstop = cs->pstop;
+    for (int k = 0; k < 4; k++) {
+        r.pos_max[k] = cs->pos_max[k];
+        r.pos_min[k] = cs->pos_min[k];
+    }
+    const double ybg = 28.0 + 2.0 * (double)cs->L, ytr = 28.0 + (double)r.n_orfs;     // functions.py:155-156,180-181,254-255
+    for (int k = 0; k < 28; k++) {
+        r.background_rbs[k] = (1.0 + (double)cs->hist_bg[k]) / ybg;
+        r.training_rbs[k] = (1.0 + (double)cs->hist_tr[k]) / ytr;
+    }
+    out[c] = r;
+}
 PB_HDN void pack_node(const Batch& B, i64 ni, NodeRec* out) {
     if (ni >= B.nn) return;
     NodeRec r;

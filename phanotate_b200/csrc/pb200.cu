@@ -19,6 +19,7 @@ static_assert(sizeof(pb200_call) == sizeof(CallRec), "CallRec layout");
 static_assert(sizeof(pb200_edge) == sizeof(EdgeRec), "EdgeRec layout");
 static_assert(sizeof(pb200_orf) == sizeof(OrfRec), "OrfRec layout");
 static_assert(sizeof(pb200_node) == sizeof(NodeRec), "NodeRec layout");
+static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
 
 #define NPHASE 12
 
@@ -106,6 +107,9 @@ __global__ void __launch_bounds__(PB_BLOCK) k_reach(const Batch B, i32 nc) {
 }
 __global__ void k_pack_orfs(const Batch B, OrfRec* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.no; i += (i64)gridDim.x * blockDim.x) pack_orf(B, i, out);
+}
+__global__ void k_pack_contigs(const Batch B, ContigRec* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.nc; i += (i64)gridDim.x * blockDim.x) pack_contig(B, i, out);
 }
 __global__ void k_pack_nodes(const Batch B, NodeRec* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.nn; i += (i64)gridDim.x * blockDim.x) pack_node(B, i, out);
@@ -788,35 +792,16 @@ int pb200_get_calls(pb200_ctx* ctx, pb200_call* out) {
 
 int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out) {
     if (!ctx || !ctx->have) return -2;
-    const Batch& B = ctx->B;
-    std::vector<CStat> cs(B.nc);
-    std::vector<i32> cnode(B.nc + 1), corf(B.nc + 1);
-    std::vector<u32> ccall(B.nc + 1);
-    PB_TO_HOST(cs.data(), B.cs, (size_t)B.nc * sizeof(CStat));
-    PB_TO_HOST(cnode.data(), B.cnode, (size_t)(B.nc + 1) * 4);
-    PB_TO_HOST(corf.data(), B.corf, (size_t)(B.nc + 1) * 4);
-    PB_TO_HOST(ccall.data(), B.call_cnt, (size_t)(B.nc + 1) * 4);
-    for (int c = 0; c < B.nc; c++) {
-        pb200_contig& o = out[c];
-        memset(&o, 0, sizeof(o));
-        o.length = cs[c].L;
-        o.err = cs[c].err;
-        o.node_off = cnode[c];
-        o.n_nodes = cnode[c + 1] - cnode[c];
-        o.orf_off = corf[c];
-        o.n_orfs = corf[c + 1] - corf[c];
-        o.call_off = (i32)ccall[c];
-        o.n_calls = (i32)(ccall[c + 1] - ccall[c]);
-        o.n_ties = (i32)cs[c].n_ties;
-        memcpy(&o.pstop, &cs[c].pstop, sizeof(Dec));
-        memcpy(o.pos_max, cs[c].pos_max, sizeof(Dec) * 4);
-        memcpy(o.pos_min, cs[c].pos_min, sizeof(Dec) * 4);
-        double ybg = 28.0 + 2.0 * (double)cs[c].L, ytr = 28.0 + (double)o.n_orfs;
-        for (int r = 0; r < 28; r++) {
-            o.background_rbs[r] = (1.0 + (double)cs[c].hist_bg[r]) / ybg;
-            o.training_rbs[r] = (1.0 + (double)cs[c].hist_tr[r]) / ytr;
-        }
-    }
+    Batch& B = ctx->B;
+    PB_PHASE(11, (size_t)B.nc * sizeof(ContigRec) + 1024);
+    ContigRec* tmp = PB_ALLOC(11, ContigRec, B.nc);
+#ifndef PB_HOSTSIM
+    k_pack_contigs<<<grid_for(ctx, B.nc, 128), 128, 0, ctx->stream>>>(B, tmp);
+    CK(cudaGetLastError());
+#else
+    for (i64 i = 0; i < B.nc; i++) pack_contig(B, i, tmp);
+#endif
+    PB_TO_HOST(out, tmp, (size_t)B.nc * sizeof(ContigRec));
     return 0;
 }
 

@@ -239,41 +239,21 @@ class Engine:
 
 class MergedResult:
     """Call and contig tables of a batch that ran as several groups (PipelinedEngine): same columns as Result,
-    contig ids and table offsets renumbered to the whole batch.  The per-group Results stay reachable for
-    the lazily fetched ORF / node / edge tables (`group_of(contig)`)."""
+    contig ids and table offsets renumbered to the whole batch.  `calls` and `contigs` are views into the
+    engine's pinned output buffers: valid until its next run (copy them to keep them)."""
 
-    def __init__(self, parts, first_contig):
-        self.parts, self.first_contig = parts, list(first_contig)
-        calls, contigs = [], []
-        call_off = node_off = orf_off = 0
-        for r, c0 in zip(parts, self.first_contig):
-            cl = r.calls.copy()
-            cl["contig"] += c0
-            ct = r.contigs.copy()
-            ct["call_off"] += call_off
-            ct["node_off"] += node_off
-            ct["orf_off"] += orf_off
-            calls.append(cl)
-            contigs.append(ct)
-            call_off += r.n_calls
-            node_off += r.n_nodes
-            orf_off += r.n_orfs
-        self.calls = np.concatenate(calls) if calls else np.zeros(0, dtype=N.CALL)
-        self.contigs = np.concatenate(contigs) if contigs else np.zeros(0, dtype=N.CONTIG)
-        self.n_contigs, self.n_calls = len(self.contigs), len(self.calls)
-        self.n_bases = sum(r.n_bases for r in parts)
-        self.n_nodes, self.n_orfs = node_off, orf_off
-        self.n_overlaps = sum(r.n_overlaps for r in parts)
-        self.n_bridges = sum(r.n_bridges for r in parts)
-        self.launches = sum(r.launches for r in parts)
-        self.n_literal_presolve = sum(r.n_literal_presolve for r in parts)
-        self.n_literal_postsolve = sum(r.n_literal_postsolve for r in parts)
-        self.n_literal_overlaps = sum(r.n_literal_overlaps for r in parts)
-
-    def group_of(self, contig: int):
-        """(Result of the group holding `contig`, its index inside that group)"""
-        g = int(np.searchsorted(self.first_contig, contig, side="right")) - 1
-        return self.parts[g], contig - self.first_contig[g]
+    def __init__(self, calls, contigs, first_contig, sizes, stats, launches):
+        self.calls, self.contigs, self.first_contig = calls, contigs, list(first_contig)
+        self.n_contigs, self.n_calls = len(contigs), len(calls)
+        self.n_bases = sum(z[1] for z in sizes)
+        self.n_nodes = sum(z[2] for z in sizes)
+        self.n_orfs = sum(z[3] for z in sizes)
+        self.n_overlaps = sum(z[4] for z in sizes)
+        self.n_bridges = sum(z[5] for z in sizes)
+        self.n_literal_presolve = sum(z[0] for z in stats)
+        self.n_literal_postsolve = sum(z[1] for z in stats)
+        self.n_literal_overlaps = sum(z[2] for z in stats)
+        self.launches = launches
 
     check = Result.check
     call_rows = Result.call_rows
@@ -281,17 +261,25 @@ class MergedResult:
 
 class PipelinedEngine:
     """Several contexts (streams) on one GPU, one host thread each.  A batch is cut into consecutive groups of
-    contigs; while one group's kernels run, the next group's letters are copied in and the previous group's
-    call table is copied out, so a run from pinned host buffers costs little more than the kernels alone.
-    Contigs are independent (phanotate.py:40-56), so grouping does not change any result."""
+    contigs; while one group's kernels run, the next group's letters are being copied in, so a run from
+    pinned host buffers costs little more than the kernels alone.  The call and contig tables of all groups
+    land in one pinned output buffer.  Contigs are independent (phanotate.py:40-56), so grouping does not
+    change any result.  For the ORF / node / edge tables use Engine."""
 
     def __init__(self, device: int = 0, lanes: int = 4, lib_path: str | None = None):
         from concurrent.futures import ThreadPoolExecutor
         self.engines = [Engine(device, lib_path) for _ in range(max(1, lanes))]
         self.pool = ThreadPoolExecutor(len(self.engines))
         self.device = device
+        self._calls = np.zeros(0, dtype=N.CALL)
+        self._contigs = np.zeros(0, dtype=N.CONTIG)
 
     def close(self):
+        for buf in (self._calls, self._contigs):
+            if len(buf):
+                self.engines[0].unpin(buf)
+        self._calls = np.zeros(0, dtype=N.CALL)
+        self._contigs = np.zeros(0, dtype=N.CONTIG)
         for e in self.engines:
             e.close()
         self.pool.shutdown(wait=True)
@@ -302,27 +290,60 @@ class PipelinedEngine:
     def unpin(self, arr):
         return self.engines[0].unpin(arr)
 
-    def run_packed(self, bases, offsets, params=None, **kw):
+    def _grow(self, name, rows, dtype):
+        buf = getattr(self, name)
+        if rows > len(buf):
+            if len(buf):
+                self.engines[0].unpin(buf)
+            buf = np.zeros(rows + rows // 4 + 1024, dtype=dtype)
+            self.engines[0].pin(buf)                  # page-locked: the device->host copies are plain DMA
+            setattr(self, name, buf)
+        return buf
+
+    def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0):
         if params is None:
             params = make_params()
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         lanes = min(len(self.engines), max(n, 1))
-        # consecutive groups of about equal size in bases
-        cuts = [0]
+        cuts = [0]                                    # consecutive groups of about equal size in bases
         for k in range(1, lanes):
             c = int(np.searchsorted(offsets, offsets[-1] * k // lanes, side="left"))
             cuts.append(min(max(c, cuts[-1]), n))
         cuts.append(n)
+        live = [k for k in range(lanes) if cuts[k + 1] > cuts[k]]
 
-        def work(k):
+        def compute(k):
             a, b = cuts[k], cuts[k + 1]
-            if b <= a:
-                return None
-            sub_off = offsets[a:b + 1] - offsets[a]
-            return self.engines[k].run_packed(bases[offsets[a]:offsets[b]], sub_off, params, **kw)
+            e = self.engines[k]
+            e.run_packed(bases[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], params, fetch=False,
+                         literal=literal, call_weights=call_weights, flags=flags)
+            st = np.zeros(8, dtype=np.int64)
+            e._ck(e.lib.pb200_stats(e.ctx, st.ctypes.data))
+            return e.sizes(), [int(v) for v in st[:3]], int(e.lib.pb200_launch_count(e.ctx))
 
-        parts = list(self.pool.map(work, range(lanes)))
-        keep = [(r, cuts[k]) for k, r in enumerate(parts) if r is not None]
-        return MergedResult([r for r, _ in keep], [c for _, c in keep])
+        done = list(self.pool.map(compute, live))
+        sizes = [d[0] for d in done]
+        ncalls, ncont = sum(z[6] for z in sizes), sum(z[0] for z in sizes)
+        calls = self._grow("_calls", ncalls, N.CALL)[:ncalls]
+        contigs = self._grow("_contigs", ncont, N.CONTIG)[:ncont]
+        call_off = np.concatenate(([0], np.cumsum([z[6] for z in sizes]))).astype(np.int64)
+        cont_off = np.concatenate(([0], np.cumsum([z[0] for z in sizes]))).astype(np.int64)
+        node_off = np.concatenate(([0], np.cumsum([z[2] for z in sizes]))).astype(np.int64)
+        orf_off = np.concatenate(([0], np.cumsum([z[3] for z in sizes]))).astype(np.int64)
+
+        def fetch(j):
+            e = self.engines[live[j]]
+            cl = calls[call_off[j]:call_off[j + 1]]
+            ct = contigs[cont_off[j]:cont_off[j + 1]]
+            if len(cl):
+                e._ck(e.lib.pb200_get_calls(e.ctx, cl.ctypes.data))
+                cl["contig"] += cuts[live[j]]
+            e._ck(e.lib.pb200_get_contigs(e.ctx, ct.ctypes.data))
+            ct["call_off"] += call_off[j]
+            ct["node_off"] += node_off[j]
+            ct["orf_off"] += orf_off[j]
+
+        list(self.pool.map(fetch, range(len(live))))
+        return MergedResult(calls, contigs, [cuts[k] for k in live], sizes, [d[1] for d in done], sum(d[2] for d in done))
