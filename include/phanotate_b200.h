@@ -87,7 +87,7 @@ typedef struct pb200_contig {
     uint32_t err;               /* PB200_ERR_* bits */
     int32_t node_off, n_nodes, orf_off, n_orfs, call_off, n_calls;
     int32_t n_ties;             /* relaxations that found an equal distance (tie-break diagnostics) */
-    int32_t reserved;
+    int32_t wide;               /* 1: some edge weight exceeds 110 bits and the solve ran on 256-bit distances */
     pb200_dec pstop;            /* contig-level P(stop) = pgap (functions.py:178,309) */
     pb200_dec pos_max[4], pos_min[4];   /* GC-frame exponents (functions.py:281-284) */
     double background_rbs[28], training_rbs[28];
@@ -109,6 +109,7 @@ enum {
     PB200_CALL_WEIGHTS = 16,  /* also fill pb200_call.weight with the 28-digit Decimal of every call (otherwise it is
                                  filled only where the Decimal chain ran anyway and is 0 elsewhere; pb200_call.score,
                                  the float that Locus.tabular prints with '%E', is always exact) */
+    PB200_SOLVE_WIDE = 32,    /* testing: 256-bit distances in the solve for every contig */
     PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly

@@ -25,7 +25,7 @@ NODE = np.dtype([("contig", "<i4"), ("position", "<i4"), ("kind", "<i4"), ("fram
                  ("orf", "<i4"), ("other_end", "<i4"), ("trigger", "<i4")])
 EDGE = np.dtype([("contig", "<i4"), ("src", "<i4"), ("dst", "<i4"), ("kind", "<i4"), ("weight", DEC)])
 CONTIG = np.dtype([("length", "<i4"), ("err", "<u4"), ("node_off", "<i4"), ("n_nodes", "<i4"), ("orf_off", "<i4"),
-                   ("n_orfs", "<i4"), ("call_off", "<i4"), ("n_calls", "<i4"), ("n_ties", "<i4"), ("reserved", "<i4"),
+                   ("n_orfs", "<i4"), ("call_off", "<i4"), ("n_calls", "<i4"), ("n_ties", "<i4"), ("wide", "<i4"),
                    ("pstop", DEC), ("pos_max", DEC, (4,)), ("pos_min", DEC, (4,)),
                    ("background_rbs", "<f8", (28,)), ("training_rbs", "<f8", (28,))])
 PARAMS = np.dtype([("n_start", "<i4"), ("start_codon", "S4", (8,)), ("start_weight", DEC, (8,)),
@@ -39,6 +39,7 @@ REUSE_INPUT = 2
 LITERAL = 4
 SCAN_REFERENCE = 8
 CALL_WEIGHTS = 16
+SOLVE_WIDE = 32
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 

@@ -155,6 +155,7 @@ PB_HDN void st_ov_weight(const Batch& B, i64 sl) {
     WInt wi;
     if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
     B.ov_wint[k] = wi;
+    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
     bool small = (wi.w[1] >> 30) == 0;               // 0 <= weight < 2^62 (overlap weights are positive)
 #pragma unroll
     for (int i = 2; i < WN; i++) small = small && wi.w[i] == 0;
@@ -228,6 +229,7 @@ PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
                     B.br_w[k] = w;
                     WInt wi;
                     if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+                    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
                     B.br_wint[k] = wi;
                     k++;
                 }
@@ -244,24 +246,6 @@ PB_HDN void st_br_fill(const Batch& B, i64 i) {
     if (i < B.nn) bridges_of(B, (i32)i, true);
 }
 
-// integer weight of score_gap(len,'same'|'diff') as the solver sees it
-PB_HD WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok, bool generic = false) {
-    *ok = true;
-    if (len <= 300) {
-        i64 k = (i64)c * GAPN + (len + 2);
-        return wint_from_i64(diff ? B.gapi_diff[k] : B.gapi_same[k]);
-    }
-    if (len <= 999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi3);
-    if (len <= 9999) return wint_from_i64((i64)len * 1000 + B.cs[c].gap_hi4);
-    if (!generic) {          // the solver only sees len < 500 (connect) and len <= 2000 (terminals)
-        *ok = false;
-        return wint_from_i64(0);
-    }
-    WInt w;
-    *ok = dec_to_wint(gap_score(B, c, len, diff), w);
-    return w;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Stage 12: exact single-source shortest path source -> target.  One warp per contig: nodes are
 // visited in position order, each visit pushes the node's out-edges (lanes over edges); an
@@ -273,45 +257,124 @@ PB_HD WInt gap_wint(const Batch& B, int c, int len, bool diff, bool* ok, bool ge
 #define PB_SYNCWARP()
 #endif
 
-struct SolveCtx {
-    const Batch* B;
-    int c;
-    u32 ties;
+// The distances are exact integers.  Two widths of the same algorithm: 128 bit (all weights of the contig below
+// 2^110, i.e. practically always: one 16-byte load/store and two 64-bit add/compare steps per relaxation) and 256
+// bit (CStat.wide: some ORF weight is astronomically large).
+struct
+#ifdef __CUDACC__
+    __align__(16)
+#endif
+    I128 {
+    u64 lo;
+    i64 hi;
 };
-PB_HD bool relax(const Batch& B, SolveCtx& S, i32 v, const WInt& cand, i32 from) {
-    WInt cur = B.dist[v];
-    if (wint_less(cand, cur)) {
-        B.dist[v] = cand;
+struct D256 {
+    typedef WInt T;
+    static PB_HD T inf() { return wint_inf(); }
+    static PB_HD bool is_inf(const T& a) { return wint_is_inf(a); }
+    static PB_HD bool less(const T& a, const T& b) { return wint_less(a, b); }
+    static PB_HD bool eq(const T& a, const T& b) { return w_cmp(a, b) == 0; }
+    static PB_HD T add(T a, const T& b) {
+        w_add(a, b);
+        return a;
+    }
+    static PB_HD T from_i64(i64 v) { return wint_from_i64(v); }
+    static PB_HD T load_w(const WInt* p) { return *p; }
+    static PB_HD T* dist(const Batch& B) { return B.dist; }
+    static PB_HD WInt to_wint(const T& a) { return a; }
+};
+struct D128 {
+    typedef I128 T;
+    static PB_HD T inf() {
+        T r;
+        r.lo = ~0ull;
+        r.hi = 0x7FFFFFFFFFFFFFFFll;
+        return r;
+    }
+    static PB_HD bool is_inf(const T& a) { return a.hi == 0x7FFFFFFFFFFFFFFFll; }
+    static PB_HD bool less(const T& a, const T& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+    static PB_HD bool eq(const T& a, const T& b) { return a.hi == b.hi && a.lo == b.lo; }
+    static PB_HD T add(T a, const T& b) {
+        const u64 lo = a.lo + b.lo;
+        a.hi = (i64)((u64)a.hi + (u64)b.hi + (lo < a.lo ? 1ull : 0ull));
+        a.lo = lo;
+        return a;
+    }
+    static PB_HD T from_i64(i64 v) {
+        T r;
+        r.lo = (u64)v;
+        r.hi = v < 0 ? -1ll : 0ll;
+        return r;
+    }
+    static PB_HD T load_w(const WInt* p) {      // low 128 bits of the two's complement value
+        const U4 q = *(const U4*)p;
+        T r;
+        r.lo = ((u64)q.y << 32) | q.x;
+        r.hi = (i64)(((u64)q.w << 32) | q.z);
+        return r;
+    }
+    static PB_HD T* dist(const Batch& B) { return B.dist128; }
+    static PB_HD WInt to_wint(const T& a) {
+        WInt r;
+        r.w[0] = (u32)a.lo;
+        r.w[1] = (u32)(a.lo >> 32);
+        r.w[2] = (u32)(u64)a.hi;
+        r.w[3] = (u32)((u64)a.hi >> 32);
+        const u32 ext = a.hi < 0 ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+        for (int i = 4; i < WN; i++) r.w[i] = ext;
+        if (is_inf(a)) r = wint_inf();
+        return r;
+    }
+};
+// integer weight of score_gap(len,'same'|'diff') as the solver sees it; len < 500 (connect), <= 2000 (terminals)
+PB_HD i64 gap_w64(const Batch& B, int c, int len, bool diff, bool* ok) {
+    *ok = true;
+    if (len <= 300) {
+        const i64 k = (i64)c * GAPN + (len + 2);
+        return diff ? B.gapi_diff[k] : B.gapi_same[k];
+    }
+    if (len <= 999) return (i64)len * 1000 + B.cs[c].gap_hi3;
+    if (len <= 9999) return (i64)len * 1000 + B.cs[c].gap_hi4;
+    *ok = false;
+    return 0;
+}
+
+template <class D>
+PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const typename D::T& cand, i32 from) {
+    const typename D::T cur = dist[v];
+    if (D::less(cand, cur)) {
+        dist[v] = cand;
         B.parent[v] = from;
         B.dirty[v] = 1;
         return true;
     }
-    if (!wint_is_inf(cur) && w_cmp(cand, cur) == 0 && B.parent[v] != from) S.ties++;
+    if (!D::is_inf(cur) && D::eq(cand, cur) && B.parent[v] != from) ties++;
     return false;
 }
 
-PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
+template <class D>
+PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
+    typedef typename D::T T;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
     CStat* cs = B.cs + c;
     const int L = cs->L;
-    SolveCtx S;
-    S.B = &B;
-    S.c = c;
-    S.ties = 0;
+    T* dist = D::dist(B);
+    u32 ties = 0;
     bool okw = true;
     for (i32 i = nb + lane; i < ne; i += NL) {
-        B.dist[i] = wint_inf();
+        dist[i] = D::inf();
         B.parent[i] = -1;
         B.dirty[i] = 0;
     }
-    WInt tdist = wint_inf();
+    T tdist = D::inf();
     i32 tpar = -1;
     PB_SYNCWARP();
     // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
     for (i32 i = nb + lane; i < ne && B.n_pos[i] <= 2000; i += NL) {
         if (kind_is_entry(B.n_kind[i] & 3)) {
             bool o;
-            B.dist[i] = gap_wint(B, c, B.n_pos[i], false, &o);
+            dist[i] = D::from_i64(gap_w64(B, c, B.n_pos[i], false, &o));
             okw = okw && o;
             B.parent[i] = -2;
             B.dirty[i] = 1;
@@ -347,26 +410,19 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
             break;
         }
         const i32 u = i;
-        const WInt Du = B.dist[u];
+        const T Du = dist[u];
         const int kind = B.n_kind[u] & 3;
         const int pu = B.n_pos[u];
         PB_SYNCWARP();
         if (lane == 0) B.dirty[u] = 0;
         i32 rewind = 0x7FFFFFFF;
         if (kind == K_FSTART) {
-            if (lane == 0) {
-                WInt cand = Du;
-                w_add(cand, B.o_wint[B.n_orf[u]]);
-                relax(B, S, B.n_mate[u], cand, u);
-            }
+            if (lane == 0) relax<D>(B, ties, dist, B.n_mate[u], D::add(Du, D::load_w(B.o_wint + B.n_orf[u])), u);
         } else if (kind == K_RSTOP) {
             const int farpos = B.n_pos[B.n_mate[u]];
             for (i32 j = u + 1 + lane; j < ne && B.n_pos[j] <= farpos; j += NL) {
-                if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == u) {
-                    WInt cand = Du;
-                    w_add(cand, B.o_wint[B.n_orf[j]]);
-                    relax(B, S, j, cand, u);
-                }
+                if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == u)
+                    relax<D>(B, ties, dist, j, D::add(Du, D::load_w(B.o_wint + B.n_orf[j])), u);
             }
         } else {
             // gap edges to entries within 500 bp downstream (functions.py:360-438)
@@ -377,36 +433,29 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
                 bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
                 if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
                 bool o;
-                WInt cand = Du;
-                w_add(cand, gap_wint(B, c, d - 3, diff, &o));
-                relax(B, S, j, cand, u);
+                relax<D>(B, ties, dist, j, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
             }
             // overlap edges (backwards)
             for (u32 k = B.ov_cnt[u] + lane; k < B.ov_cnt[u + 1]; k += NL) {
-                WInt cand = Du;
                 const i64 w64 = B.ov_w64[k];
-                if (w64 != OV_W64_WIDE) w_add(cand, wint_from_i64(w64));
-                else w_add(cand, B.ov_wint[k]);
-                i32 v = B.ov_dst[k];
-                if (relax(B, S, v, cand, u) && v < rewind) rewind = v;
+                const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
+                const i32 v = B.ov_dst[k];
+                if (relax<D>(B, ties, dist, v, cand, u) && v < rewind) rewind = v;
             }
             // bridges
             for (u32 k = brb + lane; k < bre; k += NL) {
                 if (B.br_src[k] != u) continue;
-                WInt cand = Du;
-                w_add(cand, B.br_wint[k]);
-                relax(B, S, B.br_dst[k], cand, u);
+                relax<D>(B, ties, dist, B.br_dst[k], D::add(Du, D::load_w(B.br_wint + k)), u);
             }
             // exit -> target within 2000 bp of the right end (functions.py:448-451)
             if (L - pu <= 2000) {
                 bool o;
-                WInt cand = Du;
-                w_add(cand, gap_wint(B, c, L - pu, false, &o));
+                const T cand = D::add(Du, D::from_i64(gap_w64(B, c, L - pu, false, &o)));
                 okw = okw && o;
-                if (wint_less(cand, tdist)) {
+                if (D::less(cand, tdist)) {
                     tdist = cand;
                     tpar = u;
-                } else if (!wint_is_inf(tdist) && w_cmp(cand, tdist) == 0 && tpar != u) S.ties++;
+                } else if (!D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
             }
         }
 #ifdef __CUDA_ARCH__
@@ -418,12 +467,16 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
         PB_SYNCWARP();
         i = (rewind < u) ? rewind : u + 1;
     }
-    if (S.ties) PB_ATOMIC_ADD(&cs->n_ties, S.ties);
+    if (ties) PB_ATOMIC_ADD(&cs->n_ties, ties);
     if (!okw && lane == 0) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
     if (lane == 0) {
-        B.tdist[c] = tdist;
+        B.tdist[c] = D::to_wint(tdist);
         B.tparent[c] = tpar;
     }
+}
+PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
+    if (B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE)) solve_contig_t<D256>(B, c, lane, NL);
+    else solve_contig_t<D128>(B, c, lane, NL);
 }
 
 // Stage 13: walk the parent pointers back from the target; the ORF edges on the path are the calls
@@ -629,7 +682,7 @@ PB_HDN void pack_orf(const Batch& B, i64 oi, OrfRec* out) {
 struct ContigRec {        // = pb200_contig
     i32 length;
     u32 err;
-    i32 node_off, n_nodes, orf_off, n_orfs, call_off, n_calls, n_ties, reserved;
+    i32 node_off, n_nodes, orf_off, n_orfs, call_off, n_calls, n_ties, wide;
     Dec pstop, pos_max[4], pos_min[4];
     double background_rbs[28], training_rbs[28];
 };
@@ -646,7 +699,7 @@ PB_HDN void pack_contig(const Batch& B, i64 c, ContigRec* out) {
     r.call_off = (i32)B.call_cnt[c];
     r.n_calls = (i32)(B.call_cnt[c + 1] - B.call_cnt[c]);
     r.n_ties = (i32)cs->n_ties;
-    r.reserved = 0;
+    r.wide = (cs->wide || (B.flags & PB200_SOLVE_WIDE)) ? 1 : 0;
     r.pstop = cs->pstop;
     for (int k = 0; k < 4; k++) {
         r.pos_max[k] = cs->pos_max[k];

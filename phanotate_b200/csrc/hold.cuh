@@ -404,5 +404,6 @@ PB_HDN void st_orf_finish(const Batch& B, i64 sl) {
     WInt wi;
     if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
     B.o_wint[oi] = wi;
+    if (!wint_is_narrow(wi)) cs->wide = 1;         // (benign race: every writer stores 1)
     B.o_lit[oi] = 1;
 }

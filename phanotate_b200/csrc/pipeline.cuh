@@ -67,6 +67,7 @@ struct CStat {
     Fx fmax[4], fmin[4];
     u8 max_one[4], min_one[4];
     i32 n_calls;
+    i32 wide;               // some edge weight of the contig needs more than 110 bits: 256-bit distances in the solve
     i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
     DD fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
@@ -138,6 +139,7 @@ struct Batch {
     WInt* br_wint;
     // solve
     WInt* dist;
+    struct I128* dist128; // [nn] distances of the contigs solved at 128 bits
     i32* parent;
     u8* dirty;
     WInt* tdist;          // [nc] distance of the target

@@ -187,6 +187,15 @@ PB_HD WInt wint_inf() {
     r.w[WN - 1] = 0x7FFFFFFFu;
     return r;
 }
+// |w| < 2^110 ?  (sums over a contig's <= 2^14-edge paths then stay inside 128 bits)
+PB_HD bool wint_is_narrow(const WInt& w) {
+    const u32 ext = (w.w[WN - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+    bool ok = true;
+#pragma unroll
+    for (int i = 4; i < WN; i++) ok = ok && w.w[i] == ext;
+    const u32 top = w.w[3] ^ ext;               // bits 96..127 relative to the sign
+    return ok && (top >> 14) == 0;
+}
 PB_HDNI bool dec_to_wint(const Dec& d, WInt& out) {
     Wide<WN> mag;
     bool ok = dec_to_milli_int<WN>(d, mag);

@@ -119,3 +119,22 @@ def test_closed_form_error_bound_holds_on_reference_weights():
                 worst = max(worst, rel / bound)
     assert worst < Decimal("0.25")                    # observed: 0.03
     assert worst_x < Decimal("0.5")
+
+
+def test_wide_and_narrow_solver_agree(sim):
+    """128-bit and 256-bit distances are the same algorithm: forcing the wide solver changes nothing; and a contig
+    with an astronomically heavy ORF (an 800-codon repeat without a stop, weight ~1e40) is solved wide on its own and matches the oracle."""
+    import random
+    from oracle import phanotate_oracle as O
+    seqs = [seq_of(n) for n in ("T4", "lambda", "phiX174")]
+    a = sim.run(seqs)
+    b = sim.run(seqs, flags=N.SOLVE_WIDE)
+    assert np.array_equal(a.calls, b.calls) and int(a.contigs["wide"].sum()) == 0 and int(b.contigs["wide"].sum()) == 3
+    rng = random.Random(7)
+    rnd = lambda n: "".join(rng.choice("acgt") for _ in range(n))
+    heavy = rnd(400) + "atg" + "atc" * 800 + "taa" + rnd(400)
+    r = sim.run([heavy, seq_of("phiX174")])
+    assert int(r.contigs[0]["wide"]) == 1 and int(r.contigs[1]["wide"]) == 0 and int(r.contigs[0]["err"]) == 0
+    want = [row[:4] for row in O.call_contig(heavy)[3]]
+    assert r.call_rows(0) == want
+    assert "".join("%d\t%d\t%s\t%s\n" % x for x in r.call_rows(1)) == golden_text("phiX174", "calls.tsv")

@@ -112,3 +112,12 @@ def test_tiled_scan_equals_reference_scan(eng):
     assert np.array_equal(a.calls, b.calls)
     assert np.array_equal(a.orfs, b.orfs)
     assert np.array_equal(a.nodes, b.nodes)
+
+
+def test_wide_solver_on_gpu(eng):
+    """256-bit distances forced for every contig give the same calls as the default 128-bit solve."""
+    seqs = [seq_of(n).encode() for n in ("T4", "lambda", "phiX174")] + [seq_of(n).encode() for n in STRESS[:16]]
+    a = eng.run(seqs)
+    b = eng.run(seqs, flags=N.SOLVE_WIDE)
+    assert np.array_equal(a.calls, b.calls)
+    assert int(a.contigs["wide"].sum()) == 0 and int(b.contigs["wide"].sum()) == len(seqs)
