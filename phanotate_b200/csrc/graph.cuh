@@ -60,6 +60,7 @@ PB_HDN void st_node_attrs(const Batch& B, i64 ni64) {
     }
     B.n_oth[ni] = oth;
     B.n_oidx[ni] = oidx;
+    B.n_pk[ni] = ((u32)p << 4) | (u32)(B.n_kind[ni] & 15);
 }
 
 // overlap predicate for (left entry e at l, right exit x at r), functions.py:400-438
@@ -340,9 +341,10 @@ PB_HD i64 gap_w64(const Batch& B, int c, int len, bool diff, bool* ok) {
     return 0;
 }
 
+// relaxation of node v whose current distance `cur` the caller already holds
 template <class D>
-PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const typename D::T& cand, i32 from) {
-    const typename D::T cur = dist[v];
+PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const typename D::T& cur, const typename D::T& cand,
+                 i32 from) {
     if (D::less(cand, cur)) {
         dist[v] = cand;
         B.parent[v] = from;
@@ -353,6 +355,8 @@ PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const ty
     return false;
 }
 
+// Loads that do not depend on each other are issued together (node word, distance of the candidate target,
+// edge ranges), so a visit is two or three memory round trips deep instead of five.
 template <class D>
 PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
     typedef typename D::T T;
@@ -360,30 +364,32 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
     CStat* cs = B.cs + c;
     const int L = cs->L;
     T* dist = D::dist(B);
+    const u32* pk = B.n_pk;                       // position << 4 | kind | frame << 2
     u32 ties = 0;
     bool okw = true;
     for (i32 i = nb + lane; i < ne; i += NL) {
-        dist[i] = D::inf();
-        B.parent[i] = -1;
-        B.dirty[i] = 0;
+        const u32 w = pk[i];
+        T d0 = D::inf();
+        i32 p0 = -1;
+        u8 f0 = 0;
+        // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
+        if ((int)(w >> 4) <= 2000 && kind_is_entry((int)(w & 3))) {
+            bool o;
+            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4), false, &o));
+            okw = okw && o;
+            p0 = -2;
+            f0 = 1;
+        }
+        dist[i] = d0;
+        B.parent[i] = p0;
+        B.dirty[i] = f0;
     }
     T tdist = D::inf();
     i32 tpar = -1;
     PB_SYNCWARP();
-    // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
-    for (i32 i = nb + lane; i < ne && B.n_pos[i] <= 2000; i += NL) {
-        if (kind_is_entry(B.n_kind[i] & 3)) {
-            bool o;
-            dist[i] = D::from_i64(gap_w64(B, c, B.n_pos[i], false, &o));
-            okw = okw && o;
-            B.parent[i] = -2;
-            B.dirty[i] = 1;
-        }
-    }
-    PB_SYNCWARP();
     const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
     i32 i = nb;
-    i64 budget = 64 * (i64)(ne - nb) + 1024;
+    int budget = 64 * (ne - nb) + 1024;
     while (i < ne) {
         // next dirty node at or after i
 #ifdef __CUDA_ARCH__
@@ -410,42 +416,63 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
             break;
         }
         const i32 u = i;
+        const u32 wu = pk[u];
         const T Du = dist[u];
-        const int kind = B.n_kind[u] & 3;
-        const int pu = B.n_pos[u];
+        const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
         PB_SYNCWARP();
         if (lane == 0) B.dirty[u] = 0;
         i32 rewind = 0x7FFFFFFF;
         if (kind == K_FSTART) {
-            if (lane == 0) relax<D>(B, ties, dist, B.n_mate[u], D::add(Du, D::load_w(B.o_wint + B.n_orf[u])), u);
+            if (lane == 0) {
+                const i32 v = B.n_mate[u], orf = B.n_orf[u];
+                const T cur = dist[v];
+                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+            }
         } else if (kind == K_RSTOP) {
-            const int farpos = B.n_pos[B.n_mate[u]];
-            for (i32 j = u + 1 + lane; j < ne && B.n_pos[j] <= farpos; j += NL) {
-                if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == u)
-                    relax<D>(B, ties, dist, j, D::add(Du, D::load_w(B.o_wint + B.n_orf[j])), u);
+            const int farpos = (int)(pk[B.n_mate[u]] >> 4);
+            for (i32 j = u + 1 + lane; j < ne; j += NL) {
+                const u32 wj = pk[j];
+                const i32 mj = B.n_mate[j];
+                if ((int)(wj >> 4) > farpos) break;
+                if ((int)(wj & 3) == K_RSTART && mj == u) {
+                    const i32 orf = B.n_orf[j];
+                    const T cur = dist[j];
+                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+                }
             }
         } else {
+            const u32 ovb = B.ov_cnt[u], ove = B.ov_cnt[u + 1];
             // gap edges to entries within 500 bp downstream (functions.py:360-438)
-            for (i32 j = u + 1 + lane; j < ne && B.n_pos[j] - pu < 500; j += NL) {
-                const int kj = B.n_kind[j] & 3;
-                const int d = B.n_pos[j] - pu;
+            for (i32 j = u + 1 + lane; j < ne; j += NL) {
+                const u32 wj = pk[j];
+                const T cur = dist[j];
+                const int kj = (int)(wj & 3), d = (int)(wj >> 4) - pu;
+                if (d >= 500) break;
                 if (d <= 0 || !kind_is_entry(kj)) continue;
                 bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
                 if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
                 bool o;
-                relax<D>(B, ties, dist, j, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                relax<D>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
             }
             // overlap edges (backwards)
-            for (u32 k = B.ov_cnt[u] + lane; k < B.ov_cnt[u + 1]; k += NL) {
-                const i64 w64 = B.ov_w64[k];
-                const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
-                const i32 v = B.ov_dst[k];
-                if (relax<D>(B, ties, dist, v, cand, u) && v < rewind) rewind = v;
+            if (ove > ovb) {
+                for (u32 k = ovb + lane; k < ove; k += NL) {
+                    const i64 w64 = B.ov_w64[k];
+                    const i32 v = B.ov_dst[k];
+                    const T cur = dist[v];
+                    const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
+                    if (relax<D>(B, ties, dist, v, cur, cand, u) && v < rewind) rewind = v;
+                }
+#ifdef __CUDA_ARCH__
+                rewind = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)rewind);
+#endif
             }
             // bridges
             for (u32 k = brb + lane; k < bre; k += NL) {
                 if (B.br_src[k] != u) continue;
-                relax<D>(B, ties, dist, B.br_dst[k], D::add(Du, D::load_w(B.br_wint + k)), u);
+                const i32 v = B.br_dst[k];
+                const T cur = dist[v];
+                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u);
             }
             // exit -> target within 2000 bp of the right end (functions.py:448-451)
             if (L - pu <= 2000) {
@@ -458,12 +485,6 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
                 } else if (!D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
             }
         }
-#ifdef __CUDA_ARCH__
-        for (int o = 16; o > 0; o >>= 1) {
-            i32 other = __shfl_xor_sync(0xFFFFFFFFu, rewind, o);
-            rewind = other < rewind ? other : rewind;
-        }
-#endif
         PB_SYNCWARP();
         i = (rewind < u) ? rewind : u + 1;
     }
@@ -474,8 +495,9 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
         B.tparent[c] = tpar;
     }
 }
+PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE); }
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
-    if (B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE)) solve_contig_t<D256>(B, c, lane, NL);
+    if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
     else solve_contig_t<D128>(B, c, lane, NL);
 }
 
@@ -699,7 +721,7 @@ PB_HDN void pack_contig(const Batch& B, i64 c, ContigRec* out) {
     r.call_off = (i32)B.call_cnt[c];
     r.n_calls = (i32)(B.call_cnt[c + 1] - B.call_cnt[c]);
     r.n_ties = (i32)cs->n_ties;
-    r.wide = (cs->wide || (B.flags & PB200_SOLVE_WIDE)) ? 1 : 0;
+    r.wide = contig_is_wide(B, (int)c) ? 1 : 0;
     r.pstop = cs->pstop;
     for (int k = 0; k < 4; k++) {
         r.pos_max[k] = cs->pos_max[k];

@@ -79,12 +79,21 @@ PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 
 #include "scan_tile.cuh"
-// one warp per contig
-__global__ void __launch_bounds__(PB_BLOCK) k_solve(const Batch B, i32 nc) {
+// one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
+// dependent memory round trips per contig: throughput comes from the number of contigs in flight)
+__global__ void __launch_bounds__(PB_BLOCK, 12) k_solve(const Batch B, i32 nc) {
     const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    for (i64 c = warp; c < nc; c += nwarps) solve_contig(B, (int)c, lane, 32);
+    for (i64 c = warp; c < nc; c += nwarps)
+        if (!contig_is_wide(B, (int)c)) solve_contig_t<D128>(B, (int)c, lane, 32);
+}
+__global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 c = warp; c < nc; c += nwarps)
+        if (contig_is_wide(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
 }
 // per-codon product + Orf.score, ORFs in length-sorted order; each thread keeps its six prepared
 // factors in shared memory (18 x 16 B, stride = block size: conflict-free 128-bit loads)
@@ -316,6 +325,8 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         t_.b = ev_get(ctx);                                                                      \
         cudaEventRecord(t_.a, ctx->stream);                                                      \
         k_solve<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        ctx->launches++;                                                                         \
         cudaEventRecord(t_.b, ctx->stream);                                                      \
         ctx->times.push_back(t_);                                                                \
         ctx->launches++;                                                                         \

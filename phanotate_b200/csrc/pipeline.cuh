@@ -114,6 +114,7 @@ struct Batch {
     i32* n_trig;
     i32* n_oth;
     i32* n_oidx;
+    u32* n_pk;            // [nn] position << 4 | kind | frame << 2: the one word the solve reads per node
     // ORFs
     i32* o_start;
     i32* o_stop;
