@@ -25,21 +25,6 @@
 #pragma once
 #include "graph.cuh"
 
-// number of set bits of M in [g0, g1) at positions = rg (mod 3), for five masks at once
-PB_HD void count_frame_bits5(u64* const* M, i64 g0, i64 g1, int rg, u32* n) {
-#pragma unroll
-    for (int k = 0; k < 5; k++) n[k] = 0;
-    if (g1 <= g0) return;
-    const i64 w0 = g0 >> 6, w1 = (g1 - 1) >> 6;
-    for (i64 w = w0; w <= w1; w++) {
-        u64 m = frame_pat(w, rg);
-        if (w == w0) m &= ~0ull << (g0 & 63);
-        if (w == w1) m &= ~0ull >> (63 - ((g1 - 1) & 63));
-#pragma unroll
-        for (int k = 0; k < 5; k++) n[k] += (u32)pb_popc64(M[k][w] & m);
-    }
-}
-
 // Per-contig / global double-double constants of the closed form.  item = contig*28 + r (RBS bin);
 // items 0..8 of contig 0 also convert the start-codon weights (index 8 = no start codon -> 1000).
 PB_HDN void st_fast_tables(const Batch& B, i64 item) {

@@ -165,6 +165,8 @@ struct Batch {
     u64* bT;
     u64* mNS;             // bit set where a start node sits
     u64* mNK;             // bit set where a stop-key node sits
+    u8* rbsf;             // [nb] score_rbs(dna[i:i+21]) per base (the RBS background, functions.py:168)
+    u8* rbsr;             // [nb] score_rbs(rev_comp(dna[i:i+21])) (functions.py:169)
     u64* cF[5];           // bit set where the forward codon starting here has GC-frame factor index k (k = 5: the rest)
     u64* cR[5];           // same for the reverse strand
     // node-parallel fill / ORF scoring split
@@ -232,6 +234,7 @@ PB_HD int base_code(u8 ch) {
     }
 }
 PB_HD int gc_flag(u8 ch) { return (ch == 'g' || ch == 'c' || ch == 's' || ch == 'b' || ch == 'v') ? 1 : 0; }
+PB_HD int base_code_of(u8 raw) { return TBL(ch_code)[raw] & 7; }      // = base_code(lower(raw)), one table load
 
 PB_HD int contig_of(const Batch& B, i64 g) {
     int lo = 0, hi = B.nc;             // coff[lo] <= g < coff[hi]
@@ -444,6 +447,8 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         }
         if (sf) PB_ATOMIC_ADD(&cs->hist_bg[sf], 1u);
         if (sr) PB_ATOMIC_ADD(&cs->hist_bg[sr], 1u);
+        B.rbsf[(meta - B.meta) + i] = (u8)sf;
+        B.rbsr[(meta - B.meta) + i] = (u8)sr;
     }
     PB_ATOMIC_ADD(&cs->nAT, nAT);
     PB_ATOMIC_ADD(&cs->nGC, nGC);

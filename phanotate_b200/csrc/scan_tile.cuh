@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
         const i64 tg1 = (tg0 + ST_T < B.nb) ? tg0 + ST_T : B.nb;
         const i64 gb = tg0 + 8 * tid;                // this thread's bases: gb .. gb+7
         u32 meta_lo = 0, meta_hi = 0;
-        u64 acc_cls = 0, acc_cd = 0, acc_kf = 0, acc_kr = 0;
+        u64 acc_cls = 0, acc_cd = 0, acc_kf = 0, acc_kr = 0, acc_sf = 0, acc_sr = 0;
         const uint4 raw = raw_next;
         if (tile + 1 < t1) raw_next = scan_load_chunk(B, tg0 + ST_T, tid, wide);   // in flight during this tile's phases
         while (ce <= tg0 && c + 1 < B.nc) {           // (skips empty contigs too)
@@ -290,6 +290,8 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     }
                     if (sf) S.hpriv[sf][tid]++;
                     if (sr) S.hpriv[sr][tid]++;
+                    acc_sf |= (u64)sf << (8 * k);
+                    acc_sr |= (u64)sr << (8 * k);
                 }
             }
             __syncthreads();
@@ -332,7 +334,13 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
         // ---- outputs of the tile
         if (gb + 8 <= B.nb) {
             *(u64*)(B.meta + gb) = ((u64)meta_hi << 32) | meta_lo;
+            *(u64*)(B.rbsf + gb) = acc_sf;
+            *(u64*)(B.rbsr + gb) = acc_sr;
         } else {
+            for (int k = 0; k < 8 && gb + k < B.nb; k++) {
+                B.rbsf[gb + k] = (u8)(acc_sf >> (8 * k));
+                B.rbsr[gb + k] = (u8)(acc_sr >> (8 * k));
+            }
             for (int k = 0; k < 8 && gb + k < B.nb; k++)
                 B.meta[gb + k] = (u8)((k < 4 ? (meta_lo >> (8 * k)) : (meta_hi >> (8 * (k - 4)))) & 0xFFu);
         }
