@@ -8,7 +8,7 @@
 // into /root/reference.
 //
 // HBM layout (structure of arrays, contigs concatenated):
-//   per base   : seq (input, 1 B), meta (1 B: GC-frame factor index fwd | rev), nflag (1 B), 10 bit masks (1.25 B)
+//   per base   : seq (input, 1 B), meta (1 B: GC-frame factor index fwd | rev), RBS scores (2 B), 26 bit masks (3.25 B)
 //   per 64 bp  : rank_nodes / rank_orfs (exclusive prefix counts -> node / ORF index of a position)
 //   per node   : position, kind, mate, ORF id, trigger, other_end, pstop index (sorted by contig, position)
 //   per ORF    : start, stop, frame, rbs score, start-codon weight id, pstop, weight (Dec), integer weight
@@ -93,7 +93,6 @@ struct Batch {
     const u8* seq;
     const i64* coff;
     u8* meta;
-    u8* nflag;
     u64* rank;            // per 64-base block: low 32 = nodes before, high 32 = ORFs before
     CStat* cs;
     Dec* gap_same;
@@ -165,6 +164,7 @@ struct Batch {
     u64* bT;
     u64* mNS;             // bit set where a start node sits
     u64* mNK;             // bit set where a stop-key node sits
+    u64* mk[4];           // the same by node type: forward start, reverse start, forward stop key, reverse stop key
     u8* rbsf;             // [nb] score_rbs(dna[i:i+21]) per base (the RBS background, functions.py:168)
     u8* rbsr;             // [nb] score_rbs(rev_comp(dna[i:i+21])) (functions.py:169)
     u64* cF[5];           // bit set where the forward codon starting here has GC-frame factor index k (k = 5: the rest)
@@ -489,6 +489,14 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
 #include "enum_fwd.inc"
 // Stage 3: per 64-base block counts (nodes in the low word, ORFs = start nodes in the high word)
 PB_HDN void st_count64(const Batch& B, i64 blk) {
+    const u64 sf = B.mk[0][blk], sr = B.mk[1][blk], kf = B.mk[2][blk], kr = B.mk[3][blk];
+    B.mNS[blk] = sf | sr;
+    B.mNK[blk] = kf | kr;
+    if ((sf & sr) | (kf & kr)) {             // one position, two nodes of the same role: cannot happen (exclusive codon classes)
+        i64 g = blk << 6;
+        if (g >= B.nb) g = B.nb - 1;
+        PB_ATOMIC_OR(&B.cs[contig_of(B, g)].err, (u32)ERR_INTERNAL);
+    }
     u32 ns = (u32)pb_popc64(B.mNS[blk]), nk = (u32)pb_popc64(B.mNK[blk]);
     B.rank[blk] = (u64)(ns + nk) | ((u64)ns << 32);
 }
