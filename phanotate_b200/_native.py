@@ -74,6 +74,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_stats.argtypes = [vp, vp]
     lib.pb200_get_orf_int_weights.argtypes = [vp, vp]
     lib.pb200_get_overlap_int_weights.argtypes = [vp, vp]
+    lib.pb200_get_gap_int_weights.argtypes = [vp, vp, vp]
     for f in ("pb200_get_calls", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_get_edges"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pb200_build_edges.argtypes = [vp]
@@ -96,7 +97,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
 
 
 EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_sizes", "pb200_stats",
-           "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_calls",
+           "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_gap_int_weights", "pb200_get_calls",
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_stage_times", "pb200_launch_count", "pb200_last_run_ms",
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes"]

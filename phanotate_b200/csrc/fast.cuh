@@ -187,6 +187,70 @@ PB_HDN void st_lit_rest(const Batch& B, i64 oi) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gap edges (functions.py:36-46) for 0 <= len <= 300: trunc(1000 / g**(len/3)) (+ 20000 for 'diff') from
+// exp((len/3) * -ln g) in double-double arithmetic, g = 1 - pstop of the contig (its literal Decimal).  Roundings of
+// the reference: the power (<= 1 ulp), 1/x, + 20 (half an ulp each): <= 2.01e-27 relative; accepted when the value
+// (1 +- 2^-86) does not straddle an integer, else (and for g outside [7/8, 1)) the Decimal arithmetic runs
+// right here.  The Decimal tables gap_same / gap_diff themselves are only built for the edge dump.  item = contig*GAPN + len+2
+PB_HDN void st_gap_fast(const Batch& B, i64 item) {
+    const i64 c = item / GAPN;
+    if (c >= B.nc) return;
+    CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    const int len = (int)(item % GAPN) - 2;
+    DD g;
+    bool fast = dd_from_dec(cs->g, g) && g.hi < 1.0 && g.hi >= 0.875;
+    i64 vs = 0, vd = 0;
+    if (fast) {
+        const DD p = dd_add(dd_from_d(1.0), dd_neg(g));
+        const DD T = dd_mul_d(dd_neglog1m(p), fabs((double)len / 3.0));    // Decimal(len/3) is exactly this double
+        int K;
+        DD P = dd_exp_split(T, &K);
+        P.hi = ldexp(P.hi, K);
+        P.lo = ldexp(P.lo, K);
+        if (len < 0) P = dd_recip(P);                                      // 1 / g**(len/3) = g**(|len|/3)
+        const DD V = dd_mul_d(P, 1000.0);
+#pragma unroll 1
+        for (int d = 0; d < 2 && fast; d++) {
+            const DD W = d ? dd_add(V, dd_from_d(20000.0)) : V;
+            if (!(W.hi >= 1.0 && W.hi < 1.0e15)) fast = false;
+            else {
+                const double ih = floor(W.hi), il = floor(W.lo);
+                double f = (W.hi - ih) + (W.lo - il);
+                i64 I = (i64)ih + (i64)il;
+                if (f >= 1.0) {
+                    I += 1;
+                    f -= 1.0;
+                }
+                const double thr = W.hi * 1.2924697071141057e-26 + 8.8817841970012523e-16;   // 2^-86, 2^-50
+                if (!(f >= thr && f <= 1.0 - thr)) fast = false;
+                if (d) vd = I;
+                else vs = I;
+            }
+        }
+    }
+    if (!fast) {                                   // the reference's Decimal arithmetic for this one entry
+        Dec pw;
+        bool ok = true;
+        if (len % 3 == 0 && len >= 0) pw = dec_powi(cs->g, (u32)(len / 3));
+        else {
+            const double y = (double)len / 3.0;
+            pw = dec_pow_fx(cs->g, fx_from_double(fabs(y)), y < 0, PB_PREC, &ok);
+        }
+        if (!ok) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+        const Dec same = dec_div(dec_one(), pw), diff = dec_add(same, dec_twenty());
+        Wide<2> m;
+        const bool f1 = dec_to_milli_int<2>(same, m);
+        vs = (i64)(((u64)m.w[1] << 32) | m.w[0]);
+        const bool f2 = dec_to_milli_int<2>(diff, m);
+        vd = (i64)(((u64)m.w[1] << 32) | m.w[0]);
+        if (!f1 || !f2) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+    }
+    B.gapi_same[item] = vs;
+    B.gapi_diff[item] = vd;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Overlap edges (functions.py:26-34,140-141,386): weight = 1/o**len (+20 if 'diff'), o = 1 - ave([o1,o2]).
 // Closed form in double-double arithmetic (two IEEE doubles, ~2^-104 per operation):
 //     W_true = (1 - (o1+o2)/2) ** -len  (+ 20)

@@ -75,6 +75,9 @@ PB_KERNEL(st_orf_fast)
 PB_KERNEL(st_lit_calls)
 PB_KERNEL(st_lit_rest)
 PB_KERNEL(st_ov_fast)
+PB_KERNEL(st_gap_fast)
+PB_KERNEL(st_contig_lng)
+PB_KERNEL(st_rbs_weights)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 
@@ -558,6 +561,18 @@ static int literal_chain(pb200_ctx* ctx, i32 nlit) {
     return 0;
 }
 #undef ALN
+// score_gap for every length -2..300 in Decimal arithmetic: gap_same / gap_diff and their integers
+static int gap_tables(pb200_ctx* ctx) {
+    Batch& B = ctx->B;
+    if (B.gap_dec) return 0;
+    const i32 nc = B.nc;
+    PB_RUN(st_contig_lng, nc);
+    PB_RUN(st_gap_pow_int, (i64)nc * 101);
+    PB_RUN(st_gap_pow_real, (i64)nc * 202);
+    PB_RUN(st_gap_lut, (i64)nc * GAPN);
+    B.gap_dec = 1;
+    return 0;
+}
 // score_overlap replayed in Decimal arithmetic over the first n entries of B.ovlit_ids (or every edge when B.ov_all)
 static int overlap_chain(pb200_ctx* ctx, i32 n) {
     Batch& B = ctx->B;
@@ -789,6 +804,14 @@ int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out) {
     return 0;
 }
 
+int pb200_get_gap_int_weights(pb200_ctx* ctx, int64_t* same, int64_t* diff) {
+    if (!ctx || !ctx->have) return -2;
+    const size_t n = (size_t)ctx->B.nc * GAPN;
+    PB_TO_HOST(same, ctx->B.gapi_same, n * 8);
+    PB_TO_HOST(diff, ctx->B.gapi_diff, n * 8);
+    return 0;
+}
+
 int pb200_get_overlap_int_weights(pb200_ctx* ctx, int64_t* out) {
     if (!ctx || !ctx->have) return -2;
     if (ctx->B.nov > 0) PB_TO_HOST(out, ctx->B.ov_w64, (size_t)ctx->B.nov * 8);
@@ -856,6 +879,7 @@ int pb200_build_edges(pb200_ctx* ctx) {
     if (B.nn < 1) return 0;
     if (ensure_literal_orfs(ctx)) return -1;
     if (ensure_literal_overlaps(ctx)) return -1;
+    if (gap_tables(ctx)) return -1;
     PB_PHASE(7, ((size_t)B.nn + 2) * 4 + 1024);
     B.ed_cnt = PB_ALLOC(7, u32, (size_t)B.nn + 1);
     PB_RUN(st_edge_count, B.nn);

@@ -38,30 +38,11 @@ PB_HDN void st_contig_stats(const Batch& B, i64 c) {
         cs->gap_hi4 = (i64)(((u64)m.w[1] << 32) | m.w[0]) - 1000000;
         if (!o3 || !o4) cs->err |= ERR_OVERFLOW;
     }
-    bool ok = true, ok2 = true;
-    if (dec_is_one_abs(cs->g)) {
-        w_zero(cs->ln_g.m);
-        cs->ln_g.neg = 0;
-    } else {
-        Fx X = fx_from_dec(cs->g, &ok);
-        cs->ln_g = fx_ln(X, &ok2);
-    }
-    if (!ok || !ok2) cs->err |= ERR_RANGE;
-    // RBS likelihood ratio per score bin, IEEE doubles (functions.py:155-156,180-181,254-257)
+    // (the RBS likelihood ratios per score bin are converted by st_rbs_weights, 28 threads per contig;
+    //  ln g by st_contig_lng, only where the literal gap tables are built)
     u32 nz = 0;
     for (int r = 1; r < 28; r++) nz += cs->hist_bg[r];
     cs->hist_bg[0] = 2u * (u32)L - nz;
-    double ybg = 28.0 + 2.0 * (double)L;
-    u32 norf = (u32)(B.corf[c + 1] - B.corf[c]);
-    double ytr = 28.0 + (double)norf;
-    for (int r = 0; r < 28; r++) {
-        double bg = (1.0 + (double)cs->hist_bg[r]) / ybg;
-        double tr = (1.0 + (double)cs->hist_tr[r]) / ytr;
-        double wr = tr / bg;
-        bool okr;
-        cs->wrbs[r] = dec_from_double_repr(wr, &okr);
-        if (!okr) cs->err |= ERR_RANGE;
-    }
     // GC-frame exponents (functions.py:262-263,281-284): counts start at 1, divided by their max
     u32 mx = 1, mn = 1;
     for (int k = 1; k < 4; k++) {
@@ -86,6 +67,38 @@ PB_HDN void st_contig_stats(const Batch& B, i64 c) {
         if (!dd_from_dec(cs->pos_max[im], a) || !dd_from_dec(cs->pos_min[il], b)) cs->fast_ok = 0;
         cs->fe[k] = dd_mul(a, b);
     }
+}
+
+// ln g in fixed point for the real-exponent gap scores.  item = contig
+PB_HDN void st_contig_lng(const Batch& B, i64 c) {
+    if (c >= B.nc) return;
+    CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    bool ok = true, ok2 = true;
+    if (dec_is_one_abs(cs->g)) {
+        w_zero(cs->ln_g.m);
+        cs->ln_g.neg = 0;
+    } else {
+        Fx X = fx_from_dec(cs->g, &ok);
+        cs->ln_g = fx_ln(X, &ok2);
+    }
+    if (!ok || !ok2) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
+}
+// RBS likelihood ratio per score bin, IEEE doubles, then Decimal(str(float)) (functions.py:155-156,180-181,254-257;
+// orfs.py:126).  item = contig*28 + bin
+PB_HDN void st_rbs_weights(const Batch& B, i64 item) {
+    const i64 c = item / 28;
+    if (c >= B.nc) return;
+    const int r = (int)(item % 28);
+    CStat* cs = B.cs + c;
+    if (cs->L < 1) return;
+    const double ybg = 28.0 + 2.0 * (double)cs->L;
+    const double ytr = 28.0 + (double)(u32)(B.corf[c + 1] - B.corf[c]);
+    const double bg = (1.0 + (double)cs->hist_bg[r]) / ybg;
+    const double tr = (1.0 + (double)cs->hist_tr[r]) / ytr;
+    bool okr;
+    cs->wrbs[r] = dec_from_double_repr(tr / bg, &okr);
+    if (!okr) PB_ATOMIC_OR(&cs->err, (u32)ERR_RANGE);
 }
 
 // score_gap for length <= 300 (functions.py:36-46): 1/g**Decimal(length/3) (+ 1/0.05 if 'diff'), as three

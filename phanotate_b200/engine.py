@@ -128,6 +128,13 @@ class Result:
         self._e._ck(self._e.lib.pb200_get_overlap_int_weights(self._e.ctx, out.ctypes.data))
         return out
 
+    def gap_int_weights(self):
+        """(same, diff): trunc(score_gap(len)*1000) for len = -2..300, one row of 303 per contig."""
+        same = np.zeros((self.n_contigs, 303), dtype=np.int64)
+        diff = np.zeros((self.n_contigs, 303), dtype=np.int64)
+        self._e._ck(self._e.lib.pb200_get_gap_int_weights(self._e.ctx, same.ctypes.data, diff.ctypes.data))
+        return same, diff
+
     def fetch_all(self):
         self.orfs, self.nodes, self.edges
         return self

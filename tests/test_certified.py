@@ -38,8 +38,11 @@ def _both(sim, seqs):
     fast = sim.run(seqs)
     wf = fast.orf_int_weights()                       # before .orfs triggers the lazy literal completion
     ovf = fast.overlap_int_weights()
+    gsf, gdf = fast.gap_int_weights()
     lit = sim.run(seqs, literal=True)
     assert np.array_equal(ovf, lit.overlap_int_weights())
+    gsl, gdl = lit.gap_int_weights()
+    assert np.array_equal(gsf, gsl) and np.array_equal(gdf, gdl)
     assert lit.n_literal_overlaps == lit.n_overlaps and fast.n_literal_overlaps <= max(2, fast.n_overlaps // 50)
     return fast, wf, lit, lit.orf_int_weights()
 

@@ -82,7 +82,10 @@ def test_certified_integers_equal_literal_on_gpu(eng):
     fast = eng.run(seqs)
     wf = fast.orf_int_weights()
     ovf = fast.overlap_int_weights()
+    gsf, gdf = fast.gap_int_weights()
     lit = eng.run(seqs, literal=True)
+    gsl, gdl = lit.gap_int_weights()
+    assert np.array_equal(gsf, gsl) and np.array_equal(gdf, gdl)
     assert np.array_equal(ovf, lit.overlap_int_weights())
     assert fast.n_literal_overlaps < fast.n_overlaps // 50
     wl = lit.orf_int_weights()
