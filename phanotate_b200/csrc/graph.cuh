@@ -96,15 +96,26 @@ PB_HDN Dec overlap_score(const Batch& B, int c, i32 e, i32 x, bool diff) {
 }
 // Stage 9/10: overlap edges out of exit node ni.  fill=false counts, fill=true writes.
 PB_HDN void overlaps_of(const Batch& B, i32 ni, bool fill) {
-    const int kind = B.n_kind[ni] & 3;
+    const u32 wx = B.n_pk[ni];                      // position << 4 | kind | frame << 2
+    const int kx = (int)(wx & 3), fx = (int)((wx >> 2) & 3), r = (int)(wx >> 4);
     u32 cnt = 0;
-    if (!kind_is_entry(kind)) {
+    if (!kind_is_entry(kx)) {
         const int c = contig_of_node(B, ni);
-        const int r = B.n_pos[ni];
+        const i32 first = B.cnode[c];
+        const int ro = B.n_oth[ni];
         u32 k = fill ? B.ov_cnt[ni] : 0;
-        for (i32 j = ni - 1; j >= B.cnode[c] && r - B.n_pos[j] < 500; j--) {
-            if (B.n_pos[j] >= r) continue;
-            int ok = overlap_kind(B, j, ni);
+        for (i32 j = ni - 1; j >= first; j--) {
+            const u32 we = B.n_pk[j];
+            const int l = (int)(we >> 4), ke = (int)(we & 3), fe = (int)((we >> 2) & 3);
+            if (r - l >= 500) break;
+            if (l >= r || !kind_is_entry(ke)) continue;
+            // the overlap predicate of overlap_kind() on the packed node words (functions.py:400-438)
+            const int lo = B.n_oth[j];
+            int ok;
+            if (ke == K_FSTART && kx == K_FSTOP) ok = (fe != fx && r < lo && ro < l) ? 1 : 0;
+            else if (ke == K_RSTOP && kx == K_RSTART) ok = (fe != fx && r < lo && ro < l) ? 1 : 0;
+            else if (ke == K_RSTOP && kx == K_FSTOP) ok = (ro + 3 < l && r < lo) ? 2 : 0;
+            else ok = (ro < l && r < lo) ? 2 : 0;          // K_FSTART entry, K_RSTART exit
             if (!ok) continue;
             if (fill) {
                 B.ov_dst[k] = j;
