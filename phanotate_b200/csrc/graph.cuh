@@ -215,6 +215,12 @@ PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
         if (tot > run) run = tot;
     }
 }
+PB_HDNI WInt bridge_wint_long(const Batch& B, int c, int len) {
+    WInt wi;
+    if (!dec_to_wint(gap_score(B, c, len, false), wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
+    return wi;
+}
 PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
     const int c = contig_of_node(B, i);
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
@@ -235,14 +241,12 @@ PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
                 int len = B.n_pos[r] - B.n_pos[l] - 3;
                 if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
                 if (fill) {
-                    Dec w = gap_score(B, c, len, false);
                     B.br_src[k] = l;
                     B.br_dst[k] = r;
-                    B.br_w[k] = w;
-                    WInt wi;
-                    if (!dec_to_wint(w, wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
-                    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
-                    B.br_wint[k] = wi;
+                    // score_gap(len > 300) = g**100 + len (functions.py:40-41): its integer is len*1000 + a per-contig constant
+                    // for 3- and 4-digit lengths; longer gaps take the Decimal route
+                    B.br_wint[k] = (len <= 9999) ? wint_from_i64((i64)len * 1000 + (len <= 999 ? B.cs[c].gap_hi3 : B.cs[c].gap_hi4))
+                                                 : bridge_wint_long(B, c, len);
                     k++;
                 }
                 cnt++;
@@ -628,7 +632,8 @@ PB_HDN void edges_of(const Batch& B, i32 u, bool fill) {
         }
         for (u32 k = B.ov_cnt[u]; k < B.ov_cnt[u + 1]; k++) EMIT(u, B.ov_dst[k], EK_OVERLAP, B.ov_w[k]);
         for (u32 k = B.br_cnt[B.cnode[c]]; k < B.br_cnt[ne]; k++)
-            if (B.br_src[k] == u) EMIT(u, B.br_dst[k], EK_BRIDGE, B.br_w[k]);
+            if (B.br_src[k] == u)
+                EMIT(u, B.br_dst[k], EK_BRIDGE, gap_score(B, c, B.n_pos[B.br_dst[k]] - B.n_pos[u] - 3, false));
         if (L - pu <= 2000) EMIT(u, -3, EK_TARGET, gap_score(B, c, L - pu, false));
     }
 #undef EMIT

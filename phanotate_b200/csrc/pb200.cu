@@ -211,7 +211,8 @@ struct StageTime {
 };
 struct pb200_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::string err;
     DevBuf ph[NPHASE];
     DevBuf in_seq, in_off, scratch;
@@ -327,8 +328,13 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         t_.a = ev_get(ctx);                                                                      \
         t_.b = ev_get(ctx);                                                                      \
         cudaEventRecord(t_.a, ctx->stream);                                                      \
+        /* the few contigs that need 256-bit distances run beside the others on a second stream */ \
+        cudaEventRecord(ctx->fork_ev, ctx->stream);                                              \
+        cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
+        k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
+        cudaEventRecord(ctx->join_ev, ctx->stream2);                                             \
         k_solve<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
-        k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0);                                       \
         ctx->launches++;                                                                         \
         cudaEventRecord(t_.b, ctx->stream);                                                      \
         ctx->times.push_back(t_);                                                                \
@@ -619,6 +625,9 @@ int pb200_create(int device, pb200_ctx** out) {
 #ifndef PB_HOSTSIM
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreate(&ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamCreate(&ctx->stream2);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         fprintf(stderr, "phanotate_b200: no usable CUDA device %d: %s\n", device, cudaGetErrorString(e));
         delete ctx;
@@ -643,6 +652,9 @@ void pb200_destroy(pb200_ctx* ctx) {
     for (auto e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
 #else
     for (int k = 0; k < NPHASE; k++) free(ctx->ph[k].p);

@@ -135,7 +135,6 @@ struct Batch {
     i32* n_reach;         // [nn] last covered base before the node
     i32* br_src;
     i32* br_dst;
-    Dec* br_w;
     WInt* br_wint;
     // solve
     WInt* dist;
