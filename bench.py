@@ -132,7 +132,7 @@ def run_reference(args, rank, world):
     last["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(len(vals), 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+int256",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+f64x2+int128",
             "data": "synthetic", "config": workload_config(args, world), "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -143,7 +143,9 @@ def workload_config(args, world):
     return {"workload": "synthetic %d phage contigs x %d bp per GPU (BASELINE.json config 4: donor lambda|T4|phiX "
                         "windows, 2%% point mutations, seed 20261017)" % (args.contigs, args.length),
             "contigs_per_gpu": args.contigs, "contig_bp": args.length, "parallelism": "contig-sharded x%d" % world,
-            "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2" % (args.contigs * args.length / 1e6)}
+            "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2" % (args.contigs * args.length / 1e6),
+            "mode": "default pb200_run: certified integer edge weights and float scores, Decimal chain only where owed; "
+                    "e2e through PipelinedEngine with %d lanes" % args.lanes}
 
 
 def main():
@@ -282,14 +284,24 @@ def main():
             per_launch_s = stage[dom] / args.steps / 1e3
             alg = total_bp * 1.0 + 24.0 * ncalls
             ach = alg / per_launch_s / 1e9
-            roof = {"bound": "hbm", "kernel": "k_" + dom if dom != "solve" else "k_solve", "achieved": ach,
-                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            kname = {"solve": "k_solve", "scan_tiles": "k_scan_tiles", "hold": "k_hold"}.get(dom, "k_" + dom)
+            # DRAM bytes of that kernel per launch from the committed `ncu --set full` capture of this workload
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+                if tj.get("contigs") == args.contigs and tj.get("contig_bp") == args.length:
+                    traffic = tj["kernels"].get(kname)
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": kname, "achieved": ach,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_s * 1e3,
                     "share_of_step": stage[dom] / max(sum(stage.values()), 1e-9),
-                    "note": "integer/decimal-emulation bound, not HBM bound (DESIGN.md): frac is reported for the contract"}
+                    "note": "issue / dependent-latency bound, not HBM bound (DESIGN.md 4): frac is reported for the contract; "
+                            "traffic = dram read+write bytes per launch from profiles/ (ncu --set full)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+int256", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+f64x2+int128", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps},
