@@ -497,7 +497,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
                 if (D::less(cand, tdist)) {
                     tdist = cand;
                     tpar = u;
-                } else if (!D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
+                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
             }
         }
         PB_SYNCWARP();

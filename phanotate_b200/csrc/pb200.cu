@@ -84,7 +84,7 @@ PB_KERNEL(st_edge_fill)
 #include "scan_tile.cuh"
 // one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
 // dependent memory round trips per contig: throughput comes from the number of contigs in flight)
-__global__ void __launch_bounds__(PB_BLOCK, 12) k_solve(const Batch B, i32 nc) {
+__global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
     const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
