@@ -18,6 +18,16 @@ def main(argv=None):
     args = file_handling.get_args(File, argv)
     if args.format == 'fasta':
         args.format = 'fna'
+    if args.format == 'tabular' and not args.dump:
+        # batch fast path: vectorised FASTA ingest -> one engine run -> the tabular text of every locus
+        from phanotate_b200 import fastio
+        names, bases, offs = fastio.read_fasta_packed(args.infile)
+        if len(bases) == 0:
+            sys.stdout.write("Error: no sequences found in infile\n")
+            return 0
+        res = functions.engine().run_packed(bases, offs, make_params(args.start_codons, args.stop_codons, args.min_orf_len))
+        fastio.write_tabular(res, names, args.outfile, check=True)
+        return 0
     genbank = File(args.infile)
     if not genbank.seq():
         sys.stdout.write("Error: no sequences found in infile\n")

@@ -191,3 +191,47 @@ def test_pipelined_engine_equals_single_context():
     assert np.array_equal(m2.calls, s.calls[:m2.n_calls]) and m2.n_contigs == 5
     pe.close()
     e.close()
+
+
+def test_fast_fasta_ingest_equals_line_reader(tmp_path):
+    """fastio.read_fasta_packed (vectorised) against phanotate_modules.file.File on a multi-record file with CRLF
+    line ends, blank lines, mixed case, text before the first header and a record without sequence; also gzipped."""
+    import gzip
+    import numpy as np
+    from phanotate_b200 import fastio
+    from phanotate_modules.file import File
+    text = ("junk before any header\n>rec1 first record\r\nACGTacgtnnRY\r\n\r\nacgt \n>empty\n>rec3\tdescription\n" +
+            "tttt\ncccc\n" + open(os.path.join(ROOT, "tests", "data", "phiX174.fasta")).read())
+    p = tmp_path / "m.fasta"
+    p.write_text(text)
+    pz = tmp_path / "m.fasta.gz"
+    pz.write_bytes(gzip.compress(text.encode()))
+    for path in (p, pz):
+        names, bases, offs = fastio.read_fasta_packed(str(path))
+        loci = list(File(str(path)))
+        assert names == [l.name() for l in loci] == ["rec1", "empty", "rec3", "phiX174"]
+        assert [bases[offs[k]:offs[k + 1]].tobytes().decode() for k in range(len(loci))] == [l.seq() for l in loci]
+
+
+def test_cli_tabular_fast_path_equals_per_locus_writer(sim_engine, capsys, tmp_path):
+    """The batch tabular writer (CLI default format) produces the bytes of Locus.tabular (locus.py:39-56), reverse-strand
+    rows included, on a two-record file."""
+    import io
+    import phanotate
+    from phanotate_modules.file import File
+    from phanotate_b200.engine import make_params
+    data = os.path.join(ROOT, "tests", "data")
+    p = tmp_path / "two.fasta"
+    p.write_text(open(os.path.join(data, "NC_001416.1.fasta")).read() + open(os.path.join(data, "phiX174.fasta")).read())
+    phanotate.main([str(p)])
+    fast = capsys.readouterr().out
+    loci = list(File(str(p)))
+    res = sim_engine.run([l.seq().encode() for l in loci], make_params())
+    slow = io.StringIO()
+    for k, locus in enumerate(loci):
+        c = res.contigs[k]
+        for r in res.calls[c["call_off"]:c["call_off"] + c["n_calls"]]:
+            f = locus.add_feature('CDS', 1 if r["strand"] > 0 else -1, [[int(r["left"]), int(r["right"]) - 2]], {})
+            f.weight = '%E' % float(r["score"])
+        locus.tabular(slow)
+    assert fast == slow.getvalue() and "\t-\t" in fast
