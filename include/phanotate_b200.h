@@ -156,6 +156,18 @@ int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const i
                        const int32_t* dst, const uint32_t* weight_limbs, int32_t source, int32_t target,
                        int32_t* path_out, int32_t* path_len);
 
+/* Host-side text ingest / output for whole batches (no device work): multi-record FASTA -> the packed batch of
+ * pb200_run, and the tabular text of a batch (Locus.tabular, locus.py:39-56).
+ * pb200_fasta_count: number of records ('>' at a line start).  pb200_fasta_parse: bases must hold n bytes, offsets
+ * max_records+1 entries; name_begin/name_end are byte ranges of the first word of every header inside data; returns
+ * the number of records or -1.  pb200_format_tabular: names = concatenated record names, name_off[n_contigs+1];
+ * returns the number of bytes written, or -(bytes needed) when cap is too small. */
+int64_t pb200_fasta_count(const char* data, int64_t n);
+int64_t pb200_fasta_parse(const char* data, int64_t n, uint8_t* bases, int64_t* offsets, int64_t* name_begin,
+                          int64_t* name_end, int64_t max_records);
+int64_t pb200_format_tabular(const pb200_call* calls, const pb200_contig* contigs, int32_t n_contigs, const char* names,
+                             const int64_t* name_off, char* out, int64_t cap);
+
 /* device time of the stages of the last pb200_run in milliseconds (CUDA events on the context's
  * stream); names[i] are static strings.  Returns the number of stages written (<= cap). */
 int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);

@@ -21,12 +21,13 @@ def main(argv=None):
     if args.format == 'tabular' and not args.dump:
         # batch fast path: vectorised FASTA ingest -> one engine run -> the tabular text of every locus
         from phanotate_b200 import fastio
-        names, bases, offs = fastio.read_fasta_packed(args.infile)
+        eng = functions.engine()
+        names, bases, offs = fastio.read_fasta_packed(args.infile, eng.lib)
         if len(bases) == 0:
             sys.stdout.write("Error: no sequences found in infile\n")
             return 0
-        res = functions.engine().run_packed(bases, offs, make_params(args.start_codons, args.stop_codons, args.min_orf_len))
-        fastio.write_tabular(res, names, args.outfile, check=True)
+        res = eng.run_packed(bases, offs, make_params(args.start_codons, args.stop_codons, args.min_orf_len))
+        fastio.write_tabular(res, names, args.outfile, check=True, lib=eng.lib)
         return 0
     genbank = File(args.infile)
     if not genbank.seq():

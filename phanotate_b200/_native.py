@@ -88,6 +88,12 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_pin_host.argtypes = [vp, ctypes.c_size_t]
     lib.pb200_unpin_host.argtypes = [vp]
     lib.pb200_struct_sizes.argtypes = [vp]
+    lib.pb200_fasta_count.argtypes = [vp, ctypes.c_int64]
+    lib.pb200_fasta_count.restype = ctypes.c_int64
+    lib.pb200_fasta_parse.argtypes = [vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int64]
+    lib.pb200_fasta_parse.restype = ctypes.c_int64
+    lib.pb200_format_tabular.argtypes = [vp, vp, i32, vp, vp, vp, ctypes.c_int64]
+    lib.pb200_format_tabular.restype = ctypes.c_int64
     sz = (ctypes.c_int32 * 8)()
     lib.pb200_struct_sizes(sz)
     want = [DEC.itemsize, PARAMS.itemsize, CALL.itemsize, ORF.itemsize, NODE.itemsize, EDGE.itemsize, CONTIG.itemsize]
@@ -100,4 +106,5 @@ EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb
            "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_gap_int_weights", "pb200_get_calls",
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_stage_times", "pb200_launch_count", "pb200_last_run_ms",
-           "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes"]
+           "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes", "pb200_fasta_count",
+           "pb200_fasta_parse", "pb200_format_tabular"]

@@ -959,6 +959,83 @@ int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const i
     return 0;
 }
 
+// ---- host-side text ingest / output for whole batches (no device work, no context needed)
+static inline bool fa_blank(unsigned char ch) { return ch == ' ' || ch == '\t' || ch == '\r'; }
+int64_t pb200_fasta_count(const char* data, int64_t n) {
+    int64_t rec = 0;
+    const char* p = data;
+    const char* end = data + n;
+    while (p < end) {
+        if (*p == '>') rec++;
+        const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!q) break;
+        p = q + 1;
+    }
+    return rec;
+}
+int64_t pb200_fasta_parse(const char* data, int64_t n, uint8_t* bases, int64_t* offsets, int64_t* name_begin,
+                          int64_t* name_end, int64_t max_records) {
+    int64_t rec = 0, nb = 0;
+    const char* p = data;
+    const char* end = data + n;
+    while (p < end) {
+        const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = q ? q : end;                    // line = [p, le)
+        if (*p == '>') {
+            if (rec >= max_records) return -1;
+            offsets[rec] = nb;
+            const char* a = p + 1;
+            while (a < le && fa_blank((unsigned char)*a)) a++;
+            const char* b = a;
+            while (b < le && !fa_blank((unsigned char)*b)) b++;
+            name_begin[rec] = a - data;
+            name_end[rec] = b - data;
+            rec++;
+        } else if (rec > 0) {                            // text before the first header is ignored
+            const char* e2 = le;
+            while (e2 > p && fa_blank((unsigned char)e2[-1])) e2--;          // CRLF / trailing blanks
+            const char* a = p;
+            while (a < e2 && fa_blank((unsigned char)*a)) a++;
+            const size_t len = (size_t)(e2 - a);
+            if (len) {
+                if (!memchr(a, ' ', len) && !memchr(a, '\t', len) && !memchr(a, '\r', len)) {
+                    memcpy(bases + nb, a, len);
+                    nb += (int64_t)len;
+                } else {
+                    for (const char* c = a; c < e2; c++)
+                        if (!fa_blank((unsigned char)*c)) bases[nb++] = (uint8_t)*c;
+                }
+            }
+        }
+        if (!q) break;
+        p = q + 1;
+    }
+    offsets[rec] = nb;
+    return rec;
+}
+// Locus.tabular (locus.py:39-56) for every contig of a batch: "#id:" / "#START..." header, then one row per call with
+// left/right swapped on the reverse strand and the score printed with %E.  Returns the bytes written or -(bytes needed).
+int64_t pb200_format_tabular(const pb200_call* calls, const pb200_contig* contigs, int32_t n_contigs, const char* names,
+                             const int64_t* name_off, char* out, int64_t cap) {
+    int64_t need = 0;
+    for (int32_t k = 0; k < n_contigs; k++)
+        need += 48 + (name_off[k + 1] - name_off[k]) + (int64_t)contigs[k].n_calls * (64 + (name_off[k + 1] - name_off[k]));
+    if (need > cap) return -need;
+    char* w = out;
+    for (int32_t k = 0; k < n_contigs; k++) {
+        const char* nm = names + name_off[k];
+        const int nl = (int)(name_off[k + 1] - name_off[k]);
+        w += sprintf(w, "#id:\t%.*s\n#START\tSTOP\tFRAME\tCONTIG\tSCORE\n", nl, nm);
+        const pb200_call* c = calls + contigs[k].call_off;
+        for (int32_t i = 0; i < contigs[k].n_calls; i++) {
+            const int fwd = c[i].strand > 0;
+            w += sprintf(w, "%d\t%d\t%c\t%.*s\t%E\n", fwd ? c[i].left : c[i].right, fwd ? c[i].right : c[i].left,
+                         fwd ? '+' : '-', nl, nm, c[i].score);
+        }
+    }
+    return (int64_t)(w - out);
+}
+
 int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap) {
     if (!ctx) return -2;
 #ifndef PB_HOSTSIM

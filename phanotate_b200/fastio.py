@@ -1,65 +1,81 @@
-"""Host-side ingest and tabular output at batch speed: a vectorised multi-record FASTA reader that
-produces the packed batch the engine takes (no per-line Python), and a tabular writer that formats the call table
-of a whole batch like Locus.tabular (reference locus.py:39-56).  Everything numeric stays in the CUDA library."""
+"""Host-side ingest and tabular output at batch speed: a multi-record FASTA reader that produces the
+packed batch the engine takes, and a tabular writer that formats the call table of a whole batch like Locus.tabular
+(reference locus.py:39-56).  Both are single passes in the C library (pb200_fasta_parse, pb200_format_tabular)."""
 from __future__ import annotations
 
+import ctypes
 import gzip
 
 import numpy as np
 
+from . import _native as N
 
-def read_fasta_packed(path):
+_lib = None
+
+
+def _library(lib=None):
+    global _lib
+    if lib is not None:
+        return lib
+    if _lib is None:
+        _lib = N.load()
+    return _lib
+
+
+def read_fasta_packed(path, lib=None):
     """-> (names, bases uint8[total], offsets int64[n+1]).  Record name = first word of the '>' line (like the
     reader in phanotate_modules/file.py); sequence = every non-blank byte of the record's other lines, case kept
     (the library lower-cases like functions.py:144)."""
+    lib = _library(lib)
     with open(path, "rb") as fh:
         data = fh.read()
     if str(path).endswith(".gz") or data[:2] == b"\x1f\x8b":
         data = gzip.decompress(data)
-    buf = np.frombuffer(data, dtype=np.uint8)
-    n = len(buf)
-    if n == 0:
-        return [], np.zeros(0, np.uint8), np.zeros(1, np.int64)
-    nl = buf == 10
-    line_start = np.concatenate(([0], np.flatnonzero(nl) + 1))
-    line_start = line_start[line_start < n]
-    is_hdr = buf[line_start] == ord(">")
-    line_id = np.cumsum(nl) - nl                         # line index of every byte (a newline belongs to its own line)
-    rec_of_line = np.cumsum(is_hdr) - 1                  # record index of every line (-1 before the first header)
-    keep = ~is_hdr[line_id] & (rec_of_line[line_id] >= 0) & ~nl & (buf != 13) & (buf != 32) & (buf != 9)
-    bases = buf[keep]
-    rec = rec_of_line[line_id[keep]]
-    nrec = int(is_hdr.sum())
+    n = len(data)
+    nrec = int(lib.pb200_fasta_count(data, n))
+    bases = np.empty(max(n, 1), dtype=np.uint8)
     offsets = np.zeros(nrec + 1, dtype=np.int64)
-    np.cumsum(np.bincount(rec, minlength=nrec), out=offsets[1:])
-    names = []
-    hs = line_start[is_hdr]
-    ends = np.flatnonzero(nl)
-    he = ends[np.searchsorted(ends, hs)] if len(ends) else np.full(len(hs), n)
-    for a, b in zip(hs.tolist(), he.tolist() if len(ends) else [n] * len(hs)):
-        words = data[a + 1:b].split()
-        names.append(words[0].decode() if words else "")
-    return names, np.ascontiguousarray(bases), offsets
+    nb, ne = np.zeros(max(nrec, 1), dtype=np.int64), np.zeros(max(nrec, 1), dtype=np.int64)
+    got = int(lib.pb200_fasta_parse(data, n, bases.ctypes.data, offsets.ctypes.data, nb.ctypes.data, ne.ctypes.data, nrec))
+    if got != nrec:
+        raise RuntimeError("FASTA parse failed")
+    names = [data[a:b].decode() for a, b in zip(nb[:nrec].tolist(), ne[:nrec].tolist())]
+    return names, bases[:int(offsets[-1])], offsets
 
 
-def write_tabular(res, names, out, check=False):
-    """Locus.tabular for every contig of a batch result (Result or MergedResult): same bytes as the per-locus writer.
-    check=True raises what the reference would have raised for a contig (KeyError / ValueError) when its turn comes,
-    after the blocks of the contigs before it were written -- like the reference's per-locus loop."""
-    calls, contigs = res.calls, res.contigs
-    left = calls["left"].tolist()
-    right = calls["right"].tolist()
-    strand = calls["strand"].tolist()
-    score = calls["score"].tolist()
-    parts = []
-    for k, name in enumerate(names):
-        if check and int(contigs[k]["err"]):
-            out.write("".join(parts))
-            parts = []
-            res.check(k)
-        a = int(contigs[k]["call_off"])
-        b = a + int(contigs[k]["n_calls"])
-        parts.append("#id:\t%s\n#START\tSTOP\tFRAME\tCONTIG\tSCORE\n" % name)
-        parts.extend(("%d\t%d\t+\t%s\t%E\n" % (left[i], right[i], name, score[i])) if strand[i] > 0 else
-                     ("%d\t%d\t-\t%s\t%E\n" % (right[i], left[i], name, score[i])) for i in range(a, b))
-    out.write("".join(parts))
+def tabular_text(res, names, lib=None) -> bytes:
+    """Locus.tabular for every contig of a batch result (Result or MergedResult), as bytes."""
+    lib = _library(lib)
+    enc = [s.encode() for s in names]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in enc], out=off[1:])
+    blob = b"".join(enc) or b"\0"
+    calls = np.ascontiguousarray(res.calls)
+    contigs = np.ascontiguousarray(res.contigs)
+    cap = 1 << 16
+    while True:
+        out = ctypes.create_string_buffer(cap)
+        got = int(lib.pb200_format_tabular(calls.ctypes.data, contigs.ctypes.data, len(enc), blob, off.ctypes.data, out, cap))
+        if got >= 0:
+            return out.raw[:got]
+        cap = -got + 64
+
+
+def write_tabular(res, names, out, check=False, lib=None):
+    """Writes tabular_text to a text stream.  check=True raises what the reference would have raised for a contig
+    (KeyError / ValueError) when its turn comes, after the blocks of the contigs before it were written -- like the
+    reference's per-locus loop."""
+    bad = [k for k in range(len(names)) if int(res.contigs[k]["err"])] if check else []
+    if not bad:
+        out.write(tabular_text(res, names, lib).decode())
+        return
+
+    class _Head:                                   # the contigs before the first failing one
+        pass
+    k = bad[0]
+    head = _Head()
+    head.contigs = res.contigs[:k]
+    head.calls = res.calls
+    out.write(tabular_text(head, names[:k], lib).decode())
+    res.check(k)
+    raise RuntimeError("contig %d: device error bits 0x%x" % (k, int(res.contigs[k]["err"])))

@@ -206,8 +206,11 @@ def test_fast_fasta_ingest_equals_line_reader(tmp_path):
     p.write_text(text)
     pz = tmp_path / "m.fasta.gz"
     pz.write_bytes(gzip.compress(text.encode()))
+    from helpers import hostsim_path
+    from phanotate_b200 import _native as N
+    lib = N.load(hostsim_path())
     for path in (p, pz):
-        names, bases, offs = fastio.read_fasta_packed(str(path))
+        names, bases, offs = fastio.read_fasta_packed(str(path), lib)
         loci = list(File(str(path)))
         assert names == [l.name() for l in loci] == ["rec1", "empty", "rec3", "phiX174"]
         assert [bases[offs[k]:offs[k + 1]].tobytes().decode() for k in range(len(loci))] == [l.seq() for l in loci]
