@@ -124,3 +124,17 @@ def test_wide_solver_on_gpu(eng):
     b = eng.run(seqs, flags=N.SOLVE_WIDE)
     assert np.array_equal(a.calls, b.calls)
     assert int(a.contigs["wide"].sum()) == 0 and int(b.contigs["wide"].sum()) == len(seqs)
+
+
+def test_empty_and_tiny_contigs_inside_a_batch(eng):
+    """Zero-length and few-base contigs between ordinary ones: they get no calls (an empty contig is flagged), their
+    neighbours are unaffected -- with the tiled and with the per-strip scan."""
+    seqs = [seq_of("phiX174").encode(), b"", b"acg", seq_of("stress3").encode(), b"", b"atgaaataa", seq_of("lambda").encode(), b"n"]
+    for flags in (0, N.SCAN_REFERENCE):
+        res = eng.run(seqs, flags=flags)
+        assert calls_text(res, 0) == golden_text("phiX174", "calls.tsv")
+        assert calls_text(res, 3) == golden_text("stress3", "calls.tsv")
+        assert calls_text(res, 6) == golden_text("lambda", "calls.tsv")
+        for k in (1, 2, 4, 5, 7):
+            assert int(res.contigs[k]["n_calls"]) == 0
+        assert int(res.contigs[1]["err"]) & N.ERR_RANGE and int(res.contigs[0]["err"]) == 0 and int(res.contigs[6]["err"]) == 0
