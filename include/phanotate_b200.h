@@ -128,6 +128,14 @@ const char* pb200_last_error(pb200_ctx* ctx);
 int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs,
               const pb200_params* params, uint32_t flags);
 
+/* host->device copy of a batch without running it; run it with pb200_run(ctx, bases, offsets, n, params,
+ * PB200_REUSE_INPUT).  With several contexts this lets the copies go one after the other while other contexts compute. */
+int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs);
+
+/* number added to the contig column of the call rows of the following runs (default 0): for a caller that cuts one
+ * batch into groups for several contexts and wants the rows numbered in the whole batch */
+int pb200_set_contig_base(pb200_ctx* ctx, int32_t base);
+
 /* out[0..7] = n_contigs, n_bases, n_nodes, n_orfs, n_overlap_edges, n_bridge_edges, n_calls, n_edges */
 int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
 /* out[0] = ORFs whose weight went through the literal Decimal chain before the solve, out[1] = after

@@ -570,7 +570,7 @@ PB_HDN void st_gather_calls(const Batch& B, i64 k) {
     const int c = B.o_contig[orf];
     CallRec r;
     const bool rev = B.o_frame[orf] < 0;
-    r.contig = (i32)c;
+    r.contig = (i32)c + B.contig_base;
     r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
     r.right = (rev ? B.o_start[orf] : B.o_stop[orf]) + 2;     // right = exit node position + 2
     r.strand = rev ? -1 : 1;

@@ -223,6 +223,7 @@ struct pb200_ctx {
     size_t evused = 0;
     int launches = 0;
     int sm_count = 148;
+    int contig_base = 0;
     bool scan_attr_set = false;
     cudaEvent_t run_a = nullptr, run_b = nullptr;
 };
@@ -394,6 +395,7 @@ struct DevBuf {
 };
 struct pb200_ctx {
     int device = 0;
+    int contig_base = 0;
     std::string err;
     DevBuf ph[NPHASE];
     DevBuf in_seq, in_off, scratch;
@@ -680,6 +682,7 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     if (rc) return rc;
     B.nc = n_contigs;
     B.flags = (i32)flags;
+    B.contig_base = ctx->contig_base;
 #ifndef PB_HOSTSIM
     CK(cudaSetDevice(ctx->device));
     ctx->times.clear();
@@ -719,11 +722,15 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
         B.coff = (const i64*)ctx->in_off.p;
     }
 #else
-    (void)flags;
     ctx->launches = 0;
     B.nb = offsets[n_contigs];
-    B.seq = bases;
-    B.coff = offsets;
+    if (flags & PB200_REUSE_INPUT) {
+        B.seq = (const u8*)ctx->in_seq.p;
+        B.coff = (const i64*)ctx->in_off.p;
+    } else {
+        B.seq = bases;
+        B.coff = offsets;
+    }
 #endif
     if (B.nb < 1) {
         ctx->err = "empty batch";
@@ -740,6 +747,38 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     CK(cudaStreamSynchronize(ctx->stream));
 #endif
     ctx->have = true;
+    return 0;
+}
+
+// Copy a batch into the context's device buffers without running it (then pb200_run(..., PB200_REUSE_INPUT)): lets a
+// caller with several contexts order the host->device copies one after the other while kernels of other contexts run.
+int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs) {
+    if (!ctx || !bases || !offsets || n_contigs < 1) return -2;
+#ifndef PB_HOSTSIM
+    const i64 nb = offsets[n_contigs];
+    if (nb < 1) {
+        ctx->err = "empty batch";
+        return -2;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (buf_ensure(ctx, ctx->in_seq, (size_t)nb + 64)) return -1;
+    if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
+    CK(cudaMemcpyAsync(ctx->in_seq.p, bases, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+#else
+    const i64 nb = offsets[n_contigs];
+    if (buf_ensure(ctx, ctx->in_seq, (size_t)nb + 64)) return -1;
+    if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
+    memcpy(ctx->in_seq.p, bases, (size_t)nb);
+    memcpy(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8);
+#endif
+    return 0;
+}
+
+int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {
+    if (!ctx) return -2;
+    ctx->contig_base = base;
     return 0;
 }
 

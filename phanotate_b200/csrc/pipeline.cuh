@@ -199,6 +199,7 @@ struct Batch {
     i32 ov_all;           // literal overlap chain over every edge (slot = edge), ov_w[] indexed by edge
     i32 novlit;
     i32 n_lit_pre, n_lit_post, n_ovlit;   // statistics of the last run
+    i32 contig_base;      // added to the contig column of the call rows (a caller that splits a batch over contexts)
     i32 gap_dec;          // the Decimal gap tables gap_same / gap_diff are built
     i32 lit_done;         // every ORF has its literal weight (lazy completion ran)
 };

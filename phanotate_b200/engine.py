@@ -307,50 +307,99 @@ class PipelinedEngine:
             setattr(self, name, buf)
         return buf
 
-    def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0):
+    def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0, resident=False,
+                   fetch=True):
+        """resident=True: every lane still holds its group of this same batch from the previous call (no copy-in).
+        fetch=False: leave the tables on the device (returns None)."""
         if params is None:
             params = make_params()
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         lanes = min(len(self.engines), max(n, 1))
-        cuts = [0]                                    # consecutive groups of about equal size in bases
-        for k in range(1, lanes):
-            c = int(np.searchsorted(offsets, offsets[-1] * k // lanes, side="left"))
+        # consecutive groups of contigs; the first is half as large as the others so that kernels start early
+        weights = [1.0] + [2.0] * (lanes - 1)
+        acc, total, cuts = 0.0, sum(weights), [0]
+        for k in range(lanes - 1):
+            acc += weights[k]
+            c = int(np.searchsorted(offsets, int(offsets[-1] * acc / total), side="left"))
             cuts.append(min(max(c, cuts[-1]), n))
         cuts.append(n)
         live = [k for k in range(lanes) if cuts[k + 1] > cuts[k]]
+        nlive = len(live)
+        import threading
+        sized = [threading.Event() for _ in range(nlive)]        # lane j knows its table sizes
+        uploaded = [threading.Event() for _ in range(nlive)]     # lane j's letters are on the device
+        sizes, stats, launches = [None] * nlive, [None] * nlive, [0] * nlive
+        late = [False] * nlive                                   # lane j did not fit the output buffer: fetched afterwards
+        ncont_total = sum(cuts[k + 1] - cuts[k] for k in live)
+        contigs = self._grow("_contigs", ncont_total, N.CONTIG)[:ncont_total] if fetch else None
+        cont_off = np.concatenate(([0], np.cumsum([cuts[k + 1] - cuts[k] for k in live]))).astype(np.int64)
+        capacity = len(self._calls)                              # fixed during the run: nothing is re-pinned under a copy
 
-        def compute(k):
-            a, b = cuts[k], cuts[k + 1]
+        def copy_out(j):
+            k = live[j]
             e = self.engines[k]
-            e.run_packed(bases[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], params, fetch=False,
-                         literal=literal, call_weights=call_weights, flags=flags)
-            st = np.zeros(8, dtype=np.int64)
-            e._ck(e.lib.pb200_stats(e.ctx, st.ctypes.data))
-            return e.sizes(), [int(v) for v in st[:3]], int(e.lib.pb200_launch_count(e.ctx))
-
-        done = list(self.pool.map(compute, live))
-        sizes = [d[0] for d in done]
-        ncalls, ncont = sum(z[6] for z in sizes), sum(z[0] for z in sizes)
-        calls = self._grow("_calls", ncalls, N.CALL)[:ncalls]
-        contigs = self._grow("_contigs", ncont, N.CONTIG)[:ncont]
-        call_off = np.concatenate(([0], np.cumsum([z[6] for z in sizes]))).astype(np.int64)
-        cont_off = np.concatenate(([0], np.cumsum([z[0] for z in sizes]))).astype(np.int64)
-        node_off = np.concatenate(([0], np.cumsum([z[2] for z in sizes]))).astype(np.int64)
-        orf_off = np.concatenate(([0], np.cumsum([z[3] for z in sizes]))).astype(np.int64)
-
-        def fetch(j):
-            e = self.engines[live[j]]
-            cl = calls[call_off[j]:call_off[j + 1]]
+            call_off = sum(sizes[i][6] for i in range(j))
+            node_off = sum(sizes[i][2] for i in range(j))
+            orf_off = sum(sizes[i][3] for i in range(j))
+            cl = self._calls[call_off:call_off + sizes[j][6]]
             ct = contigs[cont_off[j]:cont_off[j + 1]]
             if len(cl):
-                e._ck(e.lib.pb200_get_calls(e.ctx, cl.ctypes.data))
-                cl["contig"] += cuts[live[j]]
+                e._ck(e.lib.pb200_get_calls(e.ctx, cl.ctypes.data))    # (rows already numbered in the whole batch)
             e._ck(e.lib.pb200_get_contigs(e.ctx, ct.ctypes.data))
-            ct["call_off"] += call_off[j]
-            ct["node_off"] += node_off[j]
-            ct["orf_off"] += orf_off[j]
+            ct["call_off"] += call_off
+            ct["node_off"] += node_off
+            ct["orf_off"] += orf_off
 
-        list(self.pool.map(fetch, range(len(live))))
+        def lane(j):
+            k = live[j]
+            a, b = cuts[k], cuts[k + 1]
+            e = self.engines[k]
+            try:
+                sub_b, sub_o = bases[offsets[a]:offsets[b]], np.ascontiguousarray(offsets[a:b + 1] - offsets[a])
+                e._ck(e.lib.pb200_set_contig_base(e.ctx, a))
+                try:
+                    if not resident:
+                        # copies go in lane order, one at a time: the first (small) group's kernels start while the
+                        # others are still being copied, instead of all copies sharing the link and ending together
+                        if j and not uploaded[j - 1].wait(timeout=600):
+                            raise PhanotateError("an earlier group failed to upload")
+                        e._ck(e.lib.pb200_upload(e.ctx, sub_b.ctypes.data, sub_o.ctypes.data, len(sub_o) - 1))
+                finally:
+                    uploaded[j].set()
+                e.run_packed(sub_b, sub_o, params, fetch=False, literal=literal, call_weights=call_weights, flags=flags,
+                             resident=True)
+                st = np.zeros(8, dtype=np.int64)
+                e._ck(e.lib.pb200_stats(e.ctx, st.ctypes.data))
+                stats[j] = [int(v) for v in st[:3]]
+                launches[j] = int(e.lib.pb200_launch_count(e.ctx))
+                sizes[j] = e.sizes()
+            finally:
+                sized[j].set()
+            if not fetch:
+                return
+            # this lane's rows go right behind those of the lanes before it: copy out as soon as their sizes are known,
+            # while later lanes are still computing
+            for i in range(j):
+                if not sized[i].wait(timeout=600) or sizes[i] is None:
+                    raise PhanotateError("an earlier group failed")
+            if sum(sizes[i][6] for i in range(j + 1)) > capacity:
+                late[j] = True                         # first run or a larger batch: after the run, into a grown buffer
+                return
+            copy_out(j)
+
+        list(self.pool.map(lane, range(nlive)))
+        if not fetch:
+            return None
+        ncalls = sum(z[6] for z in sizes)
+        if any(late):
+            old = self._calls[:min(capacity, ncalls)].copy()
+            self._grow("_calls", ncalls + ncalls // 4, N.CALL)
+            self._calls[:len(old)] = old
+            for j in range(nlive):
+                if late[j]:
+                    copy_out(j)
+        calls = self._calls[:ncalls]
+        done = [(sizes[j], stats[j], launches[j]) for j in range(nlive)]
         return MergedResult(calls, contigs, [cuts[k] for k in live], sizes, [d[1] for d in done], sum(d[2] for d in done))
