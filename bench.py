@@ -97,7 +97,7 @@ class ClockSampler:
 def _oracle_one(seq: bytes):
     from oracle import phanotate_oracle as O
     rows = O.call_contig(seq.decode())[3]
-    return len(rows)
+    return [tuple(r[:4]) for r in rows]
 
 
 def cpu_sample(n_contigs: int, length: int, first: int = 0):
@@ -108,8 +108,10 @@ def cpu_sample(n_contigs: int, length: int, first: int = 0):
     with Pool(cores) as pool:
         pool.map(_oracle_one, seqs[:min(cores, len(seqs))])      # warm the workers (imports)
         t = time.perf_counter()
-        ncalls = sum(pool.map(_oracle_one, seqs, chunksize=1))
+        rows = pool.map(_oracle_one, seqs, chunksize=1)
         dt = time.perf_counter() - t
+    ncalls = sum(len(r) for r in rows)
+    cpu_sample.rows = rows                       # kept for the parity check of the GPU result against the oracle
     bp = n_contigs * length
     return {"value": bp / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d contigs x %d bp of the same synthetic workload (oracle/phanotate_oracle.py, "
@@ -312,6 +314,9 @@ def main():
         if world == 1 and not args.no_cpu:
             n = args.cpu_sample or 2 * (os.cpu_count() or 1)
             line["cpu_baseline"] = cpu_sample(n, args.length)[0]
+            # the oracle's calls for the sampled contigs are the checker of this run's GPU result (never its source)
+            same = sum(1 for k, want in enumerate(cpu_sample.rows) if res.call_rows(k) == [tuple(w) for w in want])
+            line["cpu_baseline"]["gpu_calls_identical_to_oracle"] = "%d of %d sampled contigs" % (same, len(cpu_sample.rows))
         print(json.dumps(line), flush=True)
     eng.unpin(bases)
     eng.unpin(offs)
