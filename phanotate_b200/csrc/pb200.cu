@@ -311,11 +311,15 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             const i64 ntiles_ = (B.nb + ST_T - 1) / ST_T;                                        \
             const int tpb_ = 32;                                                                 \
             if (!ctx->scan_attr_set) {                                                           \
+                cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)); \
                 cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
                 ctx->scan_attr_set = true;                                                       \
             }                                                                                    \
+            /* bulk TMA copies need a 16-byte aligned source with slack behind the last base: the library's own  \
+               input buffer has both, a caller-owned device buffer (PB200_INPUT_DEVICE) takes the plain loads */ \
+            const int tma_ = (!(B.flags & PB200_INPUT_DEVICE) && (((size_t)B.seq) & 15) == 0) ? 1 : 0; \
             cudaEventRecord(t_.a, ctx->stream);                                                  \
-            k_scan_tiles<<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, 0, ctx->stream>>>(B, ntiles_, tpb_); \
+            k_scan_tiles<<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, sizeof(ScanSmem), ctx->stream>>>(B, ntiles_, tpb_, tma_); \
             cudaEventRecord(t_.b, ctx->stream);                                                  \
             ctx->times.push_back(t_);                                                            \
             ctx->launches++;                                                                     \

@@ -5,8 +5,9 @@
 //
 // A block walks a contiguous range of 2048-base tiles of the concatenated batch.  Per tile and per
 // contig segment inside it (one for ordinary contigs, several for tiny ones):
-//   A  coalesced byte loads of tile + 64-base halos -> base codes in shared memory, GC / acgt bit planes
-//      by warp ballots (positions outside the segment's contig read as "no base")
+//   A  the tile's letters + 64-base halos arrive in shared memory by a 1-D bulk TMA copy (cp.async.bulk, completion on
+//      an mbarrier), issued one tile ahead into the other half of a double buffer; 137 threads turn 16 letters
+//      each into base codes and GC / acgt bit planes (positions outside the segment's contig read as "no base")
 //   B  6-mer -> Shine-Dalgarno motif-set masks for every position (tables in shared memory), restricted to the
 //      motif classes short enough for the run of plain acgt letters at that position: this makes ambiguity
 //      codes and the truncated windows at a contig's end exact without a per-letter fallback
@@ -42,7 +43,47 @@ struct ScanSmem {
     u32 hist[28];
     u32 ngc, nat;
     u64* mptr[18];
+    unsigned long long bar[2];    // mbarriers of the two letter buffers
+    uint4 raw[2][ST_NS / 16];     // letters of [tg0-64, tg0+2048+64), double buffered
 };
+
+// ---- 1-D bulk TMA copy global -> shared with mbarrier completion (PTX ISA: cp.async.bulk, sm_90+)
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u32 bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one thread: start the copy of a tile's letters into buffer `buf`.  The source range is clipped to [0, nb rounded up to
+// 16) -- the library's input buffer is padded by 64 bytes -- and the bytes outside it are never read as bases (phase A
+// masks by contig bounds).
+__device__ __forceinline__ void scan_issue_tile(const Batch& B, ScanSmem& S, i64 tg0, int buf) {
+    i64 g_lo = tg0 - ST_HL, g_hi = tg0 + ST_T + ST_HL;
+    const i64 lim = (B.nb + 15) & ~(i64)15;
+    if (g_lo < 0) g_lo = 0;
+    if (g_hi > lim) g_hi = lim;
+    const u32 bytes = (u32)(g_hi - g_lo);
+    mbar_expect_tx(&S.bar[buf], bytes);
+    tma_load_1d((char*)S.raw[buf] + (g_lo - (tg0 - ST_HL)), B.seq + g_lo, bytes, &S.bar[buf]);
+}
 
 __device__ __forceinline__ void scan_flush(const Batch& B, ScanSmem& S, int cur_c, int tid) {
     if (cur_c < 0) return;
@@ -72,8 +113,9 @@ __device__ __forceinline__ uint4 scan_load_chunk(const Batch& B, i64 tg0, int ti
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block) {
-    __shared__ __align__(16) ScanSmem S;
+__global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block, int use_tma) {
+    extern __shared__ __align__(16) unsigned char scan_smem_raw[];
+    ScanSmem& S = *reinterpret_cast<ScanSmem*>(scan_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += ST_NT) {
         S.tab_end[i] = d_rbs_end_mask[i];
@@ -113,6 +155,9 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
             S.mptr[8 + k] = B.cF[k];
             S.mptr[13 + k] = B.cR[k];
         }
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     int cur_c = -1;                                  // contig of the block's accumulators
@@ -122,15 +167,28 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
     const bool wide = (((size_t)B.seq) & 15) == 0;   // 16-byte loads of the letters (tile starts are multiples of 2048)
     int c = contig_of(B, t0 * ST_T);                 // walking contig cursor with its bounds: tiles are consecutive
     i64 cb = B.coff[c], ce = B.coff[c + 1];
-    uint4 raw_next = scan_load_chunk(B, t0 * ST_T, tid, wide);
+    uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+    if (use_tma) {
+        if (tid == 0 && t0 < t1) scan_issue_tile(B, S, t0 * ST_T, 0);
+    } else {
+        raw_next = scan_load_chunk(B, t0 * ST_T, tid, wide);
+    }
     for (i64 tile = t0; tile < t1; tile++) {
         const i64 tg0 = tile * ST_T;
         const i64 tg1 = (tg0 + ST_T < B.nb) ? tg0 + ST_T : B.nb;
         const i64 gb = tg0 + 8 * tid;                // this thread's bases: gb .. gb+7
         u32 meta_lo = 0, meta_hi = 0;
         u64 acc_cls = 0, acc_cd = 0, acc_kf = 0, acc_kr = 0, acc_sf = 0, acc_sr = 0;
-        const uint4 raw = raw_next;
-        if (tile + 1 < t1) raw_next = scan_load_chunk(B, tg0 + ST_T, tid, wide);   // in flight during this tile's phases
+        uint4 raw = raw_next;
+        if (use_tma) {
+            const int it = (int)(tile - t0), buf = it & 1;
+            // the other buffer was last read in the previous tile's phase A, which every thread left through barriers
+            if (tid == 0 && tile + 1 < t1) scan_issue_tile(B, S, tg0 + ST_T, buf ^ 1);   // in flight during this tile's phases
+            mbar_wait(&S.bar[buf], (u32)((it >> 1) & 1));
+            if (tid < ST_NS / 16) raw = S.raw[buf][tid];
+        } else if (tile + 1 < t1) {
+            raw_next = scan_load_chunk(B, tg0 + ST_T, tid, wide);
+        }
         while (ce <= tg0 && c + 1 < B.nc) {           // (skips empty contigs too)
             c++;
             cb = ce;
