@@ -179,6 +179,9 @@ int64_t pb200_format_tabular(const pb200_call* calls, const pb200_contig* contig
 /* device time of the stages of the last pb200_run in milliseconds (CUDA events on the context's
  * stream); names[i] are static strings.  Returns the number of stages written (<= cap). */
 int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);
+/* device time between the timed stages of the last pb200_run (untimed helpers, host round trips, launch latency):
+ * ms[i] = gap in front of stage names[i] */
+int pb200_stage_gaps(pb200_ctx* ctx, const char** names, float* ms, int cap);
 /* number of kernels launched by the last pb200_run */
 int pb200_launch_count(pb200_ctx* ctx);
 /* device time of the whole last pb200_run (events at its first and last operation on the stream) */

@@ -1103,6 +1103,31 @@ int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap) {
 #endif
 }
 
+// idle / untimed device time in front of every timed stage of the last run (from the end of the previous timed stage,
+// or from the start of the run): prefix scans, memsets, host round trips for table sizes, launch latency
+int pb200_stage_gaps(pb200_ctx* ctx, const char** names, float* ms, int cap) {
+    if (!ctx) return -2;
+#ifndef PB_HOSTSIM
+    int n = 0;
+    cudaEvent_t prev = ctx->run_a;
+    for (auto& t : ctx->times) {
+        if (n >= cap) break;
+        float v = 0.f;
+        if (!prev || cudaEventElapsedTime(&v, prev, t.a) != cudaSuccess) v = -1.f;
+        names[n] = t.name;
+        ms[n] = v;
+        prev = t.b;
+        n++;
+    }
+    return n;
+#else
+    (void)names;
+    (void)ms;
+    (void)cap;
+    return 0;
+#endif
+}
+
 int pb200_launch_count(pb200_ctx* ctx) { return ctx ? ctx->launches : -2; }
 
 }  // extern "C"

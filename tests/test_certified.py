@@ -141,3 +141,21 @@ def test_wide_and_narrow_solver_agree(sim):
     want = [row[:4] for row in O.call_contig(heavy)[3]]
     assert r.call_rows(0) == want
     assert "".join("%d\t%d\t%s\t%s\n" % x for x in r.call_rows(1)) == golden_text("phiX174", "calls.tsv")
+
+
+def test_random_ragged_batch_certified_equals_literal(sim):
+    """120 random contigs of ragged length with IUPAC codes and mixed case on the host build: default == PB200_LITERAL."""
+    rng = np.random.default_rng(7)
+    seqs = []
+    for k in range(120):
+        n = int(rng.integers(60, 4000))
+        gc = rng.uniform(0.25, 0.75)
+        s = rng.choice(np.frombuffer(b"acgt", dtype=np.uint8), size=n, p=[(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])
+        m = rng.random(n) < 0.002
+        s[m] = rng.choice(np.frombuffer(b"nrykmswbdhv", dtype=np.uint8), size=int(m.sum()))
+        seqs.append(s.tobytes().upper() if k % 3 == 0 else s.tobytes())
+    fast, wf, lit, wl = _both(sim, seqs)
+    assert wf == wl
+    for col in ("contig", "left", "right", "strand", "score"):
+        assert np.array_equal(fast.calls[col], lit.calls[col]), col
+    assert np.array_equal(fast.orfs, lit.orfs)

@@ -138,3 +138,30 @@ def test_empty_and_tiny_contigs_inside_a_batch(eng):
         for k in (1, 2, 4, 5, 7):
             assert int(res.contigs[k]["n_calls"]) == 0
         assert int(res.contigs[1]["err"]) & N.ERR_RANGE and int(res.contigs[0]["err"]) == 0 and int(res.contigs[6]["err"]) == 0
+
+
+def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
+    """300 random contigs of ragged length (60 .. 9000 bp, random composition, sprinkled IUPAC codes, lower/upper case):
+    the default run (tiled scan, certified weights, 128-bit solve) against the plain statement of every stage at once
+    (PB200_SCAN_REFERENCE | PB200_LITERAL | PB200_SOLVE_WIDE): calls, ORF table, node table."""
+    rng = np.random.default_rng(20261017)
+    seqs = []
+    for k in range(300):
+        n = int(rng.integers(60, 9000))
+        gc = rng.uniform(0.25, 0.75)
+        p = [(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2]
+        s = rng.choice(np.frombuffer(b"acgt", dtype=np.uint8), size=n, p=p)
+        m = rng.random(n) < 0.002
+        s[m] = rng.choice(np.frombuffer(b"nrykmswbdhv", dtype=np.uint8), size=int(m.sum()))
+        if k % 3 == 0:
+            s = np.frombuffer(s.tobytes().upper(), dtype=np.uint8)
+        seqs.append(s.tobytes())
+    a = eng.run(seqs)
+    wa = a.orf_int_weights()
+    b = eng.run(seqs, literal=True, flags=N.SCAN_REFERENCE | N.SOLVE_WIDE)
+    assert wa == b.orf_int_weights()
+    for col in ("contig", "left", "right", "strand", "score"):
+        assert np.array_equal(a.calls[col], b.calls[col]), col
+    assert np.array_equal(a.orfs, b.orfs) and np.array_equal(a.nodes, b.nodes)
+    assert np.array_equal(a.contigs["err"], b.contigs["err"]) and np.array_equal(a.contigs["n_calls"], b.contigs["n_calls"])
+    assert a.n_calls > 1000
