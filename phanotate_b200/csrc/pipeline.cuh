@@ -169,6 +169,7 @@ struct Batch {
     u64* cF[5];           // bit set where the forward codon starting here has GC-frame factor index k (k = 5: the rest)
     u64* cR[5];           // same for the reverse strand
     // node-parallel fill / ORF scoring split
+    i32* role_list;       // [nn] node ids: the start nodes in ORF order, then the stop-key nodes
     u64* n_gpos;          // [nn] (global base position << 1) | role (0 start node, 1 stop-key node)
     Dec* o_hold;          // [no] product over the codons (functions.py:286-298)
     Dec* o_x;             // [no] 1 - pstop
