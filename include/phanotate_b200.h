@@ -164,6 +164,15 @@ int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const i
                        const int32_t* dst, const uint32_t* weight_limbs, int32_t source, int32_t target,
                        int32_t* path_out, int32_t* path_len);
 
+/* The join of the reference's C extension (src/phanotate_connect.c:78-121 `get_connected`, fed by `add_edge` :62-76;
+ * the extension is built by setup.py:6-21 but phanotate.py never imports it).  Edge i = (left[i], right[i]) in add_edge
+ * order.  *n_rows = number of rows; when out != NULL and cap_rows >= *n_rows, out receives the rows as int32 pairs
+ * (right_i, left_j) in the reference's order (right entries outermost, left entries innermost, both in insertion order);
+ * the reference's third tuple member is the constant 0.  Row condition: |right_i - left_j| <= 300, right_i != right_j,
+ * left_i != left_j (:108-110; `min_distance` is ignored by the reference, :84-92).  Host pointers. */
+int pb200_connect(pb200_ctx* ctx, const int32_t* left, const int32_t* right, int32_t n, int32_t* out, int64_t cap_rows,
+                  int64_t* n_rows);
+
 /* Host-side text ingest / output for whole batches (no device work): multi-record FASTA -> the packed batch of
  * pb200_run, and the tabular text of a batch (Locus.tabular, locus.py:39-56).
  * pb200_fasta_count: number of records ('>' at a line start).  pb200_fasta_parse: bases must hold n bytes, offsets

@@ -12,6 +12,7 @@
 
 #include "../../include/phanotate_b200.h"
 #include "graph.cuh"
+#include "connect.cuh"
 #include "fast.cuh"
 
 static_assert(sizeof(pb200_dec) == sizeof(Dec), "Dec layout");
@@ -215,7 +216,7 @@ struct pb200_ctx {
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::string err;
     DevBuf ph[NPHASE];
-    DevBuf in_seq, in_off, scratch;
+    DevBuf in_seq, in_off, scratch, conn, conn_out;
     Batch B;
     bool have = false;
     std::vector<StageTime> times;
@@ -405,7 +406,7 @@ struct pb200_ctx {
     int contig_base = 0;
     std::string err;
     DevBuf ph[NPHASE];
-    DevBuf in_seq, in_off, scratch;
+    DevBuf in_seq, in_off, scratch, conn, conn_out;
     Batch B;
     bool have = false;
     int launches = 0;
@@ -658,6 +659,8 @@ void pb200_destroy(pb200_ctx* ctx) {
     cudaFree(ctx->in_seq.p);
     cudaFree(ctx->in_off.p);
     cudaFree(ctx->scratch.p);
+    cudaFree(ctx->conn.p);
+    cudaFree(ctx->conn_out.p);
     for (auto e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
@@ -670,6 +673,8 @@ void pb200_destroy(pb200_ctx* ctx) {
     free(ctx->in_seq.p);
     free(ctx->in_off.p);
     free(ctx->scratch.p);
+    free(ctx->conn.p);
+    free(ctx->conn_out.p);
 #endif
     delete ctx;
 }
@@ -1002,6 +1007,60 @@ int pb200_bellman_ford(pb200_ctx* ctx, int32_t n_nodes, int32_t n_edges, const i
 #endif
     PB_TO_HOST(path_len, a.path_len, 4);
     if (*path_len > 0) PB_TO_HOST(path_out, a.path, (size_t)(*path_len) * 4);
+    return 0;
+}
+
+// src/phanotate_connect.c:78-121 (get_connected) over the edges (left[i], right[i]) in add_edge order (:62-76)
+int pb200_connect(pb200_ctx* ctx, const int32_t* left, const int32_t* right, int32_t n, int32_t* out, int64_t cap_rows,
+                  int64_t* n_rows) {
+    if (!ctx || n < 0 || !n_rows || (n > 0 && (!left || !right))) return -2;
+    *n_rows = 0;
+    if (n == 0) return 0;
+    if (n > (1 << 22)) {
+        ctx->err = "pb200_connect: more than 4,194,304 edges";
+        return -2;
+    }
+    ConnArgs a;
+    a.n = n;
+    a.nchunk = (n + CN_CHUNK - 1) / CN_CHUNK;
+    const i64 items = (i64)n * a.nchunk;
+    if (buf_ensure(ctx, ctx->conn, 2 * ((size_t)n * 4 + 256) + (size_t)(items + 1) * 8 + 1024)) return -1;
+    i32* dl = (i32*)buf_take(ctx->conn, (size_t)n * 4);
+    i32* dr = (i32*)buf_take(ctx->conn, (size_t)n * 4);
+    a.cnt = (u64*)buf_take(ctx->conn, (size_t)(items + 1) * 8);
+    a.left = dl;
+    a.right = dr;
+    a.out = nullptr;
+    u64 total = 0;
+#ifndef PB_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dl, left, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dr, right, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    i64 gx = ((i64)n + CN_BLOCK - 1) / CN_BLOCK;
+    if (gx > (i64)ctx->sm_count * 8) gx = (i64)ctx->sm_count * 8;
+    const dim3 grid((unsigned)gx, (unsigned)a.nchunk);
+    k_connect<false><<<grid, CN_BLOCK, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+#else
+    memcpy(dl, left, (size_t)n * 4);
+    memcpy(dr, right, (size_t)n * 4);
+    for (i64 it = 0; it < items; it++) conn_item(a, it, false);
+#endif
+    if (dev_scan<u64>(ctx, a.cnt, items)) return -1;
+    PB_FETCH(&total, a.cnt + items, 8);
+    *n_rows = (int64_t)total;
+    if (!out || cap_rows < (int64_t)total || total == 0) return 0;
+    if (buf_ensure(ctx, ctx->conn_out, (size_t)total * 8 + 256)) return -1;
+    a.out = (i32*)buf_take(ctx->conn_out, (size_t)total * 8);
+#ifndef PB_HOSTSIM
+    k_connect<true><<<grid, CN_BLOCK, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+#else
+    for (i64 it = 0; it < items; it++) conn_item(a, it, true);
+#endif
+    PB_FETCH(out, a.out, (size_t)total * 8);
     return 0;
 }
 
