@@ -110,6 +110,8 @@ enum {
                                  filled only where the Decimal chain ran anyway and is 0 elsewhere; pb200_call.score,
                                  the float that Locus.tabular prints with '%E', is always exact) */
     PB200_SOLVE_WIDE = 32,    /* testing: 256-bit distances in the solve for every contig */
+    PB200_SOLVE_PLAIN = 64,   /* testing: the plain statement of the 128-bit sweep (every operand fetched when needed) instead
+                                 of the windowed kernel */
     PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly

@@ -40,6 +40,7 @@ LITERAL = 4
 SCAN_REFERENCE = 8
 CALL_WEIGHTS = 16
 SOLVE_WIDE = 32
+SOLVE_PLAIN = 64
 NODE_SOURCE, NODE_TARGET = -2, -3
 
 

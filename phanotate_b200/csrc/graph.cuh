@@ -510,6 +510,171 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
         B.tparent[c] = tpar;
     }
 }
+#ifdef __CUDACC__
+// The 128-bit sweep as the kernel runs it.  Same visits, same relaxations, same order as solve_contig_t (which stays
+// the plain statement: the host build and the 256-bit contigs run it); what changes is where the operands come from.
+// Every iteration the warp loads the records of the 32 nodes at the sweep position in ONE round of independent loads
+// (dirty flag, packed word, distance, mate, ORF, overlap range: one node per lane).  The ballot over the dirty flags
+// picks the node u to visit, its record arrives by shuffles, and the lanes behind it already hold the packed word and
+// the current distance of u's gap / reverse-ORF targets: a visit is one or two memory round trips deep instead of four.
+// Targets beyond the 32-node window (dense stretches, long reverse families) take the loops of the plain statement.
+__device__ __forceinline__ I128 shfl128(const I128& a, int src) {
+    I128 r;
+    r.lo = (u64)__shfl_sync(0xFFFFFFFFu, (unsigned long long)a.lo, src);
+    r.hi = (i64)__shfl_sync(0xFFFFFFFFu, (long long)a.hi, src);
+    return r;
+}
+__device__ void solve_contig_win(const Batch& B, int c, int lane) {
+    typedef D128 D;
+    typedef I128 T;
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    CStat* cs = B.cs + c;
+    const int L = cs->L;
+    T* dist = B.dist128;
+    const u32* pk = B.n_pk;
+    u32 ties = 0;
+    bool okw = true;
+    for (i32 i = nb + lane; i < ne; i += 32) {
+        const u32 w = pk[i];
+        T d0 = D::inf();
+        i32 p0 = -1;
+        u8 f0 = 0;
+        if ((int)(w >> 4) <= 2000 && kind_is_entry((int)(w & 3))) {       // source -> entry (functions.py:444-447)
+            bool o;
+            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4), false, &o));
+            okw = okw && o;
+            p0 = -2;
+            f0 = 1;
+        }
+        dist[i] = d0;
+        B.parent[i] = p0;
+        B.dirty[i] = f0;
+    }
+    T tdist = D::inf();
+    i32 tpar = -1;
+    __syncwarp();
+    const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
+    i32 i = nb;
+    int budget = 64 * (ne - nb) + 1024;
+    while (i < ne) {
+        // ---- the window: node i + lane
+        const i32 j0 = i + lane;
+        const bool in = j0 < ne;
+        u8 dj = 0;
+        u32 wj = 0, cj = 0;
+        i32 mj = -1, oj = -1;
+        T Tj = D::inf();
+        if (in) {
+            dj = B.dirty[j0];
+            wj = pk[j0];
+            Tj = dist[j0];
+            mj = B.n_mate[j0];
+            oj = B.n_orf[j0];
+            cj = B.ov_cnt[j0];
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, dj != 0);
+        if (!m) {
+            i += 32;
+            continue;
+        }
+        if (--budget < 0) {
+            if (lane == 0) atomicOr(&cs->err, (u32)ERR_INTERNAL);
+            break;
+        }
+        const int f = __ffs((int)m) - 1;
+        const i32 u = i + f;
+        const u32 wu = __shfl_sync(0xFFFFFFFFu, wj, f);
+        const T Du = shfl128(Tj, f);
+        const i32 mate_u = __shfl_sync(0xFFFFFFFFu, mj, f), orf_u = __shfl_sync(0xFFFFFFFFu, oj, f);
+        const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
+        if (lane == 0) B.dirty[u] = 0;
+        i32 rewind = 0x7FFFFFFF;
+        const bool behind = in && lane > f;                 // a node after u inside the window
+        if (kind == K_FSTART) {
+            if (lane == 0) {
+                const T cur = dist[mate_u];
+                relax<D>(B, ties, dist, mate_u, cur, D::add(Du, D::load_w(B.o_wint + orf_u)), u);
+            }
+        } else if (kind == K_RSTOP) {
+            // the starts of this reverse family: nodes up to its farthest start (n_mate of the stop-key node)
+            if (behind && j0 <= mate_u && (int)(wj & 3) == K_RSTART && mj == u)
+                relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::load_w(B.o_wint + oj)), u);
+            for (i32 j = i + 32 + lane; j <= mate_u; j += 32) {
+                const u32 w2 = pk[j];
+                const i32 m2 = B.n_mate[j];
+                if ((int)(w2 & 3) == K_RSTART && m2 == u) {
+                    const i32 orf = B.n_orf[j];
+                    const T cur = dist[j];
+                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+                }
+            }
+        } else {
+            const u32 ovb = __shfl_sync(0xFFFFFFFFu, cj, f);
+            u32 ove = __shfl_sync(0xFFFFFFFFu, cj, (f + 1) & 31);
+            if (f == 31 || u + 1 >= ne) ove = B.ov_cnt[u + 1];
+            // gap edges to entries within 500 bp downstream (functions.py:360-438)
+            {
+                const int kj = (int)(wj & 3), d = (int)(wj >> 4) - pu;
+                if (behind && d > 0 && d < 500 && kind_is_entry(kj) && !(kind == K_RSTART && kj == K_FSTART && d <= 2)) {
+                    const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+                    bool o;
+                    relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                }
+            }
+            const u32 wlast = __shfl_sync(0xFFFFFFFFu, wj, 31);
+            if (i + 32 < ne && (int)(wlast >> 4) - pu < 500) {
+                for (i32 j = i + 32 + lane; j < ne; j += 32) {
+                    const u32 w2 = pk[j];
+                    const T cur = dist[j];
+                    const int kj = (int)(w2 & 3), d = (int)(w2 >> 4) - pu;
+                    if (d >= 500) break;
+                    if (d <= 0 || !kind_is_entry(kj)) continue;
+                    const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+                    if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
+                    bool o;
+                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                }
+            }
+            // overlap edges (backwards)
+            if (ove > ovb) {
+                for (u32 k = ovb + lane; k < ove; k += 32) {
+                    const i64 w64 = B.ov_w64[k];
+                    const i32 v = B.ov_dst[k];
+                    const T cur = dist[v];
+                    const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
+                    if (relax<D>(B, ties, dist, v, cur, cand, u) && v < rewind) rewind = v;
+                }
+                rewind = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)rewind);
+            }
+            // bridges
+            for (u32 k = brb + lane; k < bre; k += 32) {
+                if (B.br_src[k] != u) continue;
+                const i32 v = B.br_dst[k];
+                const T cur = dist[v];
+                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u);
+            }
+            // exit -> target within 2000 bp of the right end (functions.py:448-451)
+            if (L - pu <= 2000) {
+                bool o;
+                const T cand = D::add(Du, D::from_i64(gap_w64(B, c, L - pu, false, &o)));
+                okw = okw && o;
+                if (D::less(cand, tdist)) {
+                    tdist = cand;
+                    tpar = u;
+                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
+            }
+        }
+        __syncwarp();
+        i = (rewind < u) ? rewind : u + 1;
+    }
+    if (ties) atomicAdd(&cs->n_ties, ties);
+    if (!okw && lane == 0) atomicOr(&cs->err, (u32)ERR_OVERFLOW);
+    if (lane == 0) {
+        B.tdist[c] = D::to_wint(tdist);
+        B.tparent[c] = tpar;
+    }
+}
+#endif
 PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE); }
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
     if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);

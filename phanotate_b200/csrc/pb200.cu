@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 c = warp; c < nc; c += nwarps)
-        if (!contig_is_wide(B, (int)c)) solve_contig_t<D128>(B, (int)c, lane, 32);
+        if (!contig_is_wide(B, (int)c)) {
+            if (B.flags & PB200_SOLVE_PLAIN) solve_contig_t<D128>(B, (int)c, lane, 32);
+            else solve_contig_win(B, (int)c, lane);
+        }
 }
 __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) {
     const int lane = threadIdx.x & 31;

@@ -165,3 +165,6 @@ def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
     assert np.array_equal(a.orfs, b.orfs) and np.array_equal(a.nodes, b.nodes)
     assert np.array_equal(a.contigs["err"], b.contigs["err"]) and np.array_equal(a.contigs["n_calls"], b.contigs["n_calls"])
     assert a.n_calls > 1000
+    # the windowed 128-bit sweep against its plain statement: same parents, same tie counts, same calls
+    p = eng.run(seqs, flags=N.SOLVE_PLAIN)
+    assert np.array_equal(a.calls, p.calls) and np.array_equal(a.contigs, p.contigs)
