@@ -100,7 +100,8 @@ enum {
     PB200_ERR_OVERFLOW = 8,
     PB200_ERR_NOPATH = 16,
     PB200_ERR_INTERNAL = 32,
-    PB200_ERR_LOOKUP = 64
+    PB200_ERR_LOOKUP = 64,
+    PB200_ERR_TIES = 128        /* exact ties in the solve that could not be settled in the reference's edge order */
 };
 
 enum {

@@ -33,7 +33,7 @@ PARAMS = np.dtype([("n_start", "<i4"), ("start_codon", "S4", (8,)), ("start_weig
 assert CALL.itemsize == 48 and ORF.itemsize == 80 and NODE.itemsize == 32 and EDGE.itemsize == 40
 assert PARAMS.itemsize == 4 + 32 + 192 + 4 + 32 + 8
 
-ERR_CHAR, ERR_RANGE, ERR_PARALLEL, ERR_OVERFLOW, ERR_NOPATH, ERR_INTERNAL, ERR_LOOKUP = 1, 2, 4, 8, 16, 32, 64
+ERR_CHAR, ERR_RANGE, ERR_PARALLEL, ERR_OVERFLOW, ERR_NOPATH, ERR_INTERNAL, ERR_LOOKUP, ERR_TIES = 1, 2, 4, 8, 16, 32, 64, 128
 INPUT_DEVICE = 1
 REUSE_INPUT = 2
 LITERAL = 4

@@ -284,6 +284,22 @@ struct
     u64 lo;
     i64 hi;
 };
+// An exact tie: remember the edge.  The sweep keeps the first edge IT saw reach a distance; the reference's solver
+// (Bellman-Ford over the edges in Graph.iteredges() order, strict '<', phanotate.py:56-64) keeps the first edge IT sees,
+// and st_tie_fix settles the difference afterwards from these records.
+// Recording is a handful of inline instructions in the cold branch of relax (one atomic counter, three stores): the
+// events are threaded into per-contig lists afterwards (st_tie_link).  v = -3 - contig stands for the contig's target.
+PB_HD TieEv* tie_slot(const Batch& B, int c, i32 v, i32 from) {
+    const u32 k = PB_ATOMIC_ADD_RET(B.tie_n, 1u);
+    if (k >= (u32)B.tie_cap) {
+        PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_TIES);
+        return nullptr;
+    }
+    TieEv* e = B.tie_ev + k;
+    e->v = v;
+    e->from = from;
+    return e;
+}
 struct D256 {
     typedef WInt T;
     static PB_HD T inf() { return wint_inf(); }
@@ -298,6 +314,13 @@ struct D256 {
     static PB_HD T load_w(const WInt* p) { return *p; }
     static PB_HD T* dist(const Batch& B) { return B.dist; }
     static PB_HD WInt to_wint(const T& a) { return a; }
+    static PB_HD void tie(const Batch& B, int c, i32 v, i32 from, const T& cand) {
+        TieEv* e = tie_slot(B, c, v, from);
+        if (e) {
+            e->pad = 0;
+            e->cand = cand;
+        }
+    }
 };
 struct D128 {
     typedef I128 T;
@@ -342,6 +365,15 @@ struct D128 {
         if (is_inf(a)) r = wint_inf();
         return r;
     }
+    static PB_HD void tie(const Batch& B, int c, i32 v, i32 from, const T& cand) {
+        TieEv* e = tie_slot(B, c, v, from);
+        if (e) {
+            e->pad = 1;                           // the low 128 bits; st_tie_fix extends the sign
+            u64* w = (u64*)&e->cand;
+            w[0] = cand.lo;
+            w[1] = (u64)cand.hi;
+        }
+    }
 };
 // integer weight of score_gap(len,'same'|'diff') as the solver sees it; len < 500 (connect), <= 2000 (terminals)
 PB_HD i64 gap_w64(const Batch& B, int c, int len, bool diff, bool* ok) {
@@ -366,7 +398,10 @@ PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const ty
         B.dirty[v] = 1;
         return true;
     }
-    if (!D::is_inf(cur) && D::eq(cand, cur) && B.parent[v] != from) ties++;
+    if (!D::is_inf(cur) && D::eq(cand, cur) && B.parent[v] != from) {
+        ties++;
+        D::tie(B, B.n_contig[v], v, from, cand);
+    }
     return false;
 }
 
@@ -497,7 +532,10 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
                 if (D::less(cand, tdist)) {
                     tdist = cand;
                     tpar = u;
-                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
+                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) {
+                    ties++;
+                    D::tie(B, c, -3 - c, u, cand);
+                }
             }
         }
         PB_SYNCWARP();
@@ -661,7 +699,10 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
                 if (D::less(cand, tdist)) {
                     tdist = cand;
                     tpar = u;
-                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) ties++;
+                } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != u) {
+                    ties++;
+                    D::tie(B, c, -3 - c, u, cand);
+                }
             }
         }
         __syncwarp();
@@ -679,6 +720,187 @@ PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.fla
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
     if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
     else solve_contig_t<D128>(B, c, lane, NL);
+}
+
+// Stage 12b: exact ties.  Distances do not depend on the relaxation order, parents do: where two edges into a node
+// offer the same final distance, the reference's solver keeps the one it processes first -- Bellman-Ford passes over
+// the edges in Graph.iteredges() order, i.e. grouped by source node in node insertion order sigma (graphs.py:121-126,
+// functions.py:311-318), strict '<'.  A node x whose parent is y reached its final distance while y's group was
+// processed, so x's own group offers it in the same pass if sigma(x) > sigma(y) and one pass later otherwise; hence
+//     pass(x -> v) = 1 + number of edges y -> z on the parent chain source .. x -> v's source side with sigma(z) < sigma(y)
+// and the reference's parent of v is the tight in-edge with the smallest (pass, sigma(x)).  The tight in-edges of v are
+// the sweep's parent plus the recorded ties whose value is the final distance.  Only contigs with ties do any work.
+// (Checked against the oracle's edge-order Bellman-Ford: tests/test_certified.py, tests/tie_audit.py.)
+#define TIE_MAXN 32
+// insertion index of node a inside its family's run of the node order: forward family = nearest start, stop, then the
+// other starts by descending position; reverse family = stop-key node, then the starts by ascending position
+PB_HDN int tie_sigma_idx(const Batch& B, i32 a, i32 fam) {
+    if ((B.n_kind[fam] & 3) == K_FSTOP) {
+        if (a == fam) return 1;
+        int r = 1;
+        for (i32 j = a + 1; j < fam; j++)
+            if ((B.n_kind[j] & 3) == K_FSTART && B.n_mate[j] == fam) r++;
+        return r == 1 ? 0 : r;
+    }
+    if (a == fam) return 0;
+    int r = 0;
+    for (i32 j = fam + 1; j <= a; j++)
+        if ((B.n_kind[j] & 3) == K_RSTART && B.n_mate[j] == fam) r++;
+    return r;
+}
+// sigma(a) < sigma(b); -2 = the source node, inserted after every CDS node (functions.py:440-443)
+PB_HDN bool tie_sigma_less(const Batch& B, i32 a, i32 b) {
+    if (a == b || a == -2) return false;
+    if (b == -2) return true;
+    const int ka = B.n_kind[a] & 3, kb = B.n_kind[b] & 3;
+    const i32 fa = (ka == K_FSTOP || ka == K_RSTOP) ? a : B.n_mate[a];
+    const i32 fb = (kb == K_FSTOP || kb == K_RSTOP) ? b : B.n_mate[b];
+    const i32 ta = B.n_trig[fa], tb = B.n_trig[fb];
+    if (ta != tb) return ta < tb;
+    if (fa != fb) return fa < fb;                 // (two families emitted at one scan position: custom stop codon sets)
+    return tie_sigma_idx(B, a, fa) < tie_sigma_idx(B, b, fb);
+}
+// pass in which the edge x -> (some node) offers x's final distance; -1: an unsettled tie node lies on the chain,
+// -2: the chain is broken
+PB_HDN int tie_chain_pass(const Batch& B, i32 x, const i32* tv, const bool* done, int n, i32 limit) {
+    if (x == -2) return 1;
+    int cnt = 1;
+    i32 y = x;
+    for (i32 steps = 0; steps <= limit; steps++) {
+        for (int a = 0; a < n; a++)
+            if (!done[a] && tv[a] == y) return -1;
+        const i32 py = B.parent[y];
+        if (py == -2) return cnt + 1;             // sigma(y) < sigma(source) always
+        if (py < 0) return -2;
+        if (tie_sigma_less(B, y, py)) cnt++;
+        y = py;
+    }
+    return -2;
+}
+// The candidates of one tie node usually share an ancestor a few edges back, and everything above it is common to
+// their pass counts: walk each parent chain for at most TIE_K nodes, remembering the descents so far.
+//   node[0] = x, node[i+1] = parent(node[i]) (the source, -2, ends the list); cum[i] = descents on the edges between
+//   node[i] and x.  Returns the length, -1 if an unsettled tie node lies on the walked part, -2 if the chain is broken.
+#define TIE_K 48
+PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, const bool* done, int n) {
+    int len = 0, c = 0;
+    i32 y = x;
+    while (len < TIE_K) {
+        node[len] = y;
+        cum[len] = c;
+        len++;
+        if (y == -2) break;
+        for (int a = 0; a < n; a++)
+            if (!done[a] && tv[a] == y) return -1;
+        const i32 py = B.parent[y];
+        if (py < 0 && py != -2) return -2;
+        if (tie_sigma_less(B, y, py)) c++;
+        y = py;
+    }
+    return len;
+}
+// thread the recorded events into per-contig lists.  item = event slot
+PB_HDN void st_tie_link(const Batch& B, i64 k) {
+    u32 n = *B.tie_n;
+    if (n > (u32)B.tie_cap) n = (u32)B.tie_cap;
+    if (k >= (i64)n) return;
+    TieEv* e = B.tie_ev + k;
+    const int c = (e->v <= -3) ? (-3 - e->v) : B.n_contig[e->v];
+    if (e->v <= -3) e->v = -3;
+    if (e->pad == 1) {
+        const u32 ext = (e->cand.w[3] >> 31) ? 0xFFFFFFFFu : 0u;
+        for (int i = 4; i < WN; i++) e->cand.w[i] = ext;
+    }
+    e->next = PB_ATOMIC_EXCH(&B.cs[c].tie_head, (i32)k + 1);
+}
+PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
+    if (c64 >= B.nc) return;
+    const int c = (int)c64;
+    CStat* cs = B.cs + c;
+    if (!cs->tie_head) return;
+    const bool wide = contig_is_wide(B, c);
+    const i32 nodes = B.cnode[c + 1] - B.cnode[c];
+    i32 tv[TIE_MAXN], tf[TIE_MAXN];
+    bool done[TIE_MAXN];
+    int n = 0;
+    for (i32 k = cs->tie_head; k;) {
+        const TieEv* e = B.tie_ev + (k - 1);
+        const WInt fin = (e->v == -3) ? B.tdist[c] : (wide ? B.dist[e->v] : D128::to_wint(B.dist128[e->v]));
+        if (w_cmp(fin, e->cand) == 0) {           // the tie is at the node's FINAL distance: a second tight in-edge
+            if (n == TIE_MAXN) {
+                cs->err |= ERR_TIES;
+                return;
+            }
+            tv[n] = e->v;
+            tf[n] = e->from;
+            done[n] = false;
+            n++;
+        }
+        k = e->next;
+    }
+    i32 ynode[TIE_K], znode[TIE_K];
+    int ycum[TIE_K], zcum[TIE_K];
+    for (int round = 0; round <= n; round++) {
+        bool open = false;
+        for (int a = 0; a < n; a++) {
+            if (done[a]) continue;
+            const i32 v = tv[a];
+            i32 best = (v == -3) ? B.tparent[c] : B.parent[v];
+            int ylen = tie_walk(B, best, ynode, ycum, tv, done, n);
+            bool wait = ylen == -1, broken = ylen == -2;
+            for (int b = a; b < n && !wait && !broken; b++) {
+                if (done[b] || tv[b] != v) continue;
+                const i32 x = tf[b];
+                const int zlen = tie_walk(B, x, znode, zcum, tv, done, n);
+                if (zlen == -1) {
+                    wait = true;
+                    break;
+                }
+                if (zlen == -2) {
+                    broken = true;
+                    break;
+                }
+                int dy = -1, dz = -1;             // descents of both chains below their first common node
+                for (int j = 0; j < zlen && dy < 0; j++)
+                    for (int i = 0; i < ylen; i++)
+                        if (ynode[i] == znode[j]) {
+                            dy = ycum[i];
+                            dz = zcum[j];
+                            break;
+                        }
+                if (dy < 0) {                     // no common node within TIE_K: the absolute pass numbers
+                    dy = tie_chain_pass(B, best, tv, done, n, nodes);
+                    dz = tie_chain_pass(B, x, tv, done, n, nodes);
+                    if (dy == -1 || dz == -1) {
+                        wait = true;
+                        break;
+                    }
+                    if (dy == -2 || dz == -2) {
+                        broken = true;
+                        break;
+                    }
+                }
+                if (dz < dy || (dz == dy && tie_sigma_less(B, x, best))) {
+                    best = x;
+                    ylen = tie_walk(B, best, ynode, ycum, tv, done, n);    // (cannot fail: just walked as z)
+                }
+            }
+            if (broken) {
+                cs->err |= ERR_TIES;
+                return;
+            }
+            if (wait) {
+                open = true;
+                continue;
+            }
+            if (v == -3) B.tparent[c] = best;
+            else B.parent[v] = best;
+            for (int b = a; b < n; b++)
+                if (tv[b] == v) done[b] = true;
+        }
+        if (!open) return;
+    }
+    cs->err |= ERR_TIES;                          // ties that wait on each other (a zero-weight cycle of tight edges)
 }
 
 // Stage 13: walk the parent pointers back from the target; the ORF edges on the path are the calls

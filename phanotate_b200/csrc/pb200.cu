@@ -69,6 +69,8 @@ PB_KERNEL(st_ov_fill)
 PB_KERNEL(st_br_count)
 PB_KERNEL(st_br_fill)
 PB_KERNEL(st_backtrack)
+PB_KERNEL(st_tie_fix)
+PB_KERNEL(st_tie_link)
 PB_KERNEL(st_gather_calls)
 PB_KERNEL(st_call_orf)
 PB_KERNEL(st_fast_tables)

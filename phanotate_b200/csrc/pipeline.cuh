@@ -28,7 +28,8 @@ enum {
     ERR_OVERFLOW = 8,    // integer distance does not fit the wide type
     ERR_NOPATH = 16,     // target not reachable (behaviour of the absent fastpathz is undefined)
     ERR_INTERNAL = 32,
-    ERR_LOOKUP = 64      // ValueError from Orfs.get_orf (orfs.py:62-69)
+    ERR_LOOKUP = 64,     // ValueError from Orfs.get_orf (orfs.py:62-69)
+    ERR_TIES = 128       // exact ties in the solve that the edge-order tie-break (st_tie_fix) could not settle
 };
 #define GAPN 303          // gap lengths -2..300 (functions.py:36-46)
 #define WN 8              // limbs of the exact distances (256 bit)
@@ -60,6 +61,7 @@ struct CStat {
     u32 hist_bg[28], hist_tr[28];
     u32 cmax[4], cmin[4];
     u32 n_ties, n_relax;
+    i32 tie_head;           // 1 + index of the contig's newest tie event (0: none)
     Dec pstop, g, g100;
     SFx ln_g;
     Dec wrbs[28];
@@ -71,6 +73,12 @@ struct CStat {
     i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
     DD fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
+};
+
+// an equal-distance relaxation seen by the sweep: edge from -> v offered `cand` when dist[v] was already `cand`
+struct TieEv {
+    i32 v, from, next, pad;   // v = -3: the target; next = 1 + index of the contig's previous event
+    WInt cand;
 };
 
 struct CallRec {          // one CDS call (contig, left, right, strand, weight, float score)
@@ -143,6 +151,9 @@ struct Batch {
     u8* dirty;
     WInt* tdist;          // [nc] distance of the target
     i32* tparent;         // [nc]
+    TieEv* tie_ev;        // [tie_cap] per-contig lists (CStat.tie_head)
+    u32* tie_n;           // [1] events recorded
+    i32 tie_cap;
     // calls
     i32* call_tmp;        // [no] ORF ids on the path, per contig region
     u32* call_cnt;        // [nc+1]
@@ -209,6 +220,7 @@ struct Batch {
 #define PB_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define PB_ATOMIC_ADD_RET(p, v) atomicAdd((p), (v))
 #define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define PB_ATOMIC_EXCH(p, v) atomicExch((p), (v))
 #else
 #define PB_ATOMIC_ADD(p, v) (*(p) += (v))
 static inline u32 pb_fetch_add(u32* p, u32 v) {
@@ -218,6 +230,12 @@ static inline u32 pb_fetch_add(u32* p, u32 v) {
 }
 #define PB_ATOMIC_ADD_RET(p, v) pb_fetch_add((p), (v))
 #define PB_ATOMIC_OR(p, v) (*(p) |= (v))
+static inline i32 pb_exch(i32* p, i32 v) {
+    i32 o = *p;
+    *p = v;
+    return o;
+}
+#define PB_ATOMIC_EXCH(p, v) pb_exch((p), (v))
 #endif
 
 // ------------------------------------------------------------------------------------------------
