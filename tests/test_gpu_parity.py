@@ -168,3 +168,27 @@ def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
     # the windowed 128-bit sweep against its plain statement: same parents, same tie counts, same calls
     p = eng.run(seqs, flags=N.SOLVE_PLAIN)
     assert np.array_equal(a.calls, p.calls) and np.array_equal(a.contigs, p.contigs)
+
+
+def test_three_thousand_bench_contigs_match_the_oracle_digest(eng):
+    """Contigs 0..2999 of the bench workload (150 Mbp, ~300 of them with an exact tie in the shortest path) in one batch:
+    the md5 of every contig's call table against the oracle's (tests/golden/synth4_calls_digest.json, a derived golden
+    made by tests/golden/make_synth4_digest.py), under the default run and under the plain 128-bit sweep."""
+    import hashlib
+    import json
+    import os
+    from helpers import GOLDEN
+    from phanotate_b200 import synth
+    g = json.load(open(os.path.join(GOLDEN, "synth4_calls_digest.json")))
+    n = len(g["md5_16"])
+    bases, offs = synth.synth4_batch(n, 50000)
+    for flags in (0, N.SOLVE_PLAIN):
+        res = eng.run_packed(bases, offs, flags=flags)
+        assert int((res.contigs["err"] != 0).sum()) == 0
+        assert [int(v) for v in res.contigs["n_calls"]] == g["n_calls"]
+        bad = []
+        for k in range(n):
+            text = "".join("%d\t%d\t%s\t%s\n" % r for r in res.call_rows(k))
+            if hashlib.md5(text.encode()).hexdigest()[:16] != g["md5_16"][k]:
+                bad.append(k)
+        assert bad == [], (flags, bad[:10])
