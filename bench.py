@@ -183,6 +183,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from phanotate_b200.engine import Engine, PipelinedEngine, make_params
     from phanotate_b200 import _native as N
+    from phanotate_b200.dist import bind_near_gpu
+    numa = bind_near_gpu(local)                                   # before the pinned buffers and the lane threads exist
     eng = Engine(local)
     params = make_params()
     # this rank's batch: contigs rank*C .. rank*C + C-1 of the generator
@@ -237,11 +239,20 @@ def main():
     peng = PipelinedEngine(local, lanes=args.lanes)
 
     def gather_host_calls(res):
+        """N > 1: every rank has its rows on its host (the run's device->host copy); the cross-rank gather to rank 0 goes
+        device to device over NCCL, straight from the lanes' device tables (no second upload)."""
         if dist is None:
             return
-        from phanotate_b200.dist import gather_call_tables
-        raw = torch.from_numpy(res.calls.view(np.uint8).reshape(-1)).cuda() if res.n_calls else torch.zeros(1, dtype=torch.uint8, device="cuda")
-        gather_call_tables(raw, res.n_calls, dist, rank, world)
+        from phanotate_b200.dist import DeviceCalls, gather_call_tables
+        parts, total = [], 0
+        for e in peng.engines:
+            n = e.sizes()[6]
+            if n:
+                parts.append(torch.as_tensor(DeviceCalls(e.lib.pb200_device_calls(e.ctx), n), device="cuda"))
+                total += n
+        assert total == res.n_calls
+        mine = torch.cat(parts) if parts else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        gather_call_tables(mine, total, dist, rank, world)
         if rank == 0:
             torch.cuda.synchronize()
 
@@ -304,7 +315,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+f64x2+int128", "data": "synthetic",
-                "config": workload_config(args, world), "clocks": clocks,
+                "config": dict(workload_config(args, world), numa=numa), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps},
                 "gpu_launches": launches, "roofline": roof,
