@@ -231,8 +231,15 @@ struct pb200_ctx {
     int sm_count = 148;
     int contig_base = 0;
     bool scan_attr_set = false;
-    cudaEvent_t run_a = nullptr, run_b = nullptr;
+    cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
 };
+// wait for the context's stream.  PB200_BLOCKING_SYNC=1 (environment, read at pb200_create) makes the host thread sleep on
+// a blocking-sync event instead of spinning: for boxes with fewer cores than (ranks x lanes) host threads
+static cudaError_t ctx_sync(pb200_ctx* ctx) {
+    if (!ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_ev);
+}
 static int buf_ensure(pb200_ctx* ctx, DevBuf& b, size_t bytes) {
     b.used = 0;
     if (bytes <= b.cap) return 0;
@@ -288,7 +295,7 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
 #define PB_FETCH(dst, src, bytes)                                                                \
     do {                                                                                         \
         CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream));         \
-        CK(cudaStreamSynchronize(ctx->stream));                                                  \
+        CK(ctx_sync(ctx));                                                  \
     } while (0)
 #define PB_RUN(stage, n)                                                                         \
     do {                                                                                         \
@@ -394,7 +401,7 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
 #define PB_TO_HOST(dst, src, bytes)                                                              \
     do {                                                                                         \
         CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream));         \
-        CK(cudaStreamSynchronize(ctx->stream));                                                  \
+        CK(ctx_sync(ctx));                                                  \
     } while (0)
 
 #else
@@ -643,6 +650,10 @@ int pb200_create(int device, pb200_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreate(&ctx->stream2);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+    {
+        const char* bs = getenv("PB200_BLOCKING_SYNC");
+        if (e == cudaSuccess && bs && bs[0] == '1') e = cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventDisableTiming | cudaEventBlockingSync);
+    }
     if (e != cudaSuccess) {
         fprintf(stderr, "phanotate_b200: no usable CUDA device %d: %s\n", device, cudaGetErrorString(e));
         delete ctx;
@@ -669,6 +680,7 @@ void pb200_destroy(pb200_ctx* ctx) {
     for (auto e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -713,7 +725,7 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     if (flags & PB200_INPUT_DEVICE) {
         i64 last;
         CK(cudaMemcpyAsync(&last, offsets + n_contigs, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx_sync(ctx));
         B.nb = last;
         B.seq = bases;
         B.coff = offsets;
@@ -761,7 +773,7 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     if (rc) return rc;
 #ifndef PB_HOSTSIM
     CK(cudaEventRecord(ctx->run_b, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx_sync(ctx));
 #endif
     ctx->have = true;
     return 0;
@@ -782,7 +794,7 @@ int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, i
     if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
     CK(cudaMemcpyAsync(ctx->in_seq.p, bases, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx_sync(ctx));
 #else
     const i64 nb = offsets[n_contigs];
     if (buf_ensure(ctx, ctx->in_seq, (size_t)nb + 64)) return -1;
@@ -960,7 +972,7 @@ int pb200_build_edges(pb200_ctx* ctx) {
     PB_RUN(st_edge_fill, B.nn);
     B.nedges = (i32)tot;
 #ifndef PB_HOSTSIM
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx_sync(ctx));
 #endif
     return 0;
 }
