@@ -731,7 +731,7 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
 // and the reference's parent of v is the tight in-edge with the smallest (pass, sigma(x)).  The tight in-edges of v are
 // the sweep's parent plus the recorded ties whose value is the final distance.  Only contigs with ties do any work.
 // (Checked against the oracle's edge-order Bellman-Ford: tests/test_certified.py, tests/tie_audit.py.)
-#define TIE_MAXN 32
+#define TIE_MAXN 256
 // insertion index of node a inside its family's run of the node order: forward family = nearest start, stop, then the
 // other starts by descending position; reverse family = stop-key node, then the starts by ascending position
 PB_HDN int tie_sigma_idx(const Batch& B, i32 a, i32 fam) {
