@@ -9,6 +9,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <algorithm>
 
 #include "../../include/phanotate_b200.h"
 #include "graph.cuh"
@@ -1083,10 +1085,16 @@ int pb200_connect(pb200_ctx* ctx, const int32_t* left, const int32_t* right, int
 
 // ---- host-side text ingest / output for whole batches (no device work, no context needed)
 static inline bool fa_blank(unsigned char ch) { return ch == ' ' || ch == '\t' || ch == '\r'; }
-int64_t pb200_fasta_count(const char* data, int64_t n) {
+static int host_threads(int64_t work_bytes, int64_t min_per_thread = 4 << 20) {
+    int t = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("PB200_HOST_THREADS")) t = atoi(e);
+    if (t > 32) t = 32;
+    const int64_t by_size = work_bytes / min_per_thread;
+    if (t > by_size) t = (int)by_size;
+    return t < 1 ? 1 : t;
+}
+static int64_t fa_count_range(const char* p, const char* end) {
     int64_t rec = 0;
-    const char* p = data;
-    const char* end = data + n;
     while (p < end) {
         if (*p == '>') rec++;
         const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
@@ -1095,25 +1103,45 @@ int64_t pb200_fasta_count(const char* data, int64_t n) {
     }
     return rec;
 }
-int64_t pb200_fasta_parse(const char* data, int64_t n, uint8_t* bases, int64_t* offsets, int64_t* name_begin,
-                          int64_t* name_end, int64_t max_records) {
-    int64_t rec = 0, nb = 0;
-    const char* p = data;
-    const char* end = data + n;
+int64_t pb200_fasta_count(const char* data, int64_t n) {
+    const int T = host_threads(n);
+    std::vector<const char*> cut(T + 1);
+    cut[0] = data;
+    cut[T] = data + n;
+    for (int t = 1; t < T; t++) {
+        const char* p = data + n / T * t;
+        if (p < cut[t - 1]) p = cut[t - 1];
+        const char* q = (const char*)memchr(p, '\n', (size_t)(data + n - p));
+        cut[t] = q ? q + 1 : data + n;
+    }
+    std::vector<int64_t> rec(T, 0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back([&, t] { rec[t] = fa_count_range(cut[t], cut[t + 1]); });
+    rec[0] = fa_count_range(cut[0], cut[1]);
+    for (auto& x : th) x.join();
+    int64_t r = 0;
+    for (int t = 0; t < T; t++) r += rec[t];
+    return r;
+}
+// one pass over the lines of [p, end): counts (bases == nullptr) or writes.  `rec` / `nb` = records and bases before p.
+static void fa_lines(const char* data, const char* p, const char* end, bool in_record, uint8_t* bases, int64_t* offsets,
+                     int64_t* name_begin, int64_t* name_end, int64_t& rec, int64_t& nb) {
     while (p < end) {
         const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
         const char* le = q ? q : end;                    // line = [p, le)
         if (*p == '>') {
-            if (rec >= max_records) return -1;
-            offsets[rec] = nb;
-            const char* a = p + 1;
-            while (a < le && fa_blank((unsigned char)*a)) a++;
-            const char* b = a;
-            while (b < le && !fa_blank((unsigned char)*b)) b++;
-            name_begin[rec] = a - data;
-            name_end[rec] = b - data;
+            if (bases) {
+                offsets[rec] = nb;
+                const char* a = p + 1;
+                while (a < le && fa_blank((unsigned char)*a)) a++;
+                const char* b = a;
+                while (b < le && !fa_blank((unsigned char)*b)) b++;
+                name_begin[rec] = a - data;
+                name_end[rec] = b - data;
+            }
             rec++;
-        } else if (rec > 0) {                            // text before the first header is ignored
+            in_record = true;
+        } else if (in_record) {                          // text before the first header is ignored
             const char* e2 = le;
             while (e2 > p && fa_blank((unsigned char)e2[-1])) e2--;          // CRLF / trailing blanks
             const char* a = p;
@@ -1121,41 +1149,141 @@ int64_t pb200_fasta_parse(const char* data, int64_t n, uint8_t* bases, int64_t* 
             const size_t len = (size_t)(e2 - a);
             if (len) {
                 if (!memchr(a, ' ', len) && !memchr(a, '\t', len) && !memchr(a, '\r', len)) {
-                    memcpy(bases + nb, a, len);
+                    if (bases) memcpy(bases + nb, a, len);
                     nb += (int64_t)len;
                 } else {
                     for (const char* c = a; c < e2; c++)
-                        if (!fa_blank((unsigned char)*c)) bases[nb++] = (uint8_t)*c;
+                        if (!fa_blank((unsigned char)*c)) {
+                            if (bases) bases[nb] = (uint8_t)*c;
+                            nb++;
+                        }
                 }
             }
         }
         if (!q) break;
         p = q + 1;
     }
-    offsets[rec] = nb;
-    return rec;
+}
+// The file is cut into one range of whole lines per host thread; a counting pass gives every range its first record
+// and first base, a writing pass fills the packed batch in place (two passes over memory-resident text).
+int64_t pb200_fasta_parse(const char* data, int64_t n, uint8_t* bases, int64_t* offsets, int64_t* name_begin,
+                          int64_t* name_end, int64_t max_records) {
+    const int T = host_threads(n);
+    std::vector<const char*> cut(T + 1);
+    cut[0] = data;
+    cut[T] = data + n;
+    for (int t = 1; t < T; t++) {
+        const char* p = data + n / T * t;
+        if (p < cut[t - 1]) p = cut[t - 1];
+        const char* q = (const char*)memchr(p, '\n', (size_t)(data + n - p));
+        cut[t] = q ? q + 1 : data + n;
+    }
+    std::vector<int64_t> rec(T + 1, 0), nb(T + 1, 0);
+    // a range continues a record iff any range before it saw a header: decided after the counting pass, so a range
+    // counts its header-less leading lines separately
+    std::vector<int64_t> lead(T, 0);
+    auto count = [&](int t) {
+        // leading lines before the range's first header belong to the previous record (if there is one)
+        const char* p = cut[t];
+        const char* end = cut[t + 1];
+        const char* h = p;
+        while (h < end && *h != '>') {
+            const char* q = (const char*)memchr(h, '\n', (size_t)(end - h));
+            if (!q) {
+                h = end;
+                break;
+            }
+            h = q + 1;
+        }
+        int64_t r0 = 0, b0 = 0;
+        fa_lines(data, p, h, true, nullptr, nullptr, nullptr, nullptr, r0, b0);
+        lead[t] = b0;
+        int64_t r1 = 0, b1 = 0;
+        fa_lines(data, h, end, false, nullptr, nullptr, nullptr, nullptr, r1, b1);
+        rec[t + 1] = r1;
+        nb[t + 1] = b1;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(count, t);
+        count(0);
+        for (auto& x : th) x.join();
+    }
+    // prefix: leading lines count only when a record is open
+    int64_t r = 0, b = 0;
+    std::vector<int64_t> rec0(T), nb0(T);
+    std::vector<char> open(T);
+    for (int t = 0; t < T; t++) {
+        rec0[t] = r;
+        nb0[t] = b;
+        open[t] = r > 0;
+        if (r > 0) b += lead[t];
+        r += rec[t + 1];
+        b += nb[t + 1];
+    }
+    if (r > max_records) return -1;
+    auto fill = [&](int t) {
+        int64_t rr = rec0[t], bb = nb0[t];
+        fa_lines(data, cut[t], cut[t + 1], open[t] != 0, bases, offsets, name_begin, name_end, rr, bb);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(fill, t);
+        fill(0);
+        for (auto& x : th) x.join();
+    }
+    offsets[r] = b;
+    return r;
 }
 // Locus.tabular (locus.py:39-56) for every contig of a batch: "#id:" / "#START..." header, then one row per call with
 // left/right swapped on the reverse strand and the score printed with %E.  Returns the bytes written or -(bytes needed).
+// Contig ranges are formatted by the host threads into the (upper-bound sized) output and then closed up.
 int64_t pb200_format_tabular(const pb200_call* calls, const pb200_contig* contigs, int32_t n_contigs, const char* names,
                              const int64_t* name_off, char* out, int64_t cap) {
-    int64_t need = 0;
+    std::vector<int64_t> at((size_t)n_contigs + 1, 0);
     for (int32_t k = 0; k < n_contigs; k++)
-        need += 48 + (name_off[k + 1] - name_off[k]) + (int64_t)contigs[k].n_calls * (64 + (name_off[k + 1] - name_off[k]));
+        at[k + 1] = at[k] + 48 + (name_off[k + 1] - name_off[k]) +
+                    (int64_t)contigs[k].n_calls * (64 + (name_off[k + 1] - name_off[k]));
+    const int64_t need = at[n_contigs];
     if (need > cap) return -need;
-    char* w = out;
-    for (int32_t k = 0; k < n_contigs; k++) {
-        const char* nm = names + name_off[k];
-        const int nl = (int)(name_off[k + 1] - name_off[k]);
-        w += sprintf(w, "#id:\t%.*s\n#START\tSTOP\tFRAME\tCONTIG\tSCORE\n", nl, nm);
-        const pb200_call* c = calls + contigs[k].call_off;
-        for (int32_t i = 0; i < contigs[k].n_calls; i++) {
-            const int fwd = c[i].strand > 0;
-            w += sprintf(w, "%d\t%d\t%c\t%.*s\t%E\n", fwd ? c[i].left : c[i].right, fwd ? c[i].right : c[i].left,
-                         fwd ? '+' : '-', nl, nm, c[i].score);
-        }
+    const int T = host_threads(need, 64 << 10);          // (formatting costs ~30 ns per byte: small pieces pay)
+    std::vector<int32_t> cut(T + 1, n_contigs);
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+        const int64_t want = need / T * t;
+        cut[t] = (int32_t)(std::lower_bound(at.begin(), at.end(), want) - at.begin());
+        if (cut[t] > n_contigs) cut[t] = n_contigs;
+        if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
-    return (int64_t)(w - out);
+    std::vector<int64_t> len(T, 0);
+    auto fmt = [&](int t) {
+        char* w = out + at[cut[t]];
+        char* const w0 = w;
+        for (int32_t k = cut[t]; k < cut[t + 1]; k++) {
+            const char* nm = names + name_off[k];
+            const int nl = (int)(name_off[k + 1] - name_off[k]);
+            w += sprintf(w, "#id:\t%.*s\n#START\tSTOP\tFRAME\tCONTIG\tSCORE\n", nl, nm);
+            const pb200_call* c = calls + contigs[k].call_off;
+            for (int32_t i = 0; i < contigs[k].n_calls; i++) {
+                const int fwd = c[i].strand > 0;
+                w += sprintf(w, "%d\t%d\t%c\t%.*s\t%E\n", fwd ? c[i].left : c[i].right, fwd ? c[i].right : c[i].left,
+                             fwd ? '+' : '-', nl, nm, c[i].score);
+            }
+        }
+        len[t] = w - w0;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(fmt, t);
+        fmt(0);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = len[0];
+    for (int t = 1; t < T; t++) {                        // close the gaps between the threads' blocks
+        memmove(out + total, out + at[cut[t]], (size_t)len[t]);
+        total += len[t];
+    }
+    return total;
 }
 
 int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap) {

@@ -5,6 +5,8 @@ from __future__ import annotations
 
 import ctypes
 import gzip
+import mmap
+import os
 
 import numpy as np
 
@@ -28,18 +30,24 @@ def read_fasta_packed(path, lib=None):
     (the library lower-cases like functions.py:144)."""
     lib = _library(lib)
     with open(path, "rb") as fh:
-        data = fh.read()
-    if str(path).endswith(".gz") or data[:2] == b"\x1f\x8b":
-        data = gzip.decompress(data)
+        head = fh.read(2)
+        if str(path).endswith(".gz") or head == b"\x1f\x8b":
+            fh.seek(0)
+            data = np.frombuffer(gzip.decompress(fh.read()), dtype=np.uint8)
+        else:
+            size = os.fstat(fh.fileno()).st_size
+            # the text is only read (twice, by the library's host threads): map the file instead of copying it
+            data = np.frombuffer(mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ), dtype=np.uint8) if size else np.zeros(0, np.uint8)
     n = len(data)
-    nrec = int(lib.pb200_fasta_count(data, n))
+    ptr = data.ctypes.data if n else None
+    nrec = int(lib.pb200_fasta_count(ptr, n))
     bases = np.empty(max(n, 1), dtype=np.uint8)
     offsets = np.zeros(nrec + 1, dtype=np.int64)
     nb, ne = np.zeros(max(nrec, 1), dtype=np.int64), np.zeros(max(nrec, 1), dtype=np.int64)
-    got = int(lib.pb200_fasta_parse(data, n, bases.ctypes.data, offsets.ctypes.data, nb.ctypes.data, ne.ctypes.data, nrec))
+    got = int(lib.pb200_fasta_parse(ptr, n, bases.ctypes.data, offsets.ctypes.data, nb.ctypes.data, ne.ctypes.data, nrec))
     if got != nrec:
         raise RuntimeError("FASTA parse failed")
-    names = [data[a:b].decode() for a, b in zip(nb[:nrec].tolist(), ne[:nrec].tolist())]
+    names = [data[a:b].tobytes().decode() for a, b in zip(nb[:nrec].tolist(), ne[:nrec].tolist())]
     return names, bases[:int(offsets[-1])], offsets
 
 
