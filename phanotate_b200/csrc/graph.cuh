@@ -556,13 +556,19 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
 // picks the node u to visit, its record arrives by shuffles, and the lanes behind it already hold the packed word and
 // the current distance of u's gap / reverse-ORF targets: a visit is one or two memory round trips deep instead of four.
 // Targets beyond the 32-node window (dense stretches, long reverse families) take the loops of the plain statement.
-__device__ __forceinline__ I128 shfl128(const I128& a, int src) {
+template <int NL>
+__device__ __forceinline__ I128 shfl128(unsigned mask, const I128& a, int src) {
     I128 r;
-    r.lo = (u64)__shfl_sync(0xFFFFFFFFu, (unsigned long long)a.lo, src);
-    r.hi = (i64)__shfl_sync(0xFFFFFFFFu, (long long)a.hi, src);
+    r.lo = (u64)__shfl_sync(mask, (unsigned long long)a.lo, src, NL);
+    r.hi = (i64)__shfl_sync(mask, (long long)a.hi, src, NL);
     return r;
 }
-__device__ void solve_contig_win(const Batch& B, int c, int lane) {
+// NL = lanes per contig (32: a warp; 16: two contigs share a warp, each half with its own control flow -- twice the
+// contigs in flight per SM at the same register cost, which is what a latency-bound sweep wants); lane = 0..NL-1,
+// mask = the lanes of this contig inside the warp.
+template <int NL>
+__device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask) {
+    const int lane0 = __ffs((int)mask) - 1;       // position of lane 0 of this group inside the warp
     typedef D128 D;
     typedef I128 T;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
@@ -572,7 +578,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
     const u32* pk = B.n_pk;
     u32 ties = 0;
     bool okw = true;
-    for (i32 i = nb + lane; i < ne; i += 32) {
+    for (i32 i = nb + lane; i < ne; i += NL) {
         const u32 w = pk[i];
         T d0 = D::inf();
         i32 p0 = -1;
@@ -590,7 +596,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
     }
     T tdist = D::inf();
     i32 tpar = -1;
-    __syncwarp();
+    __syncwarp(mask);
     const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
     i32 i = nb;
     int budget = 64 * (ne - nb) + 1024;
@@ -610,9 +616,9 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
             oj = B.n_orf[j0];
             cj = B.ov_cnt[j0];
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, dj != 0);
+        const unsigned m = (__ballot_sync(mask, dj != 0) >> lane0) & (NL == 32 ? 0xFFFFFFFFu : ((1u << (NL & 31)) - 1u));
         if (!m) {
-            i += 32;
+            i += NL;
             continue;
         }
         if (--budget < 0) {
@@ -621,9 +627,9 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
         }
         const int f = __ffs((int)m) - 1;
         const i32 u = i + f;
-        const u32 wu = __shfl_sync(0xFFFFFFFFu, wj, f);
-        const T Du = shfl128(Tj, f);
-        const i32 mate_u = __shfl_sync(0xFFFFFFFFu, mj, f), orf_u = __shfl_sync(0xFFFFFFFFu, oj, f);
+        const u32 wu = __shfl_sync(mask, wj, f, NL);
+        const T Du = shfl128<NL>(mask, Tj, f);
+        const i32 mate_u = __shfl_sync(mask, mj, f, NL), orf_u = __shfl_sync(mask, oj, f, NL);
         const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
         if (lane == 0) B.dirty[u] = 0;
         i32 rewind = 0x7FFFFFFF;
@@ -637,7 +643,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
             // the starts of this reverse family: nodes up to its farthest start (n_mate of the stop-key node)
             if (behind && j0 <= mate_u && (int)(wj & 3) == K_RSTART && mj == u)
                 relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::load_w(B.o_wint + oj)), u);
-            for (i32 j = i + 32 + lane; j <= mate_u; j += 32) {
+            for (i32 j = i + NL + lane; j <= mate_u; j += NL) {
                 const u32 w2 = pk[j];
                 const i32 m2 = B.n_mate[j];
                 if ((int)(w2 & 3) == K_RSTART && m2 == u) {
@@ -647,9 +653,9 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
                 }
             }
         } else {
-            const u32 ovb = __shfl_sync(0xFFFFFFFFu, cj, f);
-            u32 ove = __shfl_sync(0xFFFFFFFFu, cj, (f + 1) & 31);
-            if (f == 31 || u + 1 >= ne) ove = B.ov_cnt[u + 1];
+            const u32 ovb = __shfl_sync(mask, cj, f, NL);
+            u32 ove = __shfl_sync(mask, cj, (f + 1) & (NL - 1), NL);
+            if (f == NL - 1 || u + 1 >= ne) ove = B.ov_cnt[u + 1];
             // gap edges to entries within 500 bp downstream (functions.py:360-438)
             {
                 const int kj = (int)(wj & 3), d = (int)(wj >> 4) - pu;
@@ -659,9 +665,9 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
                     relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
                 }
             }
-            const u32 wlast = __shfl_sync(0xFFFFFFFFu, wj, 31);
-            if (i + 32 < ne && (int)(wlast >> 4) - pu < 500) {
-                for (i32 j = i + 32 + lane; j < ne; j += 32) {
+            const u32 wlast = __shfl_sync(mask, wj, NL - 1, NL);
+            if (i + NL < ne && (int)(wlast >> 4) - pu < 500) {
+                for (i32 j = i + NL + lane; j < ne; j += NL) {
                     const u32 w2 = pk[j];
                     const T cur = dist[j];
                     const int kj = (int)(w2 & 3), d = (int)(w2 >> 4) - pu;
@@ -675,17 +681,17 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
             }
             // overlap edges (backwards)
             if (ove > ovb) {
-                for (u32 k = ovb + lane; k < ove; k += 32) {
+                for (u32 k = ovb + lane; k < ove; k += NL) {
                     const i64 w64 = B.ov_w64[k];
                     const i32 v = B.ov_dst[k];
                     const T cur = dist[v];
                     const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
                     if (relax<D>(B, ties, dist, v, cur, cand, u) && v < rewind) rewind = v;
                 }
-                rewind = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)rewind);
+                rewind = (i32)__reduce_min_sync(mask, (unsigned)rewind);
             }
             // bridges
-            for (u32 k = brb + lane; k < bre; k += 32) {
+            for (u32 k = brb + lane; k < bre; k += NL) {
                 if (B.br_src[k] != u) continue;
                 const i32 v = B.br_dst[k];
                 const T cur = dist[v];
@@ -705,7 +711,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane) {
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(mask);
         i = (rewind < u) ? rewind : u + 1;
     }
     if (ties) atomicAdd(&cs->n_ties, ties);

@@ -89,14 +89,16 @@ PB_KERNEL(st_edge_fill)
 #include "scan_tile.cuh"
 // one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
 // dependent memory round trips per contig: throughput comes from the number of contigs in flight)
+template <int NL>
 __global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
-    const int lane = threadIdx.x & 31;
-    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    for (i64 c = warp; c < nc; c += nwarps)
+    const int lane = threadIdx.x & (NL - 1);
+    const unsigned mask = NL == 32 ? 0xFFFFFFFFu : (((1u << (NL & 31)) - 1u) << ((threadIdx.x & 31) - lane));
+    const i64 group = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / NL;
+    const i64 ngroups = ((i64)gridDim.x * blockDim.x) / NL;
+    for (i64 c = group; c < nc; c += ngroups)
         if (!contig_is_wide(B, (int)c)) {
-            if (B.flags & PB200_SOLVE_PLAIN) solve_contig_t<D128>(B, (int)c, lane, 32);
-            else solve_contig_win(B, (int)c, lane);
+            if (NL == 32 && (B.flags & PB200_SOLVE_PLAIN)) solve_contig_t<D128>(B, (int)c, lane, 32);
+            else solve_contig_win<NL>(B, (int)c, lane, mask);
         }
 }
 __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) {
@@ -356,7 +358,13 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
         k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
         cudaEventRecord(ctx->join_ev, ctx->stream2);                                             \
-        k_solve<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
+        /* PB200_SOLVE_HALF=1 (environment): two contigs per warp, 16 lanes each -- twice the sweeps in flight at the   \
+           same register cost.  Measured SLOWER on the bench workload (7.6 against 6.8 ms: the two halves' divergent    \
+           control flow costs more issue slots than the extra latency hiding returns), so it is opt-in */              \
+        if (!(B.flags & PB200_SOLVE_PLAIN) && getenv("PB200_SOLVE_HALF"))                                            \
+            k_solve<16><<<grid_for(ctx, (i64)(nc_) * 16, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_));             \
+        else                                                                                                         \
+            k_solve<32><<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_));             \
         cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0);                                       \
         ctx->launches++;                                                                         \
         cudaEventRecord(t_.b, ctx->stream);                                                      \

@@ -182,8 +182,16 @@ def test_three_thousand_bench_contigs_match_the_oracle_digest(eng):
     g = json.load(open(os.path.join(GOLDEN, "synth4_calls_digest.json")))
     n = len(g["md5_16"])
     bases, offs = synth.synth4_batch(n, 50000)
-    for flags in (0, N.SOLVE_PLAIN):
-        res = eng.run_packed(bases, offs, flags=flags)
+    import os
+    for flags, half in ((0, False), (N.SOLVE_PLAIN, False), (0, True)):
+        # half: two contigs per warp (the kernel large batches take), forced here through the environment
+        os.environ.pop("PB200_SOLVE_HALF", None)
+        if half:
+            os.environ["PB200_SOLVE_HALF"] = "1"
+        try:
+            res = eng.run_packed(bases, offs, flags=flags)
+        finally:
+            os.environ.pop("PB200_SOLVE_HALF", None)
         assert int((res.contigs["err"] != 0).sum()) == 0
         assert [int(v) for v in res.contigs["n_calls"]] == g["n_calls"]
         bad = []
@@ -191,4 +199,4 @@ def test_three_thousand_bench_contigs_match_the_oracle_digest(eng):
             text = "".join("%d\t%d\t%s\t%s\n" % r for r in res.call_rows(k))
             if hashlib.md5(text.encode()).hexdigest()[:16] != g["md5_16"][k]:
                 bad.append(k)
-        assert bad == [], (flags, bad[:10])
+        assert bad == [], (flags, half, bad[:10])
