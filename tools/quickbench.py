@@ -1,3 +1,4 @@
+"""Small-batch timing probe (16 / 256 / 1024 contigs) for the GPU box."""
 import sys, time, json
 sys.path.insert(0,'.')
 import numpy as np
