@@ -277,24 +277,18 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     }
                 }
                 const u64 c_lo = *(const u64*)(S.code + pb), c_hi = *(const u64*)(S.code + pb + 8);
-                u32 e2[22], s2[22];                   // e2[x] = em[x] | em[x+1]
+                // forward strand first, reverse strand in a second pass over the 8 bases: only one set of 22 motif-mask
+                // words is live at a time (the kernel runs at its 64-register cap)
+                u32 e2[22];                           // e2[x] = em[x] | em[x+1]
                 {
                     const uint4 ea = *(const uint4*)(S.em + pb), eb = *(const uint4*)(S.em + pb + 8), ec = *(const uint4*)(S.em + pb + 16);
-                    const uint4 sa = *(const uint4*)(S.sm + pb), sb = *(const uint4*)(S.sm + pb + 8), sc = *(const uint4*)(S.sm + pb + 16);
                     const u32 ew[12] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w};
-                    const u32 sw[12] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y, sc.z, sc.w};
-                    u32 ee[24], ss[24];
+                    u32 ee[24];
 #pragma unroll
-                    for (int x = 0; x < 24; x++) {
-                        ee[x] = (x & 1) ? (ew[x >> 1] >> 16) : (ew[x >> 1] & 0xFFFFu);
-                        ss[x] = (x & 1) ? (sw[x >> 1] >> 16) : (sw[x >> 1] & 0xFFFFu);
-                    }
+                    for (int x = 0; x < 24; x++) ee[x] = (x & 1) ? (ew[x >> 1] >> 16) : (ew[x >> 1] & 0xFFFFu);
 #pragma unroll
-                    for (int x = 0; x < 22; x++) {
-                        e2[x] = ee[x] | ee[x + 1];
-                        s2[x] = ss[x] | ss[x + 1];
-                    }
-                    // groups of three: em[k]|em[k+1]|em[k+2] = e2[k] | e2[k+1]; sm[k+13..15] = s2[k+13] | s2[k+14]
+                    for (int x = 0; x < 22; x++) e2[x] = ee[x] | ee[x + 1];
+                    // groups of three: em[k]|em[k+1]|em[k+2] = e2[k] | e2[k+1]
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -315,16 +309,7 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     acc_cd |= 1ull << (cd0 * 8 + k);
                     acc_kf |= 1ull << (kf * 8 + k);
                     acc_kr |= 1ull << (kr * 8 + k);
-                    int sf, sr;
-                    {
-                        // reverse strand, score_rbs(rev_comp(dna[i:i+21])): motifs start at window offsets 5..10 (gm),
-                        // 3..4 (gl), 11..12 (gh), 13..15 (gf); a truncated window only cuts motifs at the contig end
-                        const u32 rm = s2[k + 5] | s2[k + 7] | s2[k + 9], rl = s2[k + 3], rh = s2[k + 11], rf = s2[k + 13] | s2[k + 14];
-                        const int a = S.gt4[0][rm], b = S.gt4[1][rl], cc = S.gt4[2][rh], d = S.gt4[3][rf];
-                        sr = a > b ? a : b;
-                        sr = cc > sr ? cc : sr;
-                        sr = d > sr ? d : sr;
-                    }
+                    int sf;
                     const int i = (int)(g - cb);
                     if (i + 21 <= L) {
                         // forward strand, score_rbs(dna[i:i+21]): 6-mers at window offsets 5..10 (gm), 11..12 (gl), 3..4 (gh), 0..2 (gf)
@@ -349,8 +334,31 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                         sf = d > sf ? d : sf;
                     }
                     if (sf) S.hpriv[sf][tid]++;
-                    if (sr) S.hpriv[sr][tid]++;
                     acc_sf |= (u64)sf << (8 * k);
+                }
+                u32 s2[22];                           // s2[x] = sm[x] | sm[x+1]
+                {
+                    const uint4 sa = *(const uint4*)(S.sm + pb), sb = *(const uint4*)(S.sm + pb + 8), sc = *(const uint4*)(S.sm + pb + 16);
+                    const u32 sw[12] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y, sc.z, sc.w};
+                    u32 ss[24];
+#pragma unroll
+                    for (int x = 0; x < 24; x++) ss[x] = (x & 1) ? (sw[x >> 1] >> 16) : (sw[x >> 1] & 0xFFFFu);
+#pragma unroll
+                    for (int x = 0; x < 22; x++) s2[x] = ss[x] | ss[x + 1];
+                    // sm[k+13..15] = s2[k+13] | s2[k+14]
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const i64 g = gb + k;
+                    if (g < seg_lo || g >= seg_hi) continue;
+                    // reverse strand, score_rbs(rev_comp(dna[i:i+21])): motifs start at window offsets 5..10 (gm),
+                    // 3..4 (gl), 11..12 (gh), 13..15 (gf); a truncated window only cuts motifs at the contig end
+                    const u32 rm = s2[k + 5] | s2[k + 7] | s2[k + 9], rl = s2[k + 3], rh = s2[k + 11], rf = s2[k + 13] | s2[k + 14];
+                    const int a = S.gt4[0][rm], b = S.gt4[1][rl], cc = S.gt4[2][rh], d = S.gt4[3][rf];
+                    int sr = a > b ? a : b;
+                    sr = cc > sr ? cc : sr;
+                    sr = d > sr ? d : sr;
+                    if (sr) S.hpriv[sr][tid]++;
                     acc_sr |= (u64)sr << (8 * k);
                 }
             }
