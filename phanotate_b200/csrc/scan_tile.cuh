@@ -277,19 +277,9 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     }
                 }
                 const u64 c_lo = *(const u64*)(S.code + pb), c_hi = *(const u64*)(S.code + pb + 8);
-                // forward strand first, reverse strand in a second pass over the 8 bases: only one set of 22 motif-mask
-                // words is live at a time (the kernel runs at its 64-register cap)
-                u32 e2[22];                           // e2[x] = em[x] | em[x+1]
-                {
-                    const uint4 ea = *(const uint4*)(S.em + pb), eb = *(const uint4*)(S.em + pb + 8), ec = *(const uint4*)(S.em + pb + 16);
-                    const u32 ew[12] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w};
-                    u32 ee[24];
-#pragma unroll
-                    for (int x = 0; x < 24; x++) ee[x] = (x & 1) ? (ew[x >> 1] >> 16) : (ew[x >> 1] & 0xFFFFu);
-#pragma unroll
-                    for (int x = 0; x < 22; x++) e2[x] = ee[x] | ee[x + 1];
-                    // groups of three: em[k]|em[k+1]|em[k+2] = e2[k] | e2[k+1]
-                }
+                // three passes over the thread's 8 bases -- codon / GC-frame classes, forward RBS score, reverse RBS score -- so
+                // that the window sums, the forward and the reverse motif-mask words are never live together (the kernel
+                // runs at its 64-register cap)
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const i64 g = gb + k;
@@ -309,6 +299,22 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     acc_cd |= 1ull << (cd0 * 8 + k);
                     acc_kf |= 1ull << (kf * 8 + k);
                     acc_kr |= 1ull << (kr * 8 + k);
+                }
+                u32 e2[22];                           // e2[x] = em[x] | em[x+1]
+                {
+                    const uint4 ea = *(const uint4*)(S.em + pb), eb = *(const uint4*)(S.em + pb + 8), ec = *(const uint4*)(S.em + pb + 16);
+                    const u32 ew[12] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w, ec.x, ec.y, ec.z, ec.w};
+                    u32 ee[24];
+#pragma unroll
+                    for (int x = 0; x < 24; x++) ee[x] = (x & 1) ? (ew[x >> 1] >> 16) : (ew[x >> 1] & 0xFFFFu);
+#pragma unroll
+                    for (int x = 0; x < 22; x++) e2[x] = ee[x] | ee[x + 1];
+                    // groups of three: em[k]|em[k+1]|em[k+2] = e2[k] | e2[k+1]
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const i64 g = gb + k;
+                    if (g < seg_lo || g >= seg_hi) continue;
                     int sf;
                     const int i = (int)(g - cb);
                     if (i + 21 <= L) {
