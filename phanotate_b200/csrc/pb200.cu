@@ -331,15 +331,18 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             const i64 slots_ = (i64)ctx->sm_count * 4 * 12;                                      \
             const int tpb_ = (int)((ntiles_ + slots_ - 1) / slots_);                             \
             if (!ctx->scan_attr_set) {                                                           \
-                cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)); \
-                cudaFuncSetAttribute(k_scan_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+                cudaFuncSetAttribute(k_scan_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)); \
+                cudaFuncSetAttribute(k_scan_tiles<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+                cudaFuncSetAttribute(k_scan_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)); \
+                cudaFuncSetAttribute(k_scan_tiles<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
                 ctx->scan_attr_set = true;                                                       \
             }                                                                                    \
             /* bulk TMA copies need a 16-byte aligned source with slack behind the last base: the library's own  \
                input buffer has both, a caller-owned device buffer (PB200_INPUT_DEVICE) takes the plain loads */ \
             const int tma_ = (!(B.flags & PB200_INPUT_DEVICE) && (((size_t)B.seq) & 15) == 0) ? 1 : 0; \
             cudaEventRecord(t_.a, ctx->stream);                                                  \
-            k_scan_tiles<<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, sizeof(ScanSmem), ctx->stream>>>(B, ntiles_, tpb_, tma_); \
+            if (tma_) k_scan_tiles<true><<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, sizeof(ScanSmem), ctx->stream>>>(B, ntiles_, tpb_); \
+            else k_scan_tiles<false><<<(int)((ntiles_ + tpb_ - 1) / tpb_), ST_NT, sizeof(ScanSmem), ctx->stream>>>(B, ntiles_, tpb_); \
             cudaEventRecord(t_.b, ctx->stream);                                                  \
             ctx->times.push_back(t_);                                                            \
             ctx->launches++;                                                                     \

@@ -115,7 +115,11 @@ __device__ __forceinline__ uint4 scan_load_chunk(const Batch& B, i64 tg0, int ti
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block, int use_tma) {
+// use_tma: the letters arrive by bulk TMA copies (the library's own input buffer) or by plain 16-byte loads (a
+// caller-owned device buffer without alignment / padding guarantees); a template parameter, so that the path not taken
+// costs no registers
+template <bool use_tma>
+__global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntiles, int tiles_per_block) {
     extern __shared__ __align__(16) unsigned char scan_smem_raw[];
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(scan_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
