@@ -200,3 +200,31 @@ def test_three_thousand_bench_contigs_match_the_oracle_digest(eng):
             if hashlib.md5(text.encode()).hexdigest()[:16] != g["md5_16"][k]:
                 bad.append(k)
         assert bad == [], (flags, half, bad[:10])
+
+
+def test_caller_owned_device_buffers(eng):
+    """PB200_INPUT_DEVICE: letters and offsets already in device memory (the scan then takes plain loads instead of bulk
+    TMA copies).  A 16-byte aligned buffer and one shifted by 3 bytes give the calls of the host-buffer run."""
+    import ctypes
+    import torch
+    from phanotate_b200.engine import Result, make_params
+    names = ["phiX174", "lambda", "stress2", "stress19", "synth4_0", "stress12", "T4"]
+    seqs = [seq_of(n).encode() for n in names]
+    want = eng.run(seqs)
+    want_rows = [want.call_rows(k) for k in range(len(seqs))]
+    want_hist = want.contigs["background_rbs"].copy()
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    flat = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    params = make_params()
+    d_off = torch.from_numpy(offs).cuda()
+    for shift in (0, 3):
+        d_buf = torch.zeros(len(flat) + 64, dtype=torch.uint8, device="cuda")
+        d_buf[shift:shift + len(flat)] = torch.from_numpy(flat.copy()).cuda()
+        torch.cuda.synchronize()
+        eng._ck(eng.lib.pb200_run(eng.ctx, ctypes.c_void_p(d_buf.data_ptr() + shift), ctypes.c_void_p(d_off.data_ptr()),
+                                  len(seqs), params.ctypes.data, N.INPUT_DEVICE))
+        got = Result(eng)
+        assert [got.call_rows(k) for k in range(len(seqs))] == want_rows, shift
+        assert np.array_equal(got.contigs["background_rbs"], want_hist), shift
+        assert int((got.contigs["err"] != 0).sum()) == 0
