@@ -9,7 +9,7 @@ rows = [r for r in csv.reader(open(G + tag + "_launches.csv")) if len(r) > 10]
 h = rows[0]; iK, iV = h.index('Kernel Name'), h.index('Metric Value')
 agg = collections.OrderedDict()
 for r in rows[1:]:
-    a = agg.setdefault(r[iK].split('(')[0], [0, 0.0]); a[0] += 1; a[1] += float(r[iV].replace(',', ''))
+    a = agg.setdefault(r[iK].split('(')[0].replace("void ", ""), [0, 0.0]); a[0] += 1; a[1] += float(r[iV].replace(',', ''))
 tot = sum(v[1] for v in agg.values())
 with open(P + tag + "_launch_summary.csv", "w") as fh:
     fh.write("kernel,launches,total_ms,avg_ms,share_of_gpu_time\n")
@@ -30,7 +30,7 @@ with open(P + tag + "_ncu_full_top_kernels.csv", "w") as fh:
     w.writerow(["unit"] + [uu[hh.index(k)] for k in keep])
     for r in rr[2:]:
         d = dict(zip(hh, r))
-        name = d["Kernel Name"].split("(")[0]
+        name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]      # k_solve<32> -> k_solve
         w.writerow([name] + [d[k] for k in keep])
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
         rd = float(d["dram__bytes_read.sum"]) * scale[uu[hh.index("dram__bytes_read.sum")]]
