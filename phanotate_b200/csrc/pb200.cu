@@ -108,6 +108,30 @@ __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) 
     for (i64 c = warp; c < nc; c += nwarps)
         if (contig_is_wide(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
 }
+// Overlap enumeration (st_ov_count / st_ov_fill) with the exit nodes compacted inside the warp: only exit nodes have
+// work, and they are about every second node, so a warp takes 64 consecutive nodes and hands the k-th exit node among them
+// to lane k (ballots + find-nth-set-bit) instead of leaving half of its lanes idle.
+template <bool FILL>
+__global__ void __launch_bounds__(PB_BLOCK) k_ov_exits(const Batch B) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 base = warp * 64; base < B.nn; base += nwarps * 64) {
+        const i64 n0 = base + lane, n1 = base + 32 + lane;
+        const bool x0 = n0 < B.nn && !kind_is_entry((int)(B.n_pk[n0] & 3));
+        const bool x1 = n1 < B.nn && !kind_is_entry((int)(B.n_pk[n1] & 3));
+        if (!FILL) {                                   // entry nodes have no overlap edges
+            if (n0 < B.nn && !x0) B.ov_cnt[n0] = 0;
+            if (n1 < B.nn && !x1) B.ov_cnt[n1] = 0;
+        }
+        const unsigned m0 = __ballot_sync(0xFFFFFFFFu, x0), m1 = __ballot_sync(0xFFFFFFFFu, x1);
+        const int c0 = __popc(m0), total = c0 + __popc(m1);
+        for (int k = lane; k < total; k += 32) {
+            const int bit = k < c0 ? (int)__fns(m0, 0, k + 1) : 32 + (int)__fns(m1, 0, k - c0 + 1);
+            overlaps_of(B, (i32)(base + bit), FILL);
+        }
+    }
+}
 // per-codon product + Orf.score, ORFs in length-sorted order; each thread keeps its six prepared
 // factors in shared memory (18 x 16 B, stride = block size: conflict-free 128-bit loads)
 __global__ void __launch_bounds__(PB_BLOCK) k_hold(const Batch B) {
@@ -375,6 +399,22 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         ctx->launches++;                                                                         \
         CK(cudaGetLastError());                                                                  \
     } while (0)
+#define PB_RUN_OV(fill_)                                                                         \
+    do {                                                                                         \
+        if (B.nn > 0) {                                                                          \
+            StageTime t_;                                                                        \
+            t_.name = (fill_) ? "st_ov_fill" : "st_ov_count";                                    \
+            t_.a = ev_get(ctx);                                                                  \
+            t_.b = ev_get(ctx);                                                                  \
+            cudaEventRecord(t_.a, ctx->stream);                                                  \
+            if (fill_) k_ov_exits<true><<<grid_for(ctx, ((i64)B.nn + 1) / 2, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B);  \
+            else k_ov_exits<false><<<grid_for(ctx, ((i64)B.nn + 1) / 2, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B);       \
+            cudaEventRecord(t_.b, ctx->stream);                                                  \
+            ctx->times.push_back(t_);                                                            \
+            ctx->launches++;                                                                     \
+            CK(cudaGetLastError());                                                              \
+        }                                                                                        \
+    } while (0)
 #define PB_RUN_REACH(nc_)                                                                        \
     do {                                                                                         \
         StageTime t_;                                                                            \
@@ -480,6 +520,11 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
     do {                                                               \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
         ctx->launches++;                                               \
+    } while (0)
+#define PB_RUN_OV(fill_)                                 \
+    do {                                                 \
+        if (fill_) PB_RUN(st_ov_fill, B.nn);             \
+        else PB_RUN(st_ov_count, B.nn);                  \
     } while (0)
 #define PB_RUN_REACH(nc_)                                                  \
     do {                                                                   \
