@@ -246,10 +246,10 @@ struct StageTime {
 struct pb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, side_ev = nullptr;
     std::string err;
     DevBuf ph[NPHASE];
-    DevBuf in_seq, in_off, scratch, conn, conn_out;
+    DevBuf in_seq, in_off, scratch, scratch2, conn, conn_out;
     Batch B;
     bool have = false;
     std::vector<StageTime> times;
@@ -399,6 +399,22 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         ctx->launches++;                                                                         \
         CK(cudaGetLastError());                                                                  \
     } while (0)
+// A run of stages that nothing on the main stream needs for a while goes to the second stream (with its own scan
+// scratch): BEGIN forks, END hands the main stream back, JOIN makes the main stream wait for the side work.
+#define PB_SIDE_BEGIN()                                                  \
+    do {                                                                 \
+        cudaEventRecord(ctx->fork_ev, ctx->stream);                      \
+        cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);              \
+        std::swap(ctx->stream, ctx->stream2);                            \
+        std::swap(ctx->scratch, ctx->scratch2);                          \
+    } while (0)
+#define PB_SIDE_END()                                                    \
+    do {                                                                 \
+        cudaEventRecord(ctx->side_ev, ctx->stream);                      \
+        std::swap(ctx->stream, ctx->stream2);                            \
+        std::swap(ctx->scratch, ctx->scratch2);                          \
+    } while (0)
+#define PB_SIDE_JOIN() cudaStreamWaitEvent(ctx->stream, ctx->side_ev, 0)
 #define PB_RUN_OV(fill_)                                                                         \
     do {                                                                                         \
         if (B.nn > 0) {                                                                          \
@@ -521,6 +537,9 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
         ctx->launches++;                                               \
     } while (0)
+#define PB_SIDE_BEGIN()
+#define PB_SIDE_END()
+#define PB_SIDE_JOIN()
 #define PB_RUN_OV(fill_)                                 \
     do {                                                 \
         if (fill_) PB_RUN(st_ov_fill, B.nn);             \
@@ -708,6 +727,7 @@ int pb200_create(int device, pb200_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreate(&ctx->stream2);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming);
     {
         const char* bs = getenv("PB200_BLOCKING_SYNC");
         if (e == cudaSuccess && bs && bs[0] == '1') e = cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventDisableTiming | cudaEventBlockingSync);
@@ -733,12 +753,14 @@ void pb200_destroy(pb200_ctx* ctx) {
     cudaFree(ctx->in_seq.p);
     cudaFree(ctx->in_off.p);
     cudaFree(ctx->scratch.p);
+    cudaFree(ctx->scratch2.p);
     cudaFree(ctx->conn.p);
     cudaFree(ctx->conn_out.p);
     for (auto e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
