@@ -228,3 +228,34 @@ def test_caller_owned_device_buffers(eng):
         assert [got.call_rows(k) for k in range(len(seqs))] == want_rows, shift
         assert np.array_equal(got.contigs["background_rbs"], want_hist), shift
         assert int((got.contigs["err"] != 0).sum()) == 0
+
+
+@pytest.mark.parametrize("lanes", [1, 3, 4, 7])
+def test_pipelined_engine_on_the_gpu_equals_one_context(eng, lanes):
+    """The end-to-end path of bench.py: several contexts / streams / host threads on one GPU, ordered uploads from pinned
+    host buffers, rows copied out lane by lane, contig numbering applied on the device.  Same tables as one batch in one
+    context -- for a ragged batch (tiny contigs, tie contigs, T4), for a second, smaller batch that reuses the pinned
+    output buffers, and with the batch left resident."""
+    from phanotate_b200.engine import PipelinedEngine
+    names = (["phiX174", "synth4_1055"] + STRESS[:20] + ["lambda", "synth4_1999"] + STRESS[20:40] +
+             ["T4", "synth4_0", "synth4_2006"] + STRESS[40:])
+    seqs = [seq_of(n).encode() for n in names]
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy()
+    want = eng.run_packed(bases, offs)
+    pe = PipelinedEngine(0, lanes=lanes)
+    try:
+        pe.pin(bases)
+        for rep in range(2):
+            got = pe.run_packed(bases, offs)
+            assert np.array_equal(got.calls, want.calls) and np.array_equal(got.contigs, want.contigs), rep
+        res = pe.run_packed(bases, offs, resident=True)
+        assert np.array_equal(res.calls, want.calls) and np.array_equal(res.contigs, want.contigs)
+        k = len(names) // 3
+        part = pe.run_packed(bases[:offs[k]], offs[:k + 1])
+        assert part.n_contigs == k and np.array_equal(part.calls, want.calls[:part.n_calls])
+        assert np.array_equal(part.contigs["n_calls"], want.contigs["n_calls"][:k])
+        pe.unpin(bases)
+    finally:
+        pe.close()
