@@ -788,10 +788,11 @@ PB_HDN int tie_chain_pass(const Batch& B, i32 x, const i32* tv, const bool* done
 //   node[0] = x, node[i+1] = parent(node[i]) (the source, -2, ends the list); cum[i] = descents on the edges between
 //   node[i] and x.  Returns the length, -1 if an unsettled tie node lies on the walked part, -2 if the chain is broken.
 #define TIE_K 48
-PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, const bool* done, int n) {
+#define TIE_K_SHORT 6
+PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, const bool* done, int n, int kmax) {
     int len = 0, c = 0;
     i32 y = x;
-    while (len < TIE_K) {
+    while (len < kmax) {
         node[len] = y;
         cum[len] = c;
         len++;
@@ -852,28 +853,28 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
             if (done[a]) continue;
             const i32 v = tv[a];
             i32 best = (v == -3) ? B.tparent[c] : B.parent[v];
-            int ylen = tie_walk(B, best, ynode, ycum, tv, done, n);
-            bool wait = ylen == -1, broken = ylen == -2;
+            // the chains of a node's candidates usually meet within a few edges: a short walk first, the long one only
+            // if no common node turns up (each step is a handful of dependent loads for a lone thread)
+            bool wait = false, broken = false;
             for (int b = a; b < n && !wait && !broken; b++) {
                 if (done[b] || tv[b] != v) continue;
                 const i32 x = tf[b];
-                const int zlen = tie_walk(B, x, znode, zcum, tv, done, n);
-                if (zlen == -1) {
-                    wait = true;
-                    break;
-                }
-                if (zlen == -2) {
-                    broken = true;
-                    break;
-                }
                 int dy = -1, dz = -1;             // descents of both chains below their first common node
-                for (int j = 0; j < zlen && dy < 0; j++)
-                    for (int i = 0; i < ylen; i++)
-                        if (ynode[i] == znode[j]) {
-                            dy = ycum[i];
-                            dz = zcum[j];
-                            break;
-                        }
+                for (int kmax = TIE_K_SHORT; dy < 0 && kmax <= TIE_K && !wait && !broken; kmax = (kmax == TIE_K ? TIE_K + 1 : TIE_K)) {
+                    const int ylen = tie_walk(B, best, ynode, ycum, tv, done, n, kmax);
+                    const int zlen = ylen < 0 ? ylen : tie_walk(B, x, znode, zcum, tv, done, n, kmax);
+                    if (ylen == -1 || zlen == -1) wait = true;
+                    else if (ylen == -2 || zlen == -2) broken = true;
+                    else
+                        for (int j = 0; j < zlen && dy < 0; j++)
+                            for (int i = 0; i < ylen; i++)
+                                if (ynode[i] == znode[j]) {
+                                    dy = ycum[i];
+                                    dz = zcum[j];
+                                    break;
+                                }
+                }
+                if (wait || broken) break;
                 if (dy < 0) {                     // no common node within TIE_K: the absolute pass numbers
                     dy = tie_chain_pass(B, best, tv, done, n, nodes);
                     dz = tie_chain_pass(B, x, tv, done, n, nodes);
@@ -886,10 +887,7 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
                         break;
                     }
                 }
-                if (dz < dy || (dz == dy && tie_sigma_less(B, x, best))) {
-                    best = x;
-                    ylen = tie_walk(B, best, ynode, ycum, tv, done, n);    // (cannot fail: just walked as z)
-                }
+                if (dz < dy || (dz == dy && tie_sigma_less(B, x, best))) best = x;
             }
             if (broken) {
                 cs->err |= ERR_TIES;
