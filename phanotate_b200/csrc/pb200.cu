@@ -415,6 +415,11 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         std::swap(ctx->scratch, ctx->scratch2);                          \
     } while (0)
 #define PB_SIDE_JOIN() cudaStreamWaitEvent(ctx->stream, ctx->side_ev, 0)
+#define PB_SIDE_RESUME()                                                 \
+    do { /* back to the side stream without making it wait for the main stream */ \
+        std::swap(ctx->stream, ctx->stream2);                            \
+        std::swap(ctx->scratch, ctx->scratch2);                          \
+    } while (0)
 #define PB_RUN_OV(fill_)                                                                         \
     do {                                                                                         \
         if (B.nn > 0) {                                                                          \
@@ -540,6 +545,7 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
 #define PB_SIDE_BEGIN()
 #define PB_SIDE_END()
 #define PB_SIDE_JOIN()
+#define PB_SIDE_RESUME()
 #define PB_RUN_OV(fill_)                                 \
     do {                                                 \
         if (fill_) PB_RUN(st_ov_fill, B.nn);             \
@@ -635,6 +641,24 @@ static int make_params(pb200_ctx* ctx, const pb200_params* in, Params* P) {
 // The literal chain (hold.cuh) over the first nlit entries of B.lit_ids (or over every ORF when B.lit_all):
 // the six Decimal factors per ORF, the per-codon product replayed multiplication by multiplication, Orf.score().
 #define ALN(x) (((size_t)(x) + 255) & ~(size_t)255)
+// second half of phase 3: size and fill the bridge tables (on whichever stream the context currently points at)
+static int bridge_tables(pb200_ctx* ctx) {
+    Batch& B = ctx->B;
+    {
+        u32 tot;
+        PB_FETCH(&tot, B.br_cnt + B.nn, 4);
+        B.nbr = (i32)tot;
+    }
+    {
+        const size_t nbr = (size_t)B.nbr + 1;
+        PB_PHASE(3, 2 * ALN(nbr * 4) + ALN(nbr * sizeof(Dec)) + ALN(nbr * sizeof(WInt)) + 1024);
+        B.br_src = PB_ALLOC(3, i32, nbr);
+        B.br_dst = PB_ALLOC(3, i32, nbr);
+        B.br_wint = PB_ALLOC(3, WInt, nbr);
+    }
+    if (B.nbr > 0) PB_RUN(st_br_fill, B.nn);
+    return 0;
+}
 static int literal_chain(pb200_ctx* ctx, i32 nlit) {
     Batch& B = ctx->B;
     B.nlit = nlit;
