@@ -6,7 +6,7 @@ from .locus import Locus
 
 
 class File:
-    formats = ['tabular', 'genbank', 'fna', 'faa', 'fasta']
+    formats = ['tabular', 'genbank', 'fna', 'faa', 'fasta', 'gff', 'gff3']      # (get_args takes formats[:7])
 
     def __init__(self, path):
         self.path = path

@@ -78,5 +78,17 @@ class Locus:
             outfile.write(self._header(f))
             outfile.write(aa + "\n")
 
+    def gff3(self, outfile=sys.stdout):
+        """`-f gff` / `-f gff3`: the reference lists these formats (README.md:40) but their writer lives in the absent
+        ``genbank`` package and the reference shows no example, so this is plain GFF3 (one `CDS` row per call, the score
+        column = the printed score), NOT pinned to the reference's bytes."""
+        outfile.write("##gff-version 3\n")
+        outfile.write("##sequence-region %s 1 %d\n" % (self.name(), self.length()))
+        for k, f in enumerate(self.features(include=['CDS'])):
+            outfile.write("%s\tPHANOTATE\tCDS\t%s\t%s\t%s\t%s\t0\tID=%s_CDS_%d\n" % (
+                self.name(), f.pairs[0][0], f.pairs[-1][-1], f.weight, '+' if f.strand > 0 else '-', self.name(), k + 1))
+
+    gff = gff3
+
     def write(self, args):
         getattr(self, args.format)(args.outfile)

@@ -117,6 +117,25 @@ def test_cli_genbank_header_like_readme_cpu(sim_engine, capsys):
                         "     CDS             687..1622", "                     /note=score:-4.857517E+06"]
 
 
+def test_cli_gff3_and_fasta_formats_cpu(sim_engine, capsys):
+    """-f gff3 (plain GFF3; the reference's own writer is in the absent genbank package) and -f fna / faa (README.md:56-68)"""
+    import phanotate
+    fa = os.path.join(ROOT, "tests", "data", "phiX174.fasta")
+    phanotate.main([fa, "-f", "gff3"])
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "##gff-version 3" and out[1] == "##sequence-region phiX174 1 5386"
+    assert out[2].split("\t") == ["phiX174", "PHANOTATE", "CDS", "100", "627", "-4.827981E+02", "+", "0", "ID=phiX174_CDS_1"]
+    assert len(out) == 2 + 7
+    phanotate.main([fa, "-f", "gff"])
+    assert capsys.readouterr().out.splitlines() == out
+    phanotate.main([fa, "-f", "fna"])
+    fna = capsys.readouterr().out.splitlines()
+    assert fna[0] == ">phiX174_CDS_[100..627] [note=score:-4.827981E+02]" and fna[1].startswith("atgtttcagacttttatttctcgccataattcaaac")
+    phanotate.main([fa, "-f", "faa"])
+    faa = capsys.readouterr().out.splitlines()
+    assert faa[1].startswith("MFQTFISRHNSNFFSDKLVLTSVTPASSAPVLQTPKATSSTLYFDSLTVNAG") and faa[1].endswith("*")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["phiX174", "stress13", "T4"])
 def test_mirror_driven_like_reference_gpu(name):
