@@ -45,6 +45,7 @@ static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
     __global__ void __launch_bounds__(PB_BLOCK) k_##stage(const Batch B, i64 n) {               \
         for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) stage(B, i); \
     }
+PB_KERNEL(st_zero_tails)
 PB_KERNEL(st_scan)
 PB_KERNEL(st_mark)
 PB_KERNEL(st_count64)

@@ -238,6 +238,30 @@ static inline i32 pb_exch(i32* p, i32 v) {
 #define PB_ATOMIC_EXCH(p, v) pb_exch((p), (v))
 #endif
 
+// the 24 per-base bit masks of a batch, in allocation order
+PB_HD u64* mask_array(const Batch& B, int a) {
+    switch (a) {
+        case 0: return B.mS;
+        case 1: return B.ms;
+        case 2: return B.mT;
+        case 3: return B.mt;
+        case 4: return B.bA;
+        case 5: return B.bC;
+        case 6: return B.bG;
+        case 7: return B.bT;
+        case 8: return B.mNS;
+        case 23: return B.mNK;
+        default: return a < 14 ? B.cF[a - 9] : a < 19 ? B.cR[a - 14] : B.mk[a - 19];
+    }
+}
+// zero the last word below nb (its upper half may stay unwritten) and the two pad words of mask a.  item = mask
+PB_HDN void st_zero_tails(const Batch& B, i64 a) {
+    if (a >= 24) return;
+    const i64 nblk = (B.nb + 63) >> 6;
+    u64* m = mask_array(B, (int)a);
+    for (i64 w = nblk > 0 ? nblk - 1 : 0; w < nblk + 2; w++) m[w] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // alphabet (functions.py:19-24,159-163)
 PB_HD u8 lower(u8 ch) { return (ch >= 'A' && ch <= 'Z') ? (u8)(ch | 0x20) : ch; }
