@@ -113,6 +113,7 @@ enum {
     PB200_SOLVE_WIDE = 32,    /* testing: 256-bit distances in the solve for every contig */
     PB200_SOLVE_PLAIN = 64,   /* testing: the plain statement of the 128-bit sweep (every operand fetched when needed) instead
                                  of the windowed kernel */
+    PB200_SOLVE_NOCHUNK = 128, /* testing: long contigs are solved by one sweep like the others, not in chunks */
     PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly
@@ -139,10 +140,18 @@ int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, i
  * batch into groups for several contexts and wants the rows numbered in the whole batch */
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base);
 
+/* Long contigs (BASELINE config 5: one 10-Mb contig; functions.py:360-438 + phanotate.py:56-64 on a graph of 3.6e5
+ * nodes): a contig with more than `long_nodes` graph nodes (~28 bp per node; default 4096) is solved as chunks of `core`
+ * nodes (256), one warp each, swept from `warm` nodes upstream (768) to `margin` nodes downstream (64); the chunks'
+ * distances are put together and EVERY node's Bellman equation is checked, so the result is the exact solve whatever
+ * the geometry (a contig that fails the check is solved again by one sweep).  The geometry only moves the time. */
+int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margin, int32_t long_nodes);
+
 /* out[0..7] = n_contigs, n_bases, n_nodes, n_orfs, n_overlap_edges, n_bridge_edges, n_calls, n_edges */
 int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
 /* out[0] = ORFs whose weight went through the literal Decimal chain before the solve, out[1] = after
- * it (called CDS), out[2] = overlap edges through the literal power; rest reserved */
+ * it (called CDS), out[2] = overlap edges through the literal power, out[3] = chunks the long contigs were solved
+ * in, out[4] = long contigs whose chunked solve failed its check and was redone by one sweep; rest reserved */
 int pb200_stats(pb200_ctx* ctx, int64_t out[8]);
 /* the integer weight the solver used for every ORF edge: trunc(Orf.weight * 1000) (edges.py:22) as
  * 8 little-endian 32-bit limbs, two's complement, per ORF */

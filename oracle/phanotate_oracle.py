@@ -618,7 +618,7 @@ def int_weight(w: Decimal) -> int:
     return int((w * 1000).to_integral_value(rounding=ROUND_DOWN))
 
 
-def shortest_path(nodes, edges, source, target):
+def shortest_path_literal(nodes, edges, source, target):
     """Exact-integer Bellman-Ford, edges in iteredges() order, strict '<', passes to fixpoint."""
     idx = {n: i for i, n in enumerate(nodes)}
     E = [(idx[a], idx[b], int_weight(w)) for a, b, w in edges]
@@ -636,6 +636,66 @@ def shortest_path(nodes, edges, source, target):
                 dist[v], par[v], changed = nd, u, True
         if not changed:
             break
+    if dist[idx[target]] is None:
+        return []
+    path, v = [], idx[target]
+    while v != -1:
+        path.append(nodes[v])
+        v = par[v]
+    return path[::-1]
+
+
+def shortest_path(nodes, edges, source, target):
+    """The same Bellman-Ford (same relaxations in the same order, hence the same parents on exact ties), without
+    the scans that cannot change anything: relaxing u->v can only succeed if dist[u] fell since the edge was last
+    scanned, so a pass scans the edge groups of the nodes whose distance fell since their group was last scanned.
+    iteredges() groups the edges by source node in node insertion order (graphs.py:121-126); a node improved by a
+    group scanned later in the pass waits for the next pass, one improved by an earlier group is scanned in this
+    pass -- exactly what the full scan does.  Linear instead of quadratic in the contig length (the number of
+    passes grows with the path length), which is what makes Mb-sized goldens affordable.  Falls back to the
+    literal scan if the edge list is not grouped as expected."""
+    import heapq
+    idx = {n: i for i, n in enumerate(nodes)}
+    groups = {}
+    order = []
+    last = None
+    for a, b, w in edges:
+        u = idx[a]
+        if u != last:
+            if u in groups:
+                return shortest_path_literal(nodes, edges, source, target)
+            groups[u] = []
+            order.append(u)
+            last = u
+        groups[u].append((idx[b], int_weight(w)))
+    rank = {u: k for k, u in enumerate(order)}          # position of a node's group in the scan
+    dist = [None] * len(nodes)
+    par = [-1] * len(nodes)
+    s = idx[source]
+    dist[s] = 0
+    cur, nxt = [], []
+    queued = set()
+    if s in rank:
+        cur.append(rank[s])
+        queued.add(s)
+    while cur:
+        while cur:
+            k = heapq.heappop(cur)
+            u = order[k]
+            queued.discard(u)
+            du = dist[u]
+            for v, w in groups[u]:
+                nd = du + w
+                if dist[v] is None or nd < dist[v]:
+                    dist[v], par[v] = nd, u
+                    if v in rank and v not in queued:
+                        queued.add(v)
+                        if rank[v] > k:
+                            heapq.heappush(cur, rank[v])
+                        else:
+                            nxt.append(rank[v])
+        cur, nxt = nxt, []
+        heapq.heapify(cur)
     if dist[idx[target]] is None:
         return []
     path, v = [], idx[target]

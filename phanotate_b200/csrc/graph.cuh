@@ -191,6 +191,7 @@ PB_HD bool bridge_interval(const Batch& B, i32 i, int L, int& mi, int& me) {
     return false;
 }
 PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
+    if (B.ch_cnt[c + 1] > B.ch_cnt[c]) return;    // a long contig: st_reach_* (chunk.cuh)
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
     const int L = B.cs[c].L;
     int run = 0;
@@ -241,6 +242,7 @@ PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
                 int len = B.n_pos[r] - B.n_pos[l] - 3;
                 if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
                 if (fill) {
+                    B.n_brs[l] = 1;
                     B.br_src[k] = l;
                     B.br_dst[k] = r;
                     // score_gap(len > 300) = g**100 + len (functions.py:40-41): its integer is len*1000 + a per-contig constant
@@ -388,10 +390,27 @@ PB_HD i64 gap_w64(const Batch& B, int c, int len, bool diff, bool* ok) {
     return 0;
 }
 
+// A sweep over part of a contig (chunk.cuh): nodes [s, e) only, distances and dirty flags in the chunk's private arrays
+// (indexed by node id), no parents, no tie records, no target -- the distances are all that is kept.  base = position
+// the stand-in source sits at (0: the contig's real source, functions.py:444-447).
+struct SolveRange {
+    i32 s, e;
+    struct I128* dist;
+    u8* dirty;
+    i32 base;
+};
 // relaxation of node v whose current distance `cur` the caller already holds
-template <class D>
+template <class D, bool CH = false>
 PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const typename D::T& cur, const typename D::T& cand,
-                 i32 from) {
+                 i32 from, u8* dirty = nullptr) {
+    if (CH) {
+        if (D::less(cand, cur)) {
+            dist[v] = cand;
+            dirty[v] = 1;
+            return true;
+        }
+        return false;
+    }
     if (D::less(cand, cur)) {
         dist[v] = cand;
         B.parent[v] = from;
@@ -407,13 +426,16 @@ PB_HD bool relax(const Batch& B, u32& ties, typename D::T* dist, i32 v, const ty
 
 // Loads that do not depend on each other are issued together (node word, distance of the candidate target,
 // edge ranges), so a visit is two or three memory round trips deep instead of five.
-template <class D>
-PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
+// CH = true: the sweep of one chunk of a long contig over the node range R (see SolveRange).
+template <class D, bool CH = false>
+PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveRange* R = nullptr) {
     typedef typename D::T T;
-    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    const i32 nb = CH ? R->s : B.cnode[c], ne = CH ? R->e : B.cnode[c + 1];
     CStat* cs = B.cs + c;
     const int L = cs->L;
-    T* dist = D::dist(B);
+    T* dist = CH ? (T*)R->dist : D::dist(B);
+    u8* dirty = CH ? R->dirty : B.dirty;
+    const int base = CH ? R->base : 0;
     const u32* pk = B.n_pk;                       // position << 4 | kind | frame << 2
     u32 ties = 0;
     bool okw = true;
@@ -423,21 +445,21 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
         i32 p0 = -1;
         u8 f0 = 0;
         // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
-        if ((int)(w >> 4) <= 2000 && kind_is_entry((int)(w & 3))) {
+        if ((int)(w >> 4) - base <= 2000 && kind_is_entry((int)(w & 3))) {
             bool o;
-            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4), false, &o));
+            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4) - base, false, &o));
             okw = okw && o;
             p0 = -2;
             f0 = 1;
         }
         dist[i] = d0;
-        B.parent[i] = p0;
-        B.dirty[i] = f0;
+        if (!CH) B.parent[i] = p0;
+        dirty[i] = f0;
     }
     T tdist = D::inf();
     i32 tpar = -1;
     PB_SYNCWARP();
-    const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
+    const u32 brb = B.br_cnt[B.cnode[c]], bre = B.br_cnt[B.cnode[c + 1]];
     i32 i = nb;
     int budget = 64 * (ne - nb) + 1024;
     while (i < ne) {
@@ -447,7 +469,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
             bool found = false;
             while (i < ne) {
                 i32 j = i + lane;
-                unsigned m = __ballot_sync(0xFFFFFFFFu, j < ne && B.dirty[j]);
+                unsigned m = __ballot_sync(0xFFFFFFFFu, j < ne && dirty[j]);
                 if (m) {
                     i += __ffs(m) - 1;
                     found = true;
@@ -458,7 +480,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
             if (!found) break;
         }
 #else
-        while (i < ne && !B.dirty[i]) i++;
+        while (i < ne && !dirty[i]) i++;
         if (i >= ne) break;
 #endif
         if (--budget < 0) {
@@ -470,13 +492,15 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
         const T Du = dist[u];
         const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
         PB_SYNCWARP();
-        if (lane == 0) B.dirty[u] = 0;
+        if (lane == 0) dirty[u] = 0;
         i32 rewind = 0x7FFFFFFF;
         if (kind == K_FSTART) {
             if (lane == 0) {
                 const i32 v = B.n_mate[u], orf = B.n_orf[u];
-                const T cur = dist[v];
-                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+                if (!CH || v < ne) {
+                    const T cur = dist[v];
+                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.o_wint + orf)), u, dirty);
+                }
             }
         } else if (kind == K_RSTOP) {
             const int farpos = (int)(pk[B.n_mate[u]] >> 4);
@@ -487,7 +511,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
                 if ((int)(wj & 3) == K_RSTART && mj == u) {
                     const i32 orf = B.n_orf[j];
                     const T cur = dist[j];
-                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+                    relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u, dirty);
                 }
             }
         } else {
@@ -502,30 +526,34 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
                 bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
                 if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
                 bool o;
-                relax<D>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u, dirty);
             }
             // overlap edges (backwards)
             if (ove > ovb) {
                 for (u32 k = ovb + lane; k < ove; k += NL) {
                     const i64 w64 = B.ov_w64[k];
                     const i32 v = B.ov_dst[k];
+                    if (CH && v < nb) continue;
                     const T cur = dist[v];
                     const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
-                    if (relax<D>(B, ties, dist, v, cur, cand, u) && v < rewind) rewind = v;
+                    if (relax<D, CH>(B, ties, dist, v, cur, cand, u, dirty) && v < rewind) rewind = v;
                 }
 #ifdef __CUDA_ARCH__
                 rewind = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)rewind);
 #endif
             }
-            // bridges
-            for (u32 k = brb + lane; k < bre; k += NL) {
-                if (B.br_src[k] != u) continue;
-                const i32 v = B.br_dst[k];
-                const T cur = dist[v];
-                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u);
+            // bridges (rare: n_brs flags the exit nodes that have any)
+            if (bre > brb && B.n_brs[u]) {
+                for (u32 k = brb + lane; k < bre; k += NL) {
+                    if (B.br_src[k] != u) continue;
+                    const i32 v = B.br_dst[k];
+                    if (CH && v >= ne) continue;
+                    const T cur = dist[v];
+                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u, dirty);
+                }
             }
             // exit -> target within 2000 bp of the right end (functions.py:448-451)
-            if (L - pu <= 2000) {
+            if (!CH && L - pu <= 2000) {
                 bool o;
                 const T cand = D::add(Du, D::from_i64(gap_w64(B, c, L - pu, false, &o)));
                 okw = okw && o;
@@ -541,6 +569,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL) {
         PB_SYNCWARP();
         i = (rewind < u) ? rewind : u + 1;
     }
+    if (CH) return;
     if (ties) PB_ATOMIC_ADD(&cs->n_ties, ties);
     if (!okw && lane == 0) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
     if (lane == 0) {
@@ -566,15 +595,17 @@ __device__ __forceinline__ I128 shfl128(unsigned mask, const I128& a, int src) {
 // NL = lanes per contig (32: a warp; 16: two contigs share a warp, each half with its own control flow -- twice the
 // contigs in flight per SM at the same register cost, which is what a latency-bound sweep wants); lane = 0..NL-1,
 // mask = the lanes of this contig inside the warp.
-template <int NL>
-__device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask) {
+template <int NL, bool CH = false>
+__device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask, const SolveRange* R = nullptr) {
     const int lane0 = __ffs((int)mask) - 1;       // position of lane 0 of this group inside the warp
     typedef D128 D;
     typedef I128 T;
-    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    const i32 nb = CH ? R->s : B.cnode[c], ne = CH ? R->e : B.cnode[c + 1];
     CStat* cs = B.cs + c;
     const int L = cs->L;
-    T* dist = B.dist128;
+    T* dist = CH ? R->dist : B.dist128;
+    u8* dirty = CH ? R->dirty : B.dirty;
+    const int base = CH ? R->base : 0;
     const u32* pk = B.n_pk;
     u32 ties = 0;
     bool okw = true;
@@ -583,21 +614,21 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
         T d0 = D::inf();
         i32 p0 = -1;
         u8 f0 = 0;
-        if ((int)(w >> 4) <= 2000 && kind_is_entry((int)(w & 3))) {       // source -> entry (functions.py:444-447)
+        if ((int)(w >> 4) - base <= 2000 && kind_is_entry((int)(w & 3))) {       // source -> entry (functions.py:444-447)
             bool o;
-            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4), false, &o));
+            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4) - base, false, &o));
             okw = okw && o;
             p0 = -2;
             f0 = 1;
         }
         dist[i] = d0;
-        B.parent[i] = p0;
-        B.dirty[i] = f0;
+        if (!CH) B.parent[i] = p0;
+        dirty[i] = f0;
     }
     T tdist = D::inf();
     i32 tpar = -1;
     __syncwarp(mask);
-    const u32 brb = B.br_cnt[nb], bre = B.br_cnt[ne];
+    const u32 brb = B.br_cnt[B.cnode[c]], bre = B.br_cnt[B.cnode[c + 1]];
     i32 i = nb;
     int budget = 64 * (ne - nb) + 1024;
     while (i < ne) {
@@ -609,7 +640,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
         i32 mj = -1, oj = -1;
         T Tj = D::inf();
         if (in) {
-            dj = B.dirty[j0];
+            dj = dirty[j0];
             wj = pk[j0];
             Tj = dist[j0];
             mj = B.n_mate[j0];
@@ -631,25 +662,26 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
         const T Du = shfl128<NL>(mask, Tj, f);
         const i32 mate_u = __shfl_sync(mask, mj, f, NL), orf_u = __shfl_sync(mask, oj, f, NL);
         const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
-        if (lane == 0) B.dirty[u] = 0;
+        if (lane == 0) dirty[u] = 0;
         i32 rewind = 0x7FFFFFFF;
         const bool behind = in && lane > f;                 // a node after u inside the window
         if (kind == K_FSTART) {
-            if (lane == 0) {
+            if (lane == 0 && (!CH || mate_u < ne)) {
                 const T cur = dist[mate_u];
-                relax<D>(B, ties, dist, mate_u, cur, D::add(Du, D::load_w(B.o_wint + orf_u)), u);
+                relax<D, CH>(B, ties, dist, mate_u, cur, D::add(Du, D::load_w(B.o_wint + orf_u)), u, dirty);
             }
         } else if (kind == K_RSTOP) {
             // the starts of this reverse family: nodes up to its farthest start (n_mate of the stop-key node)
             if (behind && j0 <= mate_u && (int)(wj & 3) == K_RSTART && mj == u)
-                relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::load_w(B.o_wint + oj)), u);
-            for (i32 j = i + NL + lane; j <= mate_u; j += NL) {
+                relax<D, CH>(B, ties, dist, j0, Tj, D::add(Du, D::load_w(B.o_wint + oj)), u, dirty);
+            const i32 last = (CH && mate_u >= ne) ? ne - 1 : mate_u;
+            for (i32 j = i + NL + lane; j <= last; j += NL) {
                 const u32 w2 = pk[j];
                 const i32 m2 = B.n_mate[j];
                 if ((int)(w2 & 3) == K_RSTART && m2 == u) {
                     const i32 orf = B.n_orf[j];
                     const T cur = dist[j];
-                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u);
+                    relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u, dirty);
                 }
             }
         } else {
@@ -662,7 +694,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
                 if (behind && d > 0 && d < 500 && kind_is_entry(kj) && !(kind == K_RSTART && kj == K_FSTART && d <= 2)) {
                     const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
                     bool o;
-                    relax<D>(B, ties, dist, j0, Tj, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                    relax<D, CH>(B, ties, dist, j0, Tj, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u, dirty);
                 }
             }
             const u32 wlast = __shfl_sync(mask, wj, NL - 1, NL);
@@ -676,7 +708,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
                     const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
                     if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
                     bool o;
-                    relax<D>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u);
+                    relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))), u, dirty);
                 }
             }
             // overlap edges (backwards)
@@ -684,21 +716,25 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
                 for (u32 k = ovb + lane; k < ove; k += NL) {
                     const i64 w64 = B.ov_w64[k];
                     const i32 v = B.ov_dst[k];
+                    if (CH && v < nb) continue;
                     const T cur = dist[v];
                     const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + k));
-                    if (relax<D>(B, ties, dist, v, cur, cand, u) && v < rewind) rewind = v;
+                    if (relax<D, CH>(B, ties, dist, v, cur, cand, u, dirty) && v < rewind) rewind = v;
                 }
                 rewind = (i32)__reduce_min_sync(mask, (unsigned)rewind);
             }
-            // bridges
-            for (u32 k = brb + lane; k < bre; k += NL) {
-                if (B.br_src[k] != u) continue;
-                const i32 v = B.br_dst[k];
-                const T cur = dist[v];
-                relax<D>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u);
+            // bridges (rare: n_brs flags the exit nodes that have any)
+            if (bre > brb && B.n_brs[u]) {
+                for (u32 k = brb + lane; k < bre; k += NL) {
+                    if (B.br_src[k] != u) continue;
+                    const i32 v = B.br_dst[k];
+                    if (CH && v >= ne) continue;
+                    const T cur = dist[v];
+                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u, dirty);
+                }
             }
             // exit -> target within 2000 bp of the right end (functions.py:448-451)
-            if (L - pu <= 2000) {
+            if (!CH && L - pu <= 2000) {
                 bool o;
                 const T cand = D::add(Du, D::from_i64(gap_w64(B, c, L - pu, false, &o)));
                 okw = okw && o;
@@ -714,6 +750,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
         __syncwarp(mask);
         i = (rewind < u) ? rewind : u + 1;
     }
+    if (CH) return;
     if (ties) atomicAdd(&cs->n_ties, ties);
     if (!okw && lane == 0) atomicOr(&cs->err, (u32)ERR_OVERFLOW);
     if (lane == 0) {
@@ -723,9 +760,11 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask)
 }
 #endif
 PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE); }
+// a long contig whose solve runs as chunks (chunk.cuh) instead of one sweep
+PB_HD bool contig_chunked(const Batch& B, int c) { return B.ch_cnt && B.ch_cnt[c + 1] > B.ch_cnt[c] && !contig_is_wide(B, c); }
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
     if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
-    else solve_contig_t<D128>(B, c, lane, NL);
+    else if (!contig_chunked(B, c)) solve_contig_t<D128>(B, c, lane, NL);
 }
 
 // Stage 12b: exact ties.  Distances do not depend on the relaxation order, parents do: where two edges into a node
@@ -814,7 +853,9 @@ PB_HDN void st_tie_link(const Batch& B, i64 k) {
     TieEv* e = B.tie_ev + k;
     const int c = (e->v <= -3) ? (-3 - e->v) : B.n_contig[e->v];
     if (e->v <= -3) e->v = -3;
-    if (e->pad == 1) {
+    // (pad bit 1: recorded by the chunked solve's check -- void once the contig fell back to the one-warp sweep)
+    if ((e->pad & 2) && B.cs[c].chunk_viol) return;
+    if (e->pad & 1) {
         const u32 ext = (e->cand.w[3] >> 31) ? 0xFFFFFFFFu : 0u;
         for (int i = 4; i < WN; i++) e->cand.w[i] = ext;
     }
@@ -912,6 +953,7 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
 PB_HDN void st_backtrack(const Batch& B, i64 c64) {
     if (c64 >= B.nc) return;
     const int c = (int)c64;
+    if (contig_chunked(B, c)) return;             // chunk.cuh: st_pj_* trace the path of a long contig in parallel
     CStat* cs = B.cs + c;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
     i32* out = B.call_tmp + B.corf[c];

@@ -14,6 +14,7 @@
 
 #include "../../include/phanotate_b200.h"
 #include "graph.cuh"
+#include "chunk.cuh"
 #include "connect.cuh"
 #include "fast.cuh"
 
@@ -86,6 +87,23 @@ PB_KERNEL(st_contig_lng)
 PB_KERNEL(st_rbs_weights)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
+PB_KERNEL(st_chunk_plan)
+PB_KERNEL(st_chunk_ids)
+PB_KERNEL(st_chunk_delta)
+PB_KERNEL(st_chunk_prefix)
+PB_KERNEL(st_lv_init)
+PB_KERNEL(st_lv_node)
+PB_KERNEL(st_lv_orf)
+PB_KERNEL(st_lv_ov)
+PB_KERNEL(st_lv_br)
+PB_KERNEL(st_lv_check)
+PB_KERNEL(st_lv_target)
+PB_KERNEL(st_pj_init)
+PB_KERNEL(st_pj_round)
+PB_KERNEL(st_pj_calls)
+PB_KERNEL(st_reach_max)
+PB_KERNEL(st_reach_prefix)
+PB_KERNEL(st_reach_apply)
 
 #include "scan_tile.cuh"
 // one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
@@ -97,10 +115,38 @@ __global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
     const i64 group = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / NL;
     const i64 ngroups = ((i64)gridDim.x * blockDim.x) / NL;
     for (i64 c = group; c < nc; c += ngroups)
-        if (!contig_is_wide(B, (int)c)) {
+        if (!contig_is_wide(B, (int)c) && !contig_chunked(B, (int)c)) {
             if (NL == 32 && (B.flags & PB200_SOLVE_PLAIN)) solve_contig_t<D128>(B, (int)c, lane, 32);
             else solve_contig_win<NL>(B, (int)c, lane, mask);
         }
+}
+// long contigs: one warp per chunk, distances only, into the chunk's private arrays (chunk.cuh)
+__global__ void __launch_bounds__(PB_BLOCK) k_chunk_solve(const Batch B) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 id = warp; id < B.nch; id += nwarps) {
+        const ChunkGeo g = chunk_geo(B, (i32)id);
+        if (contig_is_wide(B, g.c)) continue;
+        const SolveRange R = chunk_range(B, g);
+        if (B.flags & PB200_SOLVE_PLAIN) solve_contig_t<D128, true>(B, g.c, lane, 32, &R);
+        else solve_contig_win<32, true>(B, g.c, lane, 0xFFFFFFFFu, &R);
+    }
+}
+// the one-warp sweep for the chunked contigs whose assembled distances failed a check
+__global__ void __launch_bounds__(PB_BLOCK) k_solve_fallback(const Batch B, i32 nc) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 c = warp; c < nc; c += nwarps) {
+        if (!contig_chunked(B, (int)c) || !B.cs[c].chunk_viol) continue;
+        if (lane == 0) {
+            B.cs[c].n_ties = 0;
+            atomicAdd(B.lit_cnt + 4, 1u);
+        }
+        __syncwarp();
+        solve_contig_win<32>(B, (int)c, lane, 0xFFFFFFFFu);
+    }
 }
 __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) {
     const int lane = threadIdx.x & 31;
@@ -260,6 +306,7 @@ struct pb200_ctx {
     int sm_count = 148;
     int contig_base = 0;
     bool scan_attr_set = false;
+    int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
 };
 // wait for the context's stream.  PB200_BLOCKING_SYNC=1 (environment, read at pb200_create) makes the host thread sleep on
@@ -385,6 +432,10 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         cudaEventRecord(ctx->fork_ev, ctx->stream);                                              \
         cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
         k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
+        if (B.nch > 0) {                                                                         \
+            k_chunk_solve<<<grid_for(ctx, (i64)B.nch * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B); \
+            ctx->launches++;                                                                     \
+        }                                                                                        \
         cudaEventRecord(ctx->join_ev, ctx->stream2);                                             \
         /* PB200_SOLVE_HALF=1 (environment): two contigs per warp, 16 lanes each -- twice the sweeps in flight at the   \
            same register cost.  Measured SLOWER on the bench workload (7.6 against 6.8 ms: the two halves' divergent    \
@@ -395,6 +446,19 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             k_solve<32><<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_));             \
         cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0);                                       \
         ctx->launches++;                                                                         \
+        cudaEventRecord(t_.b, ctx->stream);                                                      \
+        ctx->times.push_back(t_);                                                                \
+        ctx->launches++;                                                                         \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
+#define PB_RUN_FALLBACK(nc_)                                                                     \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = "solve_fallback";                                                              \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        k_solve_fallback<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (nc_)); \
         cudaEventRecord(t_.b, ctx->stream);                                                      \
         ctx->times.push_back(t_);                                                                \
         ctx->launches++;                                                                         \
@@ -491,6 +555,7 @@ struct DevBuf {
 struct pb200_ctx {
     int device = 0;
     int contig_base = 0;
+    int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     std::string err;
     DevBuf ph[NPHASE];
     DevBuf in_seq, in_off, scratch, conn, conn_out;
@@ -541,7 +606,13 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
 #define PB_RUN_SOLVE(nc_)                                              \
     do {                                                               \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
+        for (i32 id_ = 0; id_ < B.nch; id_++) chunk_solve(B, id_, 0, 1); \
         ctx->launches++;                                               \
+    } while (0)
+#define PB_RUN_FALLBACK(nc_)                                             \
+    do {                                                                 \
+        for (i32 c_ = 0; c_ < (nc_); c_++) solve_fallback(B, c_, 0, 1);  \
+        ctx->launches++;                                                 \
     } while (0)
 #define PB_SIDE_BEGIN()
 #define PB_SIDE_END()
@@ -766,6 +837,10 @@ int pb200_create(int device, pb200_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
 #endif
+    if (const char* e2 = getenv("PB200_CHUNK")) {
+        int a, b, c, d;
+        if (sscanf(e2, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) pb200_set_chunking(ctx, a, b, c, d);
+    }
     *out = ctx;
     return 0;
 }
@@ -817,6 +892,10 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     B.nc = n_contigs;
     B.flags = (i32)flags;
     B.contig_base = ctx->contig_base;
+    B.ch_core = ctx->ch_core;
+    B.ch_warm = ctx->ch_warm;
+    B.ch_margin = ctx->ch_margin;
+    B.ch_long = ctx->ch_long;
 #ifndef PB_HOSTSIM
     CK(cudaSetDevice(ctx->device));
     ctx->times.clear();
@@ -910,6 +989,19 @@ int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, i
     return 0;
 }
 
+// Geometry of the chunked solve of long contigs (chunk.cuh), in nodes (one node per ~28 bp): contigs with more than
+// `long_nodes` nodes are cut into chunks of `core` nodes, each swept by its own warp from `warm` nodes upstream to `margin`
+// nodes downstream.  Any geometry gives the same results (every node's distance is checked; a contig that fails is solved
+// again by one sweep); it only moves the time.  Environment PB200_CHUNK="core,warm,margin,long" sets it at pb200_create.
+int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margin, int32_t long_nodes) {
+    if (!ctx || core < 1 || warm < 0 || margin < 0 || long_nodes < 0) return -2;
+    ctx->ch_core = core;
+    ctx->ch_warm = warm;
+    ctx->ch_margin = margin;
+    ctx->ch_long = long_nodes;
+    return 0;
+}
+
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {
     if (!ctx) return -2;
     ctx->contig_base = base;
@@ -980,6 +1072,12 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
     out[0] = B.lit_all ? B.no : B.n_lit_pre;
     out[1] = B.lit_all ? 0 : B.n_lit_post;
     out[2] = (B.flags & PB200_LITERAL) ? B.nov : B.n_ovlit;
+    out[3] = B.nch;                                   // chunks the long contigs were solved in
+    if (B.nch > 0) {                                  // long contigs that failed the check and were solved by one sweep
+        u32 fb = 0;
+        PB_TO_HOST(&fb, B.lit_cnt + 4, 4);
+        out[4] = fb;
+    }
     return 0;
 }
 

@@ -73,6 +73,8 @@ struct CStat {
     i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
     DD fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
+    u32 chunk_viol;         // chunked solve (chunk.cuh): some node failed the Bellman check -> the contig is solved again by one sweep
+    u32 chunk_pad;
 };
 
 // an equal-distance relaxation seen by the sweep: edge from -> v offered `cand` when dist[v] was already `cand`
@@ -214,6 +216,21 @@ struct Batch {
     i32 contig_base;      // added to the contig column of the call rows (a caller that splits a batch over contexts)
     i32 gap_dec;          // the Decimal gap tables gap_same / gap_diff are built
     i32 lit_done;         // every ORF has its literal weight (lazy completion ran)
+    u8* n_brs;            // [nn] 1 where an exit node is the source of a bridge
+    // chunked solve of long contigs (chunk.cuh)
+    u32* ch_cnt;          // [nc+1] chunks per contig, then exclusive offsets (0 chunks: the contig is solved by one sweep)
+    i32 nch;              // chunks in the batch
+    i32 ch_core, ch_warm, ch_margin, ch_long;   // nodes per chunk / of warm-up before it / of margin behind it; contigs above ch_long nodes are chunked
+    struct I128* ch_dist; // [nch * (ch_warm + ch_core + ch_margin)] private distances of every chunk (relative to its stand-in source)
+    u8* ch_dirty;         // same shape
+    struct I128* ch_off;  // [nch] what to add to a chunk's distances (first: per-chunk delta against its left neighbour)
+    u8* ch_flag;          // [nch] 1: distances are absolute (warm-up reaches the contig start), 2: no anchor found
+    i32* ch_contig;       // [nch]
+    i32* pj_jump;         // [nn] pointer jumping over the parents of chunked contigs (parallel back-trace): 2^k-th ancestor
+    i32* pj_jump2;
+    i32* pj_depth;        // [nn] edges between the node and the source
+    i32* pj_depth2;
+    u8* pj_mark;          // [nn] node lies on the source -> target path
 };
 
 #ifdef __CUDA_ARCH__

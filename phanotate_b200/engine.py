@@ -82,6 +82,7 @@ class Result:
         st = np.zeros(8, dtype=np.int64)
         engine._ck(engine.lib.pb200_stats(engine.ctx, st.ctypes.data))
         self.n_literal_presolve, self.n_literal_postsolve, self.n_literal_overlaps = (int(v) for v in st[:3])
+        self.n_chunks, self.n_chunk_fallbacks = int(st[3]), int(st[4])
         self.launches = int(engine.lib.pb200_launch_count(engine.ctx))
         self.stage_ms = engine._stage_times()
 
@@ -220,6 +221,10 @@ class Engine:
                                     (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) |
                                     (N.CALL_WEIGHTS if call_weights else 0) | int(flags)))
         return Result(self, names) if fetch else None
+
+    def set_chunking(self, core=256, warm=768, margin=64, long_nodes=4096):
+        """Geometry (in graph nodes) of the chunked solve of long contigs; results do not depend on it."""
+        self._ck(self.lib.pb200_set_chunking(self.ctx, int(core), int(warm), int(margin), int(long_nodes)))
 
     def last_run_ms(self) -> float:
         return float(self.lib.pb200_last_run_ms(self.ctx))
