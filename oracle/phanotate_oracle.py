@@ -705,6 +705,77 @@ def shortest_path(nodes, edges, source, target):
     return path[::-1]
 
 
+def shortest_path_fast(nodes, edges, source, target):
+    """What the edge-order Bellman-Ford above ends with, computed without replaying its passes (for Mb-sized contigs, where
+    the replay is quadratic: every pass moves the improvements a few nodes further).  DERIVED, not literal:
+
+    1. the distances do not depend on the scan order: label correcting in node-position order;
+    2. the parent of v is the source of the FIRST scanned edge that offers v its final distance (any earlier offer is
+       larger, any later one is not strictly smaller).  An edge u->v offers it the first time u's group is scanned after u
+       itself became final.  If u became final while the group with scan rank k was being scanned in pass p, u's group
+       (rank r) is scanned in pass p when r > k, else in pass p+1.  So T(v) = min over tight in-edges of (pass, r), computed
+       in increasing T like Dijkstra (offers are strictly later than T(u)).
+
+    tests/test_oracle.py checks it against shortest_path on every fixture and on bench contigs with exact ties."""
+    import heapq
+    idx = {n: i for i, n in enumerate(nodes)}
+    groups, order, last = {}, [], None
+    for a, b, w in edges:
+        u = idx[a]
+        if u != last:
+            if u in groups:
+                raise ValueError("edges are not grouped by source node")
+            groups[u] = []
+            order.append(u)
+            last = u
+        groups[u].append((idx[b], int_weight(w)))
+    rank = {u: k for k, u in enumerate(order)}
+    n = len(nodes)
+    s, t = idx[source], idx[target]
+    pos = [nd[3] for nd in nodes]
+    dist = [None] * n
+    dist[s] = 0
+    heap, queued = [(pos[s], s)], {s}
+    while heap:
+        _, u = heapq.heappop(heap)
+        queued.discard(u)
+        du = dist[u]
+        for v, w in groups.get(u, ()):
+            nd = du + w
+            if dist[v] is None or nd < dist[v]:
+                dist[v] = nd
+                if v not in queued:
+                    queued.add(v)
+                    heapq.heappush(heap, (pos[v], v))
+    if dist[t] is None:
+        return []
+    par = [-1] * n
+    T = [None] * n
+    T[s] = (1, -1)
+    heap = [(T[s], s)]
+    done = [False] * n
+    while heap:
+        tu, u = heapq.heappop(heap)
+        if done[u] or tu != T[u]:
+            continue
+        done[u] = True
+        if u not in rank:
+            continue
+        r = rank[u]
+        when = (tu[0] if r > tu[1] else tu[0] + 1, r)
+        du = dist[u]
+        for v, w in groups[u]:
+            if du + w == dist[v] and (T[v] is None or when < T[v]):
+                T[v] = when
+                par[v] = u
+                heapq.heappush(heap, (when, v))
+    path, v = [], t
+    while v != -1:
+        path.append(nodes[v])
+        v = par[v]
+    return path[::-1]
+
+
 def calls_from_path(path, edges):
     """phanotate.py:65-76 + locus.py:29-37: consecutive non-overlapping pairs after dropping the source."""
     wmap = {(a, b): w for a, b, w in edges}
@@ -717,15 +788,15 @@ def calls_from_path(path, edges):
     return rows
 
 
-def call_contig(dna: str, start_codons=None, stop_codons=None, min_orf_len: int = 90, literal=False):
-    """Whole path for one contig -> (orfs, nodes, edges, rows)."""
+def call_contig(dna: str, start_codons=None, stop_codons=None, min_orf_len: int = 90, literal=False, fast=False):
+    """Whole path for one contig -> (orfs, nodes, edges, rows).  fast: shortest_path_fast (Mb-sized contigs)."""
     orfs = get_orfs(dna, start_codons, stop_codons, min_orf_len, literal)
     nodes, edges = get_graph(orfs)
     rows = []
     if len(nodes) > 2:                                     # phanotate.py:63
         source = ONode(('source', 'source', 0, 0))
         target = ONode(('target', 'target', 0, len(dna) + 1))
-        rows = calls_from_path(shortest_path(nodes, edges, source, target), edges)
+        rows = calls_from_path((shortest_path_fast if fast else shortest_path)(nodes, edges, source, target), edges)
     return orfs, nodes, edges, rows
 
 

@@ -138,13 +138,35 @@ PB_HDN void st_chunk_delta(const Batch& B, i64 id64) {
     B.ch_off[id] = cand[best];
     B.ch_flag[id] = 0;
 }
-// 2b. running sum of the deltas along the contig.  item = contig
-PB_HDN void st_chunk_prefix(const Batch& B, i64 c64) {
-    if (c64 >= B.nc) return;
-    const int c = (int)c64;
+// 2b. running sum of the deltas along the contig, restarting at every chunk that holds absolute distances.
+// item = contig (a warp: each lane sums a run of consecutive chunks, the lanes' totals are combined, then every lane
+// writes its run)
+PB_HDN void chunk_prefix(const Batch& B, int c, int lane, int NL) {
     if (!contig_chunked(B, c)) return;
-    I128 acc = D128::from_i64(0);
-    for (u32 id = B.ch_cnt[c]; id < B.ch_cnt[c + 1]; id++) {
+    const i32 ib = (i32)B.ch_cnt[c], ie = (i32)B.ch_cnt[c + 1];
+    const i32 per = (ie - ib + NL - 1) / NL;
+    const i32 a = ib + lane * per, b = a + per < ie ? a + per : ie;
+    // (sum, reset): what the run adds, and whether it contains a restart (then `sum` counts from the last restart)
+    I128 sum = D128::from_i64(0);
+    int reset = 0;
+    for (i32 id = a; id < b; id++) {
+        if (B.ch_flag[id] == 1) {
+            sum = D128::from_i64(0);
+            reset = 1;
+        } else {
+            sum = D128::add(sum, B.ch_off[id]);
+        }
+    }
+    I128 carry = D128::from_i64(0);         // value in front of this lane's run
+#ifdef __CUDA_ARCH__
+    for (int l = 0; l < NL - 1; l++) {      // sequential over 32 lanes: tiny
+        const I128 s_l = shfl128<32>(0xFFFFFFFFu, sum, l);
+        const int r_l = __shfl_sync(0xFFFFFFFFu, reset, l);
+        if (lane > l) carry = r_l ? s_l : D128::add(carry, s_l);
+    }
+#endif
+    I128 acc = carry;
+    for (i32 id = a; id < b; id++) {
         if (B.ch_flag[id] == 1) acc = D128::from_i64(0);
         else acc = D128::add(acc, B.ch_off[id]);
         B.ch_off[id] = acc;
@@ -358,61 +380,56 @@ PB_HDN void st_pj_calls(const Batch& B, i64 v64) {
     }
 }
 
-// ---- coverage prefix maximum of a chunked contig (reach_contig in three passes over its chunks).
-// value of node i: last covered base of the interval that starts at it
-PB_HD int reach_value(const Batch& B, i32 i, int L) {
-    int mi, me;
-    return bridge_interval(B, i, L, mi, me) ? me - 1 : 0;
-}
-// item = chunk: maximum over the core
-PB_HDN void st_reach_max(const Batch& B, i64 id64) {
-    if (id64 >= (i64)B.ch_cnt[B.nc]) return;
-    const i32 id = (i32)id64;
-    int lo = 0, hi = B.nc;
+// ---- coverage prefix maximum of a chunked contig (reach_contig in three passes over its chunks; one warp per chunk /
+// per contig).  The tail of n_reach (from nn + 1) holds one value per chunk.
+PB_HD void reach_chunk_geo(const Batch& B, i32 id, int& c, i32& a, i32& b) {
+    int lo = 0, hi = B.nc;                 // ch_cnt[lo] <= id < ch_cnt[lo+1]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if ((i64)B.ch_cnt[mid] <= id64) lo = mid;
+        if ((i32)B.ch_cnt[mid] <= id) lo = mid;
         else hi = mid;
     }
-    const int c = lo;
+    c = lo;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
-    const i32 a = nb + (id - (i32)B.ch_cnt[c]) * B.ch_core, b = a + B.ch_core < ne ? a + B.ch_core : ne;
-    const int L = B.cs[c].L;
-    int m = 0;
-    for (i32 i = a; i < b; i++) {
-        const int v = reach_value(B, i, L);
-        if (v > m) m = v;
-    }
-    B.n_reach[B.nn + 1 + id] = m;          // (n_reach has a tail of one entry per possible chunk)
+    a = nb + (id - (i32)B.ch_cnt[c]) * B.ch_core;
+    b = a + B.ch_core < ne ? a + B.ch_core : ne;
 }
-// item = contig: exclusive prefix maximum over its chunks
-PB_HDN void st_reach_prefix(const Batch& B, i64 c64) {
-    if (c64 >= B.nc) return;
+// pass 0: maximum over the chunk's core;  pass 2: the nodes' exclusive prefix maxima.  item = chunk (a warp)
+PB_HDN void reach_chunk(const Batch& B, i32 id, int pass, int lane, int NL) {
+    if (id >= (i32)B.ch_cnt[B.nc]) return;
+    int c;
+    i32 a, b;
+    reach_chunk_geo(B, id, c, a, b);
+    i32* slot = B.n_reach + (i64)B.nn + 1 + id;
+    if (pass == 0) {
+        const int m = reach_range(B, c, a, b, 0, false, lane, NL);
+        if (lane == 0) *slot = m;
+    } else {
+        reach_range(B, c, a, b, *slot, true, lane, NL);
+    }
+}
+// pass 1: exclusive prefix maximum over the chunks of a contig.  item = contig (a warp)
+PB_HDN void reach_chunk_prefix(const Batch& B, int c, int lane, int NL) {
+    i32* slot = B.n_reach + (i64)B.nn + 1;
+    const i32 ib = (i32)B.ch_cnt[c], ie = (i32)B.ch_cnt[c + 1];
     int run = 0;
-    for (u32 id = B.ch_cnt[c64]; id < B.ch_cnt[c64 + 1]; id++) {
-        const int m = B.n_reach[B.nn + 1 + id];
-        B.n_reach[B.nn + 1 + id] = run;
-        if (m > run) run = m;
-    }
-}
-// item = chunk: exclusive prefix maximum of every node of the core
-PB_HDN void st_reach_apply(const Batch& B, i64 id64) {
-    if (id64 >= (i64)B.ch_cnt[B.nc]) return;
-    const i32 id = (i32)id64;
-    int lo = 0, hi = B.nc;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((i64)B.ch_cnt[mid] <= id64) lo = mid;
-        else hi = mid;
-    }
-    const int c = lo;
-    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
-    const i32 a = nb + (id - (i32)B.ch_cnt[c]) * B.ch_core, b = a + B.ch_core < ne ? a + B.ch_core : ne;
-    const int L = B.cs[c].L;
-    int run = B.n_reach[B.nn + 1 + id];
-    for (i32 i = a; i < b; i++) {
-        B.n_reach[i] = run;
-        const int v = reach_value(B, i, L);
-        if (v > run) run = v;
+    for (i32 base = ib; base < ie; base += NL) {
+        const i32 i = base + lane;
+        const int v = i < ie ? slot[i] : 0;
+        int incl = v;
+#ifdef __CUDA_ARCH__
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o && t > incl) incl = t;
+        }
+        int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) prev = 0;
+        int excl = prev > run ? prev : run;
+        int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#else
+        int excl = run, tot = incl;
+#endif
+        if (i < ie) slot[i] = excl;
+        if (tot > run) run = tot;
     }
 }

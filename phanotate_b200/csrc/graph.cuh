@@ -190,11 +190,10 @@ PB_HD bool bridge_interval(const Batch& B, i32 i, int L, int& mi, int& me) {
     }
     return false;
 }
-PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
-    if (B.ch_cnt[c + 1] > B.ch_cnt[c]) return;    // a long contig: st_reach_* (chunk.cuh)
-    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+// exclusive prefix maximum of the interval ends over nodes [nb, ne) starting from `run`; returns the total.
+// (write = false: only the total)
+PB_HDN int reach_range(const Batch& B, int c, i32 nb, i32 ne, int run, bool write, int lane, int NL) {
     const int L = B.cs[c].L;
-    int run = 0;
     for (i32 base = nb; base < ne; base += NL) {
         const i32 i = base + lane;
         int v = 0, mi, me;
@@ -212,9 +211,14 @@ PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
 #else
         int excl = run, tot = incl;
 #endif
-        if (i < ne) B.n_reach[i] = excl;
+        if (write && i < ne) B.n_reach[i] = excl;
         if (tot > run) run = tot;
     }
+    return run;
+}
+PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
+    if (B.ch_cnt[c + 1] > B.ch_cnt[c]) return;    // a long contig: reach_chunk_* (chunk.cuh)
+    reach_range(B, c, B.cnode[c], B.cnode[c + 1], 0, true, lane, NL);
 }
 PB_HDNI WInt bridge_wint_long(const Batch& B, int c, int len) {
     WInt wi;

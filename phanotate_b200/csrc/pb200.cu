@@ -90,7 +90,6 @@ PB_KERNEL(st_edge_fill)
 PB_KERNEL(st_chunk_plan)
 PB_KERNEL(st_chunk_ids)
 PB_KERNEL(st_chunk_delta)
-PB_KERNEL(st_chunk_prefix)
 PB_KERNEL(st_lv_init)
 PB_KERNEL(st_lv_node)
 PB_KERNEL(st_lv_orf)
@@ -101,9 +100,6 @@ PB_KERNEL(st_lv_target)
 PB_KERNEL(st_pj_init)
 PB_KERNEL(st_pj_round)
 PB_KERNEL(st_pj_calls)
-PB_KERNEL(st_reach_max)
-PB_KERNEL(st_reach_prefix)
-PB_KERNEL(st_reach_apply)
 
 #include "scan_tile.cuh"
 // one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
@@ -131,6 +127,21 @@ __global__ void __launch_bounds__(PB_BLOCK) k_chunk_solve(const Batch B) {
         const SolveRange R = chunk_range(B, g);
         if (B.flags & PB200_SOLVE_PLAIN) solve_contig_t<D128, true>(B, g.c, lane, 32, &R);
         else solve_contig_win<32, true>(B, g.c, lane, 0xFFFFFFFFu, &R);
+    }
+}
+// warp-per-item stages of the chunked path: WHAT = 0 chunk_prefix (contig), 1 reach_chunk pass 0 (chunk), 2 reach_chunk_prefix
+// (contig), 3 reach_chunk pass 2 (chunk)
+template <int WHAT>
+__global__ void __launch_bounds__(PB_BLOCK) k_chunk_warps(const Batch B, i64 n) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 i = warp; i < n; i += nwarps) {
+        if (WHAT == 0) chunk_prefix(B, (int)i, lane, 32);
+        else if (WHAT == 1) reach_chunk(B, (i32)i, 0, lane, 32);
+        else if (WHAT == 2) {
+            if (B.ch_cnt[i + 1] > B.ch_cnt[i]) reach_chunk_prefix(B, (int)i, lane, 32);
+        } else reach_chunk(B, (i32)i, 2, lane, 32);
     }
 }
 // the one-warp sweep for the chunked contigs whose assembled distances failed a check
@@ -451,6 +462,19 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         ctx->launches++;                                                                         \
         CK(cudaGetLastError());                                                                  \
     } while (0)
+#define PB_RUN_CHUNK_WARPS(what_, name_, n_)                                                     \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = name_;                                                                         \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        k_chunk_warps<what_><<<grid_for(ctx, (i64)(n_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream>>>(B, (i64)(n_)); \
+        cudaEventRecord(t_.b, ctx->stream);                                                      \
+        ctx->times.push_back(t_);                                                                \
+        ctx->launches++;                                                                         \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
 #define PB_RUN_FALLBACK(nc_)                                                                     \
     do {                                                                                         \
         StageTime t_;                                                                            \
@@ -613,6 +637,17 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
     do {                                                                 \
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_fallback(B, c_, 0, 1);  \
         ctx->launches++;                                                 \
+    } while (0)
+#define PB_RUN_CHUNK_WARPS(what_, name_, n_)                                                      \
+    do {                                                                                          \
+        for (i64 i_ = 0; i_ < (i64)(n_); i_++) {                                                  \
+            if ((what_) == 0) chunk_prefix(B, (int)i_, 0, 1);                                     \
+            else if ((what_) == 1) reach_chunk(B, (i32)i_, 0, 0, 1);                              \
+            else if ((what_) == 2) {                                                              \
+                if (B.ch_cnt[i_ + 1] > B.ch_cnt[i_]) reach_chunk_prefix(B, (int)i_, 0, 1);        \
+            } else reach_chunk(B, (i32)i_, 2, 0, 1);                                              \
+        }                                                                                         \
+        ctx->launches++;                                                                          \
     } while (0)
 #define PB_SIDE_BEGIN()
 #define PB_SIDE_END()
@@ -896,6 +931,8 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     B.ch_warm = ctx->ch_warm;
     B.ch_margin = ctx->ch_margin;
     B.ch_long = ctx->ch_long;
+    // a small batch leaves most of the GPU idle: then every contig longer than one chunk's sweep is worth cutting
+    if (n_contigs < 1024 && B.ch_long > B.ch_warm + B.ch_core + B.ch_margin) B.ch_long = B.ch_warm + B.ch_core + B.ch_margin;
 #ifndef PB_HOSTSIM
     CK(cudaSetDevice(ctx->device));
     ctx->times.clear();

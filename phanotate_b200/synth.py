@@ -134,3 +134,8 @@ def stress_contigs(n: int = 64, seed: int = 7):
             arr[up] = arr[up] & 0xDF
         out.append(("stress%d" % k, arr.tobytes()))
     return out
+
+
+def long_contig(nwin: int = 200) -> bytes:
+    """BASELINE.json config 5: ONE contig of nwin x 50 kb (200 -> 10 Mb), the config-4 windows 10**6 .. joined."""
+    return b"".join(synth4_contig(10 ** 6 + k) for k in range(nwin))

@@ -7,7 +7,7 @@ from phanotate_b200.engine import Engine
 from phanotate_b200 import synth, _native as N
 nwin = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 geos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]] or [(256, 768, 64, 4096)]
-seq = b"".join(synth.synth4_contig(10**6 + k) for k in range(nwin))
+seq = synth.long_contig(nwin)
 e = Engine(0)
 out = {"bp": len(seq)}
 ref = None
