@@ -159,6 +159,11 @@ int pb200_get_orf_int_weights(pb200_ctx* ctx, uint32_t* out);
 /* the same for every overlap edge (n_overlap_edges entries, in edge order): trunc(score_overlap * 1000),
  * INT64_MAX where it needs more than 62 bits (the solver then uses the wide value) */
 int pb200_get_overlap_int_weights(pb200_ctx* ctx, int64_t* out);
+/* Orf.hold (orfs.py:84; functions.py:286-298: the product over the ORF's codons of ((1-pstop)**pos_max[i])**pos_min[j],
+ * before Orf.score() -- orfs.py:122-127 -- inverts it) for every ORF, in pb200_get_orfs order.  Needs a PB200_LITERAL run:
+ * a certified run never forms the product. */
+int pb200_get_orf_holds(pb200_ctx* ctx, pb200_dec* out);
+
 /* trunc(score_gap(len, 'same'|'diff') * 1000) for len = -2..300 per contig: 303 entries per contig each */
 int pb200_get_gap_int_weights(pb200_ctx* ctx, int64_t* same, int64_t* diff);
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out);

@@ -80,7 +80,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_get_orf_int_weights.argtypes = [vp, vp]
     lib.pb200_get_overlap_int_weights.argtypes = [vp, vp]
     lib.pb200_get_gap_int_weights.argtypes = [vp, vp, vp]
-    for f in ("pb200_get_calls", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_get_edges"):
+    for f in ("pb200_get_calls", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_get_edges", "pb200_get_orf_holds"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pb200_build_edges.argtypes = [vp]
     lib.pb200_bellman_ford.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]
@@ -111,7 +111,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
 
 EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_upload", "pb200_set_contig_base", "pb200_set_chunking", "pb200_sizes", "pb200_stats",
            "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_gap_int_weights", "pb200_get_calls",
-           "pb200_get_contigs", "pb200_get_orfs", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
+           "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_connect", "pb200_stage_times", "pb200_stage_gaps", "pb200_launch_count", "pb200_last_run_ms",
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes", "pb200_fasta_count",
            "pb200_fasta_parse", "pb200_format_tabular"]

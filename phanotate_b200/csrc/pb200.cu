@@ -1176,6 +1176,19 @@ int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out) {
     return 0;
 }
 
+// Orf.hold (orfs.py:84, functions.py:286-298): the per-codon product before Orf.score() inverts it, for every ORF in
+// pb200_get_orfs order.  Only a PB200_LITERAL run keeps it for every ORF (a certified run never forms it).
+int pb200_get_orf_holds(pb200_ctx* ctx, pb200_dec* out) {
+    if (!ctx || !ctx->have) return -2;
+    Batch& B = ctx->B;
+    if (!B.lit_all || !(B.flags & PB200_LITERAL)) {
+        ctx->err = "pb200_get_orf_holds needs a PB200_LITERAL run";
+        return -2;
+    }
+    if (B.no > 0) PB_TO_HOST(out, B.o_hold, (size_t)B.no * sizeof(Dec));
+    return 0;
+}
+
 int pb200_get_nodes(pb200_ctx* ctx, pb200_node* out) {
     if (!ctx || !ctx->have) return -2;
     Batch& B = ctx->B;

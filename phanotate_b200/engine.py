@@ -69,6 +69,7 @@ class Result:
 
     def __init__(self, engine, names=None):
         self._e = engine
+        self._gen = engine._generation            # the context's tables belong to this run only until the next one starts
         self.names = names
         sz = np.zeros(8, dtype=np.int64)
         engine._ck(engine.lib.pb200_sizes(engine.ctx, sz.ctypes.data))
@@ -87,9 +88,15 @@ class Result:
         self.stage_ms = engine._stage_times()
 
     # lazily fetched tables -- only valid to request before the engine runs the next batch
+    def _live(self, what):
+        if self._gen != self._e._generation:
+            raise PhanotateError("Result.%s requested after the engine ran another batch: the context holds that batch's "
+                                 "tables now (fetch_all() before the next run keeps them)" % what)
+
     @property
     def orfs(self):
         if self._orfs is None:
+            self._live("orfs")
             self._orfs = np.zeros(self.n_orfs, dtype=N.ORF)
             self._e._ck(self._e.lib.pb200_get_orfs(self._e.ctx, self._orfs.ctypes.data))
         return self._orfs
@@ -97,6 +104,7 @@ class Result:
     @property
     def nodes(self):
         if self._nodes is None:
+            self._live("nodes")
             self._nodes = np.zeros(self.n_nodes, dtype=N.NODE)
             self._e._ck(self._e.lib.pb200_get_nodes(self._e.ctx, self._nodes.ctypes.data))
         return self._nodes
@@ -104,6 +112,7 @@ class Result:
     @property
     def edges(self):
         if self._edges is None:
+            self._live("edges")
             self._e._ck(self._e.lib.pb200_build_edges(self._e.ctx))
             sz = np.zeros(8, dtype=np.int64)
             self._e._ck(self._e.lib.pb200_sizes(self._e.ctx, sz.ctypes.data))
@@ -111,8 +120,16 @@ class Result:
             self._e._ck(self._e.lib.pb200_get_edges(self._e.ctx, self._edges.ctypes.data))
         return self._edges
 
+    def orf_holds(self):
+        """Orf.hold per ORF (Decimal) -- only after a literal=True run."""
+        self._live("orf_holds")
+        raw = np.zeros(self.n_orfs, dtype=N.DEC)
+        self._e._ck(self._e.lib.pb200_get_orf_holds(self._e.ctx, raw.ctypes.data))
+        return [N.dec_to_decimal(r) for r in raw]
+
     def orf_int_weights(self):
         """trunc(Orf.weight*1000) per ORF as Python ints -- what the solver used (request before .orfs)."""
+        self._live("orf_int_weights")
         raw = np.zeros((self.n_orfs, 8), dtype=np.uint32)
         self._e._ck(self._e.lib.pb200_get_orf_int_weights(self._e.ctx, raw.ctypes.data))
         out = []
@@ -125,12 +142,14 @@ class Result:
 
     def overlap_int_weights(self):
         """trunc(score_overlap*1000) per overlap edge (int64; INT64_MAX marks a wider value)."""
+        self._live("overlap_int_weights")
         out = np.zeros(self.n_overlaps, dtype=np.int64)
         self._e._ck(self._e.lib.pb200_get_overlap_int_weights(self._e.ctx, out.ctypes.data))
         return out
 
     def gap_int_weights(self):
         """(same, diff): trunc(score_gap(len)*1000) for len = -2..300, one row of 303 per contig."""
+        self._live("gap_int_weights")
         same = np.zeros((self.n_contigs, 303), dtype=np.int64)
         diff = np.zeros((self.n_contigs, 303), dtype=np.int64)
         self._e._ck(self._e.lib.pb200_get_gap_int_weights(self._e.ctx, same.ctypes.data, diff.ctypes.data))
@@ -140,8 +159,16 @@ class Result:
         self.orfs, self.nodes, self.edges
         return self
 
+    @staticmethod
+    def fatal(err: int) -> bool:
+        """Does this contig's error word stop its output?  (ERR_NOPATH alone does not: no source->target path = no calls.)"""
+        return bool(int(err) & ~N.ERR_NOPATH)
+
     def check(self, contig: int | None = None):
-        """Raise what the reference would have raised for a contig (or for any contig)."""
+        """Raise what the reference would have raised for a contig (or for any contig): KeyError for a letter outside
+        the IUPAC alphabet (functions.py:20-24), ValueError for parallel edges (graphs.py:73-74) and for the Orfs.get_orf
+        lookup (orfs.py:62-69).  Anything else this implementation cannot finish (edge weights beyond 256 bits, see
+        DESIGN.md: known limits) raises PhanotateError."""
         cs = self.contigs if contig is None else self.contigs[contig:contig + 1]
         for i, c in enumerate(cs):
             err = int(c["err"])
@@ -152,6 +179,12 @@ class Result:
                 raise KeyError("contig %d: letter outside the IUPAC alphabet (functions.rev_comp)" % k)
             if err & N.ERR_PARALLEL:
                 raise ValueError("parallel edges are forbidden")
+            if err & N.ERR_LOOKUP:
+                raise ValueError("contig %d: orf not found (Orfs.get_orf)" % k)
+            if err & (N.ERR_OVERFLOW | N.ERR_RANGE):
+                raise PhanotateError("contig %d: an edge weight is beyond this build's 256-bit exact range (~1e74; an ORF "
+                                     "of several kb in AT-rich sequence) -- the reference has no such limit "
+                                     "(device error bits 0x%x)" % (k, err))
             if err & N.ERR_NOPATH and not (err & ~N.ERR_NOPATH):
                 continue                        # no source->target path: no calls (undefined in the reference)
             raise PhanotateError("contig %d: device error bits 0x%x" % (k, err))
@@ -174,6 +207,7 @@ class Engine:
             raise RuntimeError("phanotate_b200: cannot open CUDA device %d (no CPU fallback exists)" % device)
         self.ctx = ctx
         self.device = device
+        self._generation = 0
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -216,6 +250,7 @@ class Engine:
             params = make_params()
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._generation += 1
         self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                     params.ctypes.data,
                                     (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) |

@@ -69,21 +69,34 @@ def tabular_text(res, names, lib=None) -> bytes:
         cap = -got + 64
 
 
-def write_tabular(res, names, out, check=False, lib=None):
-    """Writes tabular_text to a text stream.  check=True raises what the reference would have raised for a contig
-    (KeyError / ValueError) when its turn comes, after the blocks of the contigs before it were written -- like the
-    reference's per-locus loop."""
-    bad = [k for k in range(len(names)) if int(res.contigs[k]["err"])] if check else []
+def write_tabular(res, names, out, check=False, lib=None, skipped=None):
+    """Writes tabular_text to a text stream.  check=True handles a contig the run could not finish when its turn comes,
+    after the blocks of the contigs before it were written -- like the reference's per-locus loop: what the reference
+    would have raised (KeyError / ValueError) is raised; a contig that only this implementation cannot finish
+    (PhanotateError: edge weights beyond the exact range) is left out, reported in `skipped` (a list, if given) and on
+    stderr, and the contigs after it are still written.  A contig without a source->target path prints its header
+    and no rows, as it does with the other output formats."""
+    import sys
+    from .engine import PhanotateError, Result
+    bad = [k for k in range(len(names)) if Result.fatal(res.contigs[k]["err"])] if check else []
     if not bad:
         out.write(tabular_text(res, names, lib).decode())
         return
 
-    class _Head:                                   # the contigs before the first failing one
+    class _Part:                                   # a run of consecutive contigs
         pass
-    k = bad[0]
-    head = _Head()
-    head.contigs = res.contigs[:k]
-    head.calls = res.calls
-    out.write(tabular_text(head, names[:k], lib).decode())
-    res.check(k)
-    raise RuntimeError("contig %d: device error bits 0x%x" % (k, int(res.contigs[k]["err"])))
+    at = 0
+    for k in bad + [len(names)]:
+        if k > at:
+            part = _Part()
+            part.contigs = res.contigs[at:k]
+            part.calls = res.calls
+            out.write(tabular_text(part, names[at:k], lib).decode())
+        if k < len(names):
+            try:
+                res.check(k)
+            except PhanotateError as e:
+                sys.stderr.write("Warning: %s: %s; contig left out\n" % (names[k], e))
+                if skipped is not None:
+                    skipped.append(k)
+        at = k + 1

@@ -44,8 +44,10 @@ def get_orfs(locus):
     """functions.py:143-303: six-frame scan + scoring of one locus -> Orfs (stop -> {start -> Orf})."""
     dna = locus.seq().lower()
     params = make_params(locus.start_codons, locus.stop_codons, locus.min_orf_len)
-    res = engine().run([dna.encode()], params).fetch_all()
+    # literal=True: the reference's Decimal chain for every ORF inside the run, which also keeps Orf.hold (orfs.py:84)
+    res = engine().run([dna.encode()], params, literal=True).fetch_all()
     res.check(0)
+    holds = res.orf_holds()
     my_orfs = Orfs(locus)
     my_orfs.seq = dna
     my_orfs.contig_length = len(dna)
@@ -65,6 +67,7 @@ def get_orfs(locus):
             length = start + 2 - stop + 1
         o = Orf(start, stop, length, frame, seq, rbs, int(r["rbs_score"]), my_orfs.start_codons, my_orfs.stop_codons)
         o.pstop = N.dec_to_decimal(r["pstop"])
+        o.hold = holds[i]                                          # functions.py:286-298
         o.weight = N.dec_to_decimal(r["weight"])
         o.weight_rbs = float(c["training_rbs"][o.rbs_score]) / float(c["background_rbs"][o.rbs_score])
         my_orfs._insert(o)

@@ -61,7 +61,11 @@ class Orf:
         self.start_codons, self.stop_codons = start_codons, stop_codons
         self.pstop = None
         self.weight = 1
+        self.weight_start = 1
         self.weight_rbs = 1
+        self.hold = 1                  # product over the codons (functions.py:286-298); filled from the device (csrc/hold.cuh)
+        self.gcfp_mins = 1
+        self.gcfp_maxs = 1
 
     def start_codon(self):
         return self.seq[0:3]
@@ -76,8 +80,15 @@ class Orf:
         return self.stop_codon() in self.stop_codons
 
     def score(self):
-        """weight is already final: Orf.score() ran on the device (csrc/hold.cuh: hold_run)."""
-        return None
+        """orfs.py:122-127: weight = -(1/hold x start-codon weight x Decimal(str(weight_rbs))).  The device already ran this
+        (csrc/hold.cuh: st_orf_finish) and functions.get_orfs stored its result; calling it again recomputes the same
+        Decimal from `hold`."""
+        from decimal import Decimal
+        s = 1 / self.hold
+        if self.start_codon() in self.start_codons:
+            s = s * self.start_codons[self.start_codon()]
+        s = s * Decimal(str(self.weight_rbs))
+        self.weight = -s
 
     def __repr__(self):
         return "%s(%r,%r,%r,%r,%r)" % (self.__class__.__name__, self.start, self.stop, self.frame,

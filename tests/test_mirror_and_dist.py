@@ -71,6 +71,20 @@ def _check(name):
     o = next(orfs.iter_orfs())
     assert o.has_stop() or o.stop + 2 >= orfs.contig_length - 2 or o.frame < 0
     assert orfs.get_orf(o.start, o.stop) is o and orfs.other_end[o.start] == o.stop
+    # Orf.hold (orfs.py:84) comes from the device's literal chain; Orf.score() (orfs.py:122-127) recomputed from it in Python
+    # must give the device's weight
+    import hashlib
+    import json
+    from helpers import GOLDEN
+    gm = json.load(open(os.path.join(GOLDEN, "mirror.json")))["holds"]
+    holds = [str(x.hold) for x in orfs.iter_orfs()]
+    if name in gm:                                   # goldens from the reference's own get_orfs (make_mirror_golden.py)
+        assert len(holds) == gm[name]["n"] and holds[:3] == gm[name]["first"]
+        assert hashlib.md5(",".join(holds).encode()).hexdigest() == gm[name]["md5"]
+    for x in orfs.iter_orfs():
+        w = x.weight
+        x.score()
+        assert x.weight == w and str(x.weight) == str(w)
 
 
 @pytest.fixture()
@@ -90,6 +104,28 @@ def sim_engine():
 @pytest.mark.parametrize("name", ["phiX174", "stress13", "stress26", "lambda"])
 def test_mirror_driven_like_reference_cpu(sim_engine, name):
     _check(name)
+
+
+def test_gcframe_class_matches_the_reference():
+    """GCframe.add_base / _close / get (gc_frame_plot.py:29-74) against md5s made with the reference's class
+    (tests/golden/make_mirror_golden.py), including the second get() that closes and appends again"""
+    import hashlib
+    import json
+    import random
+    from helpers import GOLDEN
+    from phanotate_modules.gc_frame_plot import GCframe, max_idx, min_idx
+    gm = json.load(open(os.path.join(GOLDEN, "mirror.json")))["gcframe"]
+    for n, want in gm.items():
+        rnd = random.Random(1000 + int(n))
+        g = GCframe()
+        for ch in "".join(rnd.choice("acgt") for _ in range(int(n))):
+            g.add_base(ch)
+        first = hashlib.md5(repr(g.get()).encode()).hexdigest()
+        assert [first, hashlib.md5(repr(g.get()).encode()).hexdigest()] == want, n
+    assert len(gm) >= 10
+    assert [max_idx(3, 2, 1), max_idx(1, 3, 2), max_idx(1, 1, 1), min_idx(3, 2, 1), min_idx(1, 1, 1), min_idx(2, 1, 1)] == [1, 2, 3, 3, 1, 2]
+    with pytest.raises(KeyError):
+        GCframe().add_base("n")                      # the reference's frequency dict has no such key either
 
 
 def test_cli_tabular_output_cpu(sim_engine, capsys):
