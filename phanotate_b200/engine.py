@@ -187,6 +187,10 @@ class Result:
                                      "(device error bits 0x%x)" % (k, err))
             if err & N.ERR_NOPATH and not (err & ~N.ERR_NOPATH):
                 continue                        # no source->target path: no calls (undefined in the reference)
+            if err & N.ERR_TIES:
+                raise PhanotateError("contig %d: more exact ties in the shortest path than this build settles in the "
+                                     "reference's edge order (256 per contig; exact tandem repeats) -- no calls rather "
+                                     "than calls that might differ (device error bits 0x%x)" % (k, err))
             raise PhanotateError("contig %d: device error bits 0x%x" % (k, err))
 
     def call_rows(self, contig: int):

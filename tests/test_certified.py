@@ -39,6 +39,7 @@ def _both(sim, seqs):
     wf = fast.orf_int_weights()                       # before .orfs triggers the lazy literal completion
     ovf = fast.overlap_int_weights()
     gsf, gdf = fast.gap_int_weights()
+    fast.orfs, fast.nodes                             # (lazy tables: fetched before the context runs the next batch)
     lit = sim.run(seqs, literal=True)
     assert np.array_equal(ovf, lit.overlap_int_weights())
     gsl, gdl = lit.gap_int_weights()

@@ -1,4 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the reference goldens and the oracle -- needs a B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -89,6 +91,7 @@ def test_certified_integers_equal_literal_on_gpu(eng):
     assert np.array_equal(ovf, lit.overlap_int_weights())
     assert fast.n_literal_overlaps < fast.n_overlaps // 50
     wl = lit.orf_int_weights()
+    lit.orfs                                          # (lazy table: fetched before the context runs the next batch)
     assert wf == wl
     assert fast.n_literal_presolve < fast.n_orfs // 20 and lit.n_literal_presolve == lit.n_orfs
     for col in ("contig", "left", "right", "strand", "score"):
@@ -109,7 +112,7 @@ def test_tiled_scan_equals_reference_scan(eng):
     from phanotate_b200 import synth
     seqs = ([synth.synth4_contig(k) for k in range(8)] + [seq_of(n).encode() for n in STRESS] +
             [seq_of(n).encode() for n in ("T4", "phiX174", "lambda")] + [seq_of(n).encode() for n in STRESS[:20]])
-    a = eng.run(seqs)
+    a = eng.run(seqs).fetch_all()
     b = eng.run(seqs, flags=N.SCAN_REFERENCE)
     assert np.array_equal(a.contigs, b.contigs)
     assert np.array_equal(a.calls, b.calls)
@@ -140,6 +143,14 @@ def test_empty_and_tiny_contigs_inside_a_batch(eng):
         assert int(res.contigs[1]["err"]) & N.ERR_RANGE and int(res.contigs[0]["err"]) == 0 and int(res.contigs[6]["err"]) == 0
 
 
+def _oracle_rows(seq):
+    from oracle import phanotate_oracle as O
+    try:
+        return [r[:4] for r in O.call_contig(seq)[3]]
+    except KeyError:
+        return "KeyError"
+
+
 def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
     """300 random contigs of ragged length (60 .. 9000 bp, random composition, sprinkled IUPAC codes, lower/upper case):
     the default run (tiled scan, certified weights, 128-bit solve) against the plain statement of every stage at once
@@ -158,6 +169,7 @@ def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
         seqs.append(s.tobytes())
     a = eng.run(seqs)
     wa = a.orf_int_weights()
+    a.orfs, a.nodes                                   # (lazy tables: fetched before the context runs the next batch)
     b = eng.run(seqs, literal=True, flags=N.SCAN_REFERENCE | N.SOLVE_WIDE)
     assert wa == b.orf_int_weights()
     for col in ("contig", "left", "right", "strand", "score"):
@@ -165,6 +177,16 @@ def test_random_ragged_batch_fast_paths_equal_plain_paths(eng):
     assert np.array_equal(a.orfs, b.orfs) and np.array_equal(a.nodes, b.nodes)
     assert np.array_equal(a.contigs["err"], b.contigs["err"]) and np.array_equal(a.contigs["n_calls"], b.contigs["n_calls"])
     assert a.n_calls > 1000
+    # ... and against the oracle (CPU restatement of the reference, pinned to its goldens): every contig's call table
+    from oracle import phanotate_oracle as O
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(min(16, os.cpu_count() or 1)) as pool:
+        want = list(pool.map(_oracle_rows, [s.decode() for s in seqs], chunksize=8))
+    for k in range(len(seqs)):
+        if int(a.contigs[k]["err"]) & N.ERR_CHAR:
+            assert want[k] == "KeyError", k
+        else:
+            assert a.call_rows(k) == want[k], k
     # the windowed 128-bit sweep against its plain statement: same parents, same tie counts, same calls
     p = eng.run(seqs, flags=N.SOLVE_PLAIN)
     assert np.array_equal(a.calls, p.calls) and np.array_equal(a.contigs, p.contigs)
