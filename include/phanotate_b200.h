@@ -210,6 +210,33 @@ int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);
 int pb200_stage_gaps(pb200_ctx* ctx, const char** names, float* ms, int cap);
 /* number of kernels launched by the last pb200_run */
 int pb200_launch_count(pb200_ctx* ctx);
+/* stopwatch on the context's stream: pb200_mark records event k (0..3) behind everything queued so far; pb200_elapsed_ms
+ * waits for mark b and returns the device time between marks a and b (a region of several runs and gathers) */
+int pb200_mark(pb200_ctx* ctx, int32_t k);
+float pb200_elapsed_ms(pb200_ctx* ctx, int32_t a, int32_t b);
+
+/* ---- multi-GPU: one process per GPU, contigs sharded over the ranks (they are independent:
+ * phanotate.py:40-56 is a loop over loci), and ONE collective -- the gather of the ranks' call tables to rank 0.  Raw NCCL
+ * bound at run time (dlopen libnccl.so.2, or the path in PB200_NCCL_LIB); nothing else of the library needs NCCL. */
+/* rank 0: a fresh NCCL unique id, to be handed to every rank out of band (file, socket, environment) */
+int pb200_comm_unique_id(uint8_t out[128]);
+/* every rank: join the communicator on the context's device */
+int pb200_comm_init(pb200_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+int pb200_comm_destroy(pb200_ctx* ctx);
+/* gather of call rows to rank 0 on the context's stream.  parts[i] = DEVICE pointer to part_rows[i] pb200_call records
+ * (several contexts of one process: pass their pb200_device_calls); nparts = 0: the context's own table of its last run.
+ * counts_out[world] (host, every rank) = rows per rank; rank 0: *rows_dev = device pointer to all rows in rank order
+ * (valid until the next gather), *total = their number.  Exact row counts travel (an all-gather of one int64 per rank,
+ * then one grouped send/receive), no padding. */
+int pb200_comm_gather_calls(pb200_ctx* ctx, const void* const* parts, const int64_t* part_rows, int32_t nparts,
+                            int64_t* counts_out, const pb200_call** rows_dev, int64_t* total);
+/* rank 0: rows [first, first+n) of the last gather -> host */
+int pb200_comm_fetch_gathered(pb200_ctx* ctx, int64_t first, int64_t n, pb200_call* out);
+/* in-place reduction of n <= 64 doubles over the ranks (op 0 sum, 1 max); barrier */
+int pb200_comm_allreduce(pb200_ctx* ctx, double* vals, int32_t n, int32_t op);
+int pb200_comm_barrier(pb200_ctx* ctx);
+/* NCCL version code (e.g. 22703) or -1 when NCCL is not available */
+int pb200_comm_nccl_version(void);
 /* device time of the whole last pb200_run (events at its first and last operation on the stream) */
 float pb200_last_run_ms(pb200_ctx* ctx);
 /* device address of the call table of the last run (n_calls rows), for zero-copy hand-off to a

@@ -101,6 +101,17 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_fasta_parse.restype = ctypes.c_int64
     lib.pb200_format_tabular.argtypes = [vp, vp, i32, vp, vp, vp, ctypes.c_int64]
     lib.pb200_format_tabular.restype = ctypes.c_int64
+    lib.pb200_mark.argtypes = [vp, i32]
+    lib.pb200_elapsed_ms.argtypes = [vp, i32, i32]
+    lib.pb200_elapsed_ms.restype = ctypes.c_float
+    lib.pb200_comm_unique_id.argtypes = [vp]
+    lib.pb200_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.pb200_comm_destroy.argtypes = [vp]
+    lib.pb200_comm_gather_calls.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.pb200_comm_fetch_gathered.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
+    lib.pb200_comm_allreduce.argtypes = [vp, vp, i32, i32]
+    lib.pb200_comm_barrier.argtypes = [vp]
+    lib.pb200_comm_nccl_version.argtypes = []
     sz = (ctypes.c_int32 * 8)()
     lib.pb200_struct_sizes(sz)
     want = [DEC.itemsize, PARAMS.itemsize, CALL.itemsize, ORF.itemsize, NODE.itemsize, EDGE.itemsize, CONTIG.itemsize]
@@ -114,4 +125,6 @@ EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_connect", "pb200_stage_times", "pb200_stage_gaps", "pb200_launch_count", "pb200_last_run_ms",
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes", "pb200_fasta_count",
-           "pb200_fasta_parse", "pb200_format_tabular"]
+           "pb200_fasta_parse", "pb200_format_tabular", "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_destroy",
+           "pb200_comm_gather_calls", "pb200_comm_fetch_gathered", "pb200_comm_allreduce", "pb200_comm_barrier",
+           "pb200_comm_nccl_version", "pb200_mark", "pb200_elapsed_ms"]

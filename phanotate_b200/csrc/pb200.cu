@@ -319,6 +319,8 @@ struct pb200_ctx {
     bool scan_attr_set = false;
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
+    void* comm = nullptr;        // CommState (comm.inc) once pb200_comm_init ran
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 // wait for the context's stream.  PB200_BLOCKING_SYNC=1 (environment, read at pb200_create) makes the host thread sleep on
 // a blocking-sync event instead of spinning: for boxes with fewer cores than (ranks x lanes) host threads
@@ -880,8 +882,10 @@ int pb200_create(int device, pb200_ctx** out) {
     return 0;
 }
 
+int pb200_comm_destroy(pb200_ctx* ctx);
 void pb200_destroy(pb200_ctx* ctx) {
     if (!ctx) return;
+    pb200_comm_destroy(ctx);
 #ifndef PB_HOSTSIM
     cudaSetDevice(ctx->device);
     for (int k = 0; k < NPHASE; k++) cudaFree(ctx->ph[k].p);
@@ -895,6 +899,8 @@ void pb200_destroy(pb200_ctx* ctx) {
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    for (int k = 0; k < 4; k++)
+        if (ctx->marks[k]) cudaEventDestroy(ctx->marks[k]);
     if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
@@ -1043,6 +1049,33 @@ int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {
     if (!ctx) return -2;
     ctx->contig_base = base;
     return 0;
+}
+
+// Device-side stopwatch on the context's stream: pb200_mark(ctx, k) records event k (0..3) behind everything queued so far,
+// pb200_elapsed_ms(ctx, a, b) = time between two recorded marks (waits for b).  For timing a region of several runs and
+// gathers with CUDA events on the launching stream.
+int pb200_mark(pb200_ctx* ctx, int32_t k) {
+    if (!ctx || k < 0 || k > 3) return -2;
+#ifndef PB_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->marks[k]) CK(cudaEventCreate(&ctx->marks[k]));
+    CK(cudaEventRecord(ctx->marks[k], ctx->stream));
+#endif
+    return 0;
+}
+float pb200_elapsed_ms(pb200_ctx* ctx, int32_t a, int32_t b) {
+#ifndef PB_HOSTSIM
+    float v = -1.f;
+    if (!ctx || a < 0 || a > 3 || b < 0 || b > 3 || !ctx->marks[a] || !ctx->marks[b]) return -1.f;
+    if (cudaEventSynchronize(ctx->marks[b]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&v, ctx->marks[a], ctx->marks[b]) != cudaSuccess) return -1.f;
+    return v;
+#else
+    (void)ctx;
+    (void)a;
+    (void)b;
+    return -1.f;
+#endif
 }
 
 float pb200_last_run_ms(pb200_ctx* ctx) {
@@ -1584,5 +1617,7 @@ int pb200_stage_gaps(pb200_ctx* ctx, const char** names, float* ms, int cap) {
 }
 
 int pb200_launch_count(pb200_ctx* ctx) { return ctx ? ctx->launches : -2; }
+
+#include "comm.inc"
 
 }  // extern "C"

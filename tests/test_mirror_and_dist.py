@@ -192,35 +192,58 @@ def test_lpt_sharding_balances_and_covers():
 
 
 WORKER = r'''
+# two ranks (gloo on the CPU; NCCL inside the library on the GPUs): every rank runs ITS shard of a batch through the host
+# build, rank 0 assembles the gathered rows with the product's host logic (dist.rank_slices / dist.unshard_calls) and
+# compares with the whole batch run by one process
 import os, sys
-sys.path.insert(0, %r)
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
 import numpy as np, torch, torch.distributed as dist
-from phanotate_b200 import _native as N
-from phanotate_b200.dist import gather_call_tables
+from phanotate_b200 import _native as N, engine, dist as pdist
+from helpers import STRESS, seq_of, hostsim_path
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-n = [3, 0][rank] if world == 2 else rank + 1
-rows = np.zeros(n, dtype=N.CALL)
-rows["contig"] = rank; rows["left"] = np.arange(n) * 10 + 1; rows["right"] = rows["left"] + 92; rows["strand"] = 1
-mine = torch.from_numpy(rows.view(np.uint8).copy()) if n else torch.zeros(1, dtype=torch.uint8)
-out = gather_call_tables(mine, n, dist, rank, world)
+names = ["phiX174"] + STRESS[:9] + ["lambda"]
+seqs = [seq_of(n).encode() for n in names]
+parts = pdist.shard_contigs([len(s) for s in seqs], world)
+e = engine.Engine(0, lib_path=hostsim_path())
+mine = e.run([seqs[i] for i in parts[rank]]).calls
+cnt = torch.tensor([len(mine)], dtype=torch.int64)
+allc = [torch.zeros_like(cnt) for _ in range(world)]
+dist.all_gather(allc, cnt)
+counts = [int(c) for c in allc]
+width = max(counts) * N.CALL.itemsize
+buf = torch.zeros(width, dtype=torch.uint8)
+buf[:mine.nbytes] = torch.from_numpy(mine.view(np.uint8).copy())
+out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+dist.gather(buf, out, dst=0)
 if rank == 0:
-    got = [np.frombuffer(o.numpy().tobytes(), dtype=N.CALL) for o in out]
-    assert [len(g) for g in got] == [3, 0], [len(g) for g in got]
-    assert list(got[0]["left"]) == [1, 11, 21] and all(got[0]["contig"] == 0)
-    print("GATHER_OK")
+    rows = np.concatenate([np.frombuffer(o.numpy().tobytes()[:c * N.CALL.itemsize], dtype=N.CALL) for o, c in zip(out, counts)])
+    assert pdist.rank_slices(counts)[1] == (counts[0], counts[1])
+    whole = e.run(seqs).calls
+    got = pdist.unshard_calls(rows, counts, parts)
+    assert len(got) == len(whole) and np.array_equal(got, whole)
+    print("GATHER_OK", counts)
 dist.destroy_process_group()
 '''
 
 
 def test_call_table_gather_world_size_2_gloo(tmp_path):
     script = tmp_path / "w.py"
-    script.write_text(WORKER % ROOT)
+    script.write_text(WORKER % (ROOT, ROOT))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_product_package_does_not_import_torch():
+    """north_star: host code is Python over ctypes, no PyTorch -- not even for the multi-GPU gather (csrc/comm.inc is raw NCCL)"""
+    code = ("import sys; sys.path.insert(0, %r); import phanotate_b200.engine, phanotate_b200.dist, phanotate_b200.fastio, "
+            "phanotate_b200.mirror, phanotate_b200.synth, phanotate_modules.functions, phanotate, fastpathz, phanotate_connect; "
+            "assert 'torch' not in sys.modules, 'torch imported'; print('NO_TORCH')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "NO_TORCH" in r.stdout, r.stdout + r.stderr
 
 
 def test_pipelined_engine_equals_single_context():
