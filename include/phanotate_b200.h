@@ -74,7 +74,7 @@ typedef struct pb200_node {     /* Node (nodes.py:2-21); ids are global over the
 } pb200_node;
 
 enum { PB200_EDGE_ORF = 0, PB200_EDGE_GAP = 1, PB200_EDGE_OVERLAP = 2, PB200_EDGE_BRIDGE = 3,
-       PB200_EDGE_SOURCE = 4, PB200_EDGE_TARGET = 5 };
+       PB200_EDGE_SOURCE = 4, PB200_EDGE_TARGET = 5, PB200_EDGE_TRNA = 6 /* the -20 edge of a tRNA hit */ };
 #define PB200_NODE_SOURCE (-2)
 #define PB200_NODE_TARGET (-3)
 typedef struct pb200_edge {     /* Edge (edges.py:3-23) */
@@ -136,6 +136,15 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
  * PB200_REUSE_INPUT).  With several contexts this lets the copies go one after the other while other contexts compute. */
 int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int32_t n_contigs);
 
+/* tRNA masking (functions.py:457-509 add_trnas + the tRNA branch of the connect loop, functions.py:388-399).  The
+ * reference runs aragorn / tRNAscan-SE itself; here the caller runs them (or anything else) and hands over the hit list
+ * for the following runs: hit k lies on contig contig[k] (index inside the batch, ascending) from start[k] to stop[k],
+ * 1-based, start > stop on the reverse strand -- the [start, stop] pairs add_trnas collects, in its order.  Every hit
+ * becomes a node pair (gene 'tRNA', frame +-4) joined by an edge of weight -20 and connected by 'same'-scored gap edges
+ * to every exit / entry node within 500 bp.  A tRNA on the shortest path comes back as a call row with strand +-2 and
+ * score -20.  pb200_get_nodes returns the tRNA nodes behind the regular ones (orf = -1 - k).  n = 0 clears the list. */
+int pb200_set_trnas(pb200_ctx* ctx, const int32_t* contig, const int32_t* start, const int32_t* stop, int32_t n);
+
 /* number added to the contig column of the call rows of the following runs (default 0): for a caller that cuts one
  * batch into groups for several contexts and wants the rows numbered in the whole batch */
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base);
@@ -151,7 +160,7 @@ int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margi
 int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
 /* out[0] = ORFs whose weight went through the literal Decimal chain before the solve, out[1] = after
  * it (called CDS), out[2] = overlap edges through the literal power, out[3] = chunks the long contigs were solved
- * in, out[4] = long contigs whose chunked solve failed its check and was redone by one sweep; rest reserved */
+ * in, out[4] = long contigs whose chunked solve failed its check and was redone by one sweep, out[5] = tRNA hits; rest reserved */
 int pb200_stats(pb200_ctx* ctx, int64_t out[8]);
 /* the integer weight the solver used for every ORF edge: trunc(Orf.weight * 1000) (edges.py:22) as
  * 8 little-endian 32-bit limbs, two's complement, per ORF */

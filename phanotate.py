@@ -34,7 +34,11 @@ def main(argv=None):
     args = file_handling.get_args(File, argv)
     if args.format == 'fasta':
         args.format = 'fna'
-    if args.format == 'tabular' and not args.dump:
+    import shutil
+    have_trna_tools = bool(shutil.which("aragorn") or shutil.which("tRNAscan-SE"))
+    if not have_trna_tools:
+        sys.stderr.write("Warning: tRNAscan or Aragorn were not found, proceding without tRNA masking.\n")
+    if args.format == 'tabular' and not args.dump and not have_trna_tools:
         # batch fast path: vectorised FASTA ingest -> one engine run -> the tabular text of every locus
         from phanotate_b200 import fastio
         eng = functions.engine()
@@ -54,7 +58,13 @@ def main(argv=None):
     loci = list(genbank)
     params = make_params(args.start_codons, args.stop_codons, args.min_orf_len)
     for a, b in batches([len(l.seq()) for l in loci], limit):
-        res = functions.engine().run([l.seq().encode() for l in loci[a:b]], params)
+        # tRNA masking (functions.py:457-509): the two programs run on the host, locus by locus like in the reference; their
+        # hits go into the batch run
+        trnas = []
+        if have_trna_tools:
+            for k, locus in enumerate(loci[a:b]):
+                trnas += [(k, s, e) for s, e in functions.find_trnas(locus.seq().lower()) or []]
+        res = functions.engine().run([l.seq().encode() for l in loci[a:b]], params, trnas=trnas)
         for k, locus in enumerate(loci[a:b]):
             locus.start_codons, locus.stop_codons, locus.min_orf_len = args.start_codons, args.stop_codons, args.min_orf_len
             try:
@@ -63,15 +73,15 @@ def main(argv=None):
                 sys.stderr.write("Warning: %s: %s; contig left out\n" % (locus.name(), e))
                 continue
             if args.dump:
-                sys.stderr.write("Warning: tRNAscan or Aragorn were not found, proceding without tRNA masking.\n")
                 sys.stdout.writelines(mirror.ContigGraph(res, k).dump_lines())
                 return 0
             c = res.contigs[k]
             for r in res.calls[c["call_off"]:c["call_off"] + c["n_calls"]]:
                 weight = float(r["score"])                         # '%E' % Decimal goes through float() as well
                 strand = 1 if r["strand"] > 0 else -1
+                gene = 'tRNA' if abs(int(r["strand"])) == 2 else 'CDS'     # left.gene (phanotate.py:71)
                 pairs = [[int(r["left"]), int(r["right"]) - 2]]   # add_feature adds the 2 back (locus.py:30)
-                feature = locus.add_feature('CDS', strand, pairs, {'note': ['score:%E' % weight]})
+                feature = locus.add_feature(gene, strand, pairs, {'note': ['score:%E' % weight]})
                 feature.weight = '%E' % weight
             locus.write(args)
     return 0

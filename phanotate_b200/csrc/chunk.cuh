@@ -65,7 +65,8 @@ PB_HD void chunk_viol(const Batch& B, int c) { PB_ATOMIC_OR(&B.cs[c].chunk_viol,
 PB_HDN void st_chunk_plan(const Batch& B, i64 c) {
     if (c >= B.nc) return;
     const i32 n = B.cnode[c + 1] - B.cnode[c];
-    const u32 cnt = (n > B.ch_long && !(B.flags & PB200_SOLVE_NOCHUNK)) ? (u32)((n + B.ch_core - 1) / B.ch_core) : 0u;
+    const bool trna = B.nt > 0 && B.ctrna[c + 1] > B.ctrna[c];        // tRNA contigs take the plain sweep (trna.cuh)
+    const u32 cnt = (n > B.ch_long && !trna && !(B.flags & PB200_SOLVE_NOCHUNK)) ? (u32)((n + B.ch_core - 1) / B.ch_core) : 0u;
     B.ch_cnt[c] = cnt;
     if (cnt) PB_ATOMIC_ADD(B.lit_cnt + 3, cnt);
 }
@@ -358,7 +359,7 @@ PB_HDN void st_pj_calls(const Batch& B, i64 v64) {
     if (!B.pj_mark[v]) return;
     const int kind = (int)(B.n_pk[v] & 3);
     const i32 d = B.pj_depth[v];
-    const i32 cap = B.corf[c + 1] - B.corf[c];
+    const i32 cap = call_base(B, c + 1) - call_base(B, c);
     const i32 root = B.pj_jump[v];
     if (B.parent[root] != -2) {                     // the chain does not end at the source
         PB_ATOMIC_OR(&cs->err, (u32)ERR_INTERNAL);
@@ -373,7 +374,7 @@ PB_HDN void st_pj_calls(const Batch& B, i64 v64) {
         return;
     }
     const i32 e = B.parent[v];
-    B.call_tmp[B.corf[c] + (d >> 1)] = (kind == K_RSTART) ? B.n_orf[v] : B.n_orf[e];
+    B.call_tmp[call_base(B, c) + (d >> 1)] = (kind == K_RSTART) ? B.n_orf[v] : B.n_orf[e];
     if (v == B.tparent[c]) {
         B.call_cnt[c] = (u32)((d >> 1) + 1);
         cs->n_calls = (d >> 1) + 1;

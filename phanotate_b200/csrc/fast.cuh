@@ -162,6 +162,7 @@ PB_HD bool certified_score(const DD& V, int n, double* score) {
 PB_HDN void st_lit_calls(const Batch& B, i64 k) {
     if (k >= B.ncalls) return;
     const i32 oi = B.call_orf[k];
+    if (oi < 0) return;                       // a tRNA call: weight -20, nothing owed
     if (B.o_lit[oi] == 0 && !(B.flags & PB200_CALL_WEIGHTS)) {
         const bool rev = B.o_frame[oi] < 0;
         double sc;

@@ -12,6 +12,8 @@
 #include "dec2double.cuh"
 
 PB_HD bool kind_is_entry(int k) { return k == K_FSTART || k == K_RSTOP; }
+// first entry of contig c's region of call_tmp: its ORFs and its tRNAs can all be on the path
+PB_HD i32 call_base(const Batch& B, int c) { return B.corf[c] + (B.nt > 0 ? B.ctrna[c] : 0); }
 PB_HD int contig_of_node(const Batch& B, i32 ni) { return B.n_contig[ni]; }
 
 // Stage 8: other_end[] and the pstop used for overlap averaging, per node, with the reference's
@@ -246,7 +248,7 @@ PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
                 int len = B.n_pos[r] - B.n_pos[l] - 3;
                 if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
                 if (fill) {
-                    B.n_brs[l] = 1;
+                    B.n_brs[l] |= 1;
                     B.br_src[k] = l;
                     B.br_dst[k] = r;
                     // score_gap(len > 300) = g**100 + len (functions.py:40-41): its integer is len*1000 + a per-contig constant
@@ -443,29 +445,35 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveR
     const u32* pk = B.n_pk;                       // position << 4 | kind | frame << 2
     u32 ties = 0;
     bool okw = true;
-    for (i32 i = nb + lane; i < ne; i += NL) {
-        const u32 w = pk[i];
-        T d0 = D::inf();
-        i32 p0 = -1;
-        u8 f0 = 0;
-        // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
-        if ((int)(w >> 4) - base <= 2000 && kind_is_entry((int)(w & 3))) {
-            bool o;
-            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4) - base, false, &o));
-            okw = okw && o;
-            p0 = -2;
-            f0 = 1;
+    // tRNA nodes of the contig (trna.cuh): behind the regular nodes of the batch, edges in the explicit list te_*
+    const bool TR = !CH && B.nt > 0 && B.ctrna[c + 1] > B.ctrna[c];
+    const i32 tnb = TR ? B.nn + 2 * B.ctrna[c] : 0, tne = TR ? B.nn + 2 * B.ctrna[c + 1] : 0;
+    const u32 teb = TR ? B.te_cnt[2 * B.ctrna[c]] : 0, tee = TR ? B.te_cnt[2 * B.ctrna[c + 1]] : 0;
+    for (int part = 0; part < (TR ? 2 : 1); part++)
+        for (i32 i = (part ? tnb : nb) + lane; i < (part ? tne : ne); i += NL) {
+            const u32 w = pk[i];
+            T d0 = D::inf();
+            i32 p0 = -1;
+            u8 f0 = 0;
+            // source -> entry nodes within 2000 bp of the left end (functions.py:444-447)
+            if ((int)(w >> 4) - base <= 2000 && kind_is_entry((int)(w & 3))) {
+                bool o;
+                d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4) - base, false, &o));
+                okw = okw && o;
+                p0 = -2;
+                f0 = 1;
+            }
+            dist[i] = d0;
+            if (!CH) B.parent[i] = p0;
+            dirty[i] = f0;
         }
-        dist[i] = d0;
-        if (!CH) B.parent[i] = p0;
-        dirty[i] = f0;
-    }
     T tdist = D::inf();
     i32 tpar = -1;
     PB_SYNCWARP();
     const u32 brb = B.br_cnt[B.cnode[c]], bre = B.br_cnt[B.cnode[c + 1]];
     i32 i = nb;
-    int budget = 64 * (ne - nb) + 1024;
+    int budget = 64 * (ne - nb) + 1024 + (TR ? 4096 * (tne - tnb) : 0);
+    for (;;) {
     while (i < ne) {
         // next dirty node at or after i
 #ifdef __CUDA_ARCH__
@@ -547,13 +555,22 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveR
 #endif
             }
             // bridges (rare: n_brs flags the exit nodes that have any)
-            if (bre > brb && B.n_brs[u]) {
+            if (bre > brb && (B.n_brs[u] & 1)) {
                 for (u32 k = brb + lane; k < bre; k += NL) {
                     if (B.br_src[k] != u) continue;
                     const i32 v = B.br_dst[k];
                     if (CH && v >= ne) continue;
                     const T cur = dist[v];
                     relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.br_wint + k)), u, dirty);
+                }
+            }
+            // gap edges into tRNA entry nodes (functions.py:388-399)
+            if (TR && (B.n_brs[u] & 2)) {
+                for (u32 k = teb + lane; k < tee; k += NL) {
+                    if (B.te_src[k] != u) continue;
+                    const i32 v = B.te_dst[k];
+                    const T cur = dist[v];
+                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::from_i64(B.te_w[k])), u, dirty);
                 }
             }
             // exit -> target within 2000 bp of the right end (functions.py:448-451)
@@ -572,6 +589,53 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveR
         }
         PB_SYNCWARP();
         i = (rewind < u) ? rewind : u + 1;
+    }
+    if (!TR) break;
+    // the contig's tRNA nodes: every improved one pushes its explicit edges; an improvement of a regular node takes
+    // the sweep back to it, one of another tRNA node repeats this pass
+    i32 back = 0x7FFFFFFF;
+    bool again = false;
+    for (i32 t = tnb; t < tne; t++) {
+        if (!dirty[t]) continue;
+        if (--budget < 0) {
+            if (lane == 0) PB_ATOMIC_OR(&cs->err, (u32)ERR_INTERNAL);
+            break;
+        }
+        const T Du = dist[t];
+        const int kind = (int)(pk[t] & 3), pu = (int)(pk[t] >> 4);
+        PB_SYNCWARP();
+        if (lane == 0) dirty[t] = 0;
+        for (u32 k = teb + lane; k < tee; k += NL) {
+            if (B.te_src[k] != t) continue;
+            const i32 v = B.te_dst[k];
+            const T cur = dist[v];
+            if (relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::from_i64(B.te_w[k])), t, dirty)) {
+                if (v < ne) back = v < back ? v : back;
+                else again = true;
+            }
+        }
+        if (!kind_is_entry(kind) && L - pu <= 2000) {
+            bool o;
+            const T cand = D::add(Du, D::from_i64(gap_w64(B, c, L - pu, false, &o)));
+            okw = okw && o;
+            if (D::less(cand, tdist)) {
+                tdist = cand;
+                tpar = t;
+            } else if (lane == 0 && !D::is_inf(tdist) && D::eq(cand, tdist) && tpar != t) {
+                ties++;
+                D::tie(B, c, -3 - c, t, cand);
+            }
+        }
+        PB_SYNCWARP();
+    }
+#ifdef __CUDA_ARCH__
+    back = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)back);
+    again = __any_sync(0xFFFFFFFFu, again);
+#endif
+    if (budget < 0) break;
+    if (back < 0x7FFFFFFF) i = back;
+    else if (again) i = ne;
+    else break;
     }
     if (CH) return;
     if (ties) PB_ATOMIC_ADD(&cs->n_ties, ties);
@@ -728,7 +792,7 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask,
                 rewind = (i32)__reduce_min_sync(mask, (unsigned)rewind);
             }
             // bridges (rare: n_brs flags the exit nodes that have any)
-            if (bre > brb && B.n_brs[u]) {
+            if (bre > brb && (B.n_brs[u] & 1)) {
                 for (u32 k = brb + lane; k < bre; k += NL) {
                     if (B.br_src[k] != u) continue;
                     const i32 v = B.br_dst[k];
@@ -801,6 +865,8 @@ PB_HDN int tie_sigma_idx(const Batch& B, i32 a, i32 fam) {
 PB_HDN bool tie_sigma_less(const Batch& B, i32 a, i32 b) {
     if (a == b || a == -2) return false;
     if (b == -2) return true;
+    // tRNA nodes (indices from nn) are inserted by add_trnas after every CDS node, entry then exit per hit (functions.py:496-508)
+    if (a >= B.nn || b >= B.nn) return (a >= B.nn && b >= B.nn) ? a < b : b >= B.nn;
     const int ka = B.n_kind[a] & 3, kb = B.n_kind[b] & 3;
     const i32 fa = (ka == K_FSTOP || ka == K_RSTOP) ? a : B.n_mate[a];
     const i32 fb = (kb == K_FSTOP || kb == K_RSTOP) ? b : B.n_mate[b];
@@ -871,7 +937,7 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
     CStat* cs = B.cs + c;
     if (!cs->tie_head) return;
     const bool wide = contig_is_wide(B, c);
-    const i32 nodes = B.cnode[c + 1] - B.cnode[c];
+    const i32 nodes = B.cnode[c + 1] - B.cnode[c] + (B.nt > 0 ? 2 * (B.ctrna[c + 1] - B.ctrna[c]) : 0);
     i32 tv[TIE_MAXN], tf[TIE_MAXN];
     bool done[TIE_MAXN];
     int n = 0;
@@ -960,8 +1026,8 @@ PB_HDN void st_backtrack(const Batch& B, i64 c64) {
     if (contig_chunked(B, c)) return;             // chunk.cuh: st_pj_* trace the path of a long contig in parallel
     CStat* cs = B.cs + c;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
-    i32* out = B.call_tmp + B.corf[c];
-    const i32 cap = B.corf[c + 1] - B.corf[c];
+    i32* out = B.call_tmp + call_base(B, c);
+    const i32 cap = call_base(B, c + 1) - call_base(B, c);
     i32 n = 0;
     i32 x = B.tparent[c];
     if (x < 0) {
@@ -998,14 +1064,26 @@ PB_HDN void st_call_orf(const Batch& B, i64 k) {
         else hi = mid;
     }
     const int c = lo;
-    B.call_orf[k] = B.call_tmp[B.corf[c] + (k - B.call_cnt[c])];
+    B.call_orf[k] = B.call_tmp[call_base(B, c) + (k - B.call_cnt[c])];
 }
 // call table row: entry/exit node positions as phanotate.py:71-75 + locus.py:29-30 produce them.  item = call
 PB_HDN void st_gather_calls(const Batch& B, i64 k) {
     if (k >= B.ncalls) return;
     const i32 orf = B.call_orf[k];
-    const int c = B.o_contig[orf];
     CallRec r;
+    if (orf < 0) {                               // a tRNA on the path (functions.py:508: weight -20); strand +-2 marks the gene
+        const i32 t = -1 - orf, e = B.nn + 2 * t;
+        r.contig = B.t_contig[t] + B.contig_base;
+        r.left = B.n_pos[e];
+        r.right = B.n_pos[e + 1] + 2;
+        r.strand = B.t_start[t] < B.t_stop[t] ? 2 : -2;
+        r.weight = dec_from_u64(20);             // -Decimal(20)
+        r.weight.neg = 1;
+        r.score = -20.0;
+        B.calls[k] = r;
+        return;
+    }
+    const int c = B.o_contig[orf];
     const bool rev = B.o_frame[orf] < 0;
     r.contig = (i32)c + B.contig_base;
     r.left = rev ? B.o_stop[orf] : B.o_start[orf];            // left = entry node position
@@ -1049,7 +1127,22 @@ PB_HDN void edges_of(const Batch& B, i32 u, bool fill) {
         }                                \
         cnt++;                           \
     } while (0)
-    if (kind_is_entry(kind)) {
+    const bool TR = B.nt > 0 && B.ctrna[c + 1] > B.ctrna[c];
+    const u32 teb = TR ? B.te_cnt[2 * B.ctrna[c]] : 0, tee = TR ? B.te_cnt[2 * B.ctrna[c + 1]] : 0;
+    if (u >= B.nn) {                             // a tRNA node (trna.cuh): its edges are in the explicit list
+        if (kind_is_entry(kind) && pu <= 2000) EMIT(-2, u, EK_SOURCE, gap_score(B, c, pu, false));
+        for (u32 k = teb; k < tee; k++)
+            if (B.te_src[k] == u) {
+                if (B.te_dst[k] == u + 1 && kind_is_entry(kind)) {
+                    Dec w = dec_from_u64(20);          // -Decimal(20)
+                    w.neg = 1;
+                    EMIT(u, u + 1, EK_TRNA, w);
+                } else {
+                    EMIT(u, B.te_dst[k], EK_GAP, gap_score(B, c, B.n_pos[B.te_dst[k]] - pu - 3, false));
+                }
+            }
+        if (!kind_is_entry(kind) && L - pu <= 2000) EMIT(u, -3, EK_TARGET, gap_score(B, c, L - pu, false));
+    } else if (kind_is_entry(kind)) {
         if (pu <= 2000) EMIT(-2, u, EK_SOURCE, gap_score(B, c, pu, false));
         if (kind == K_FSTART) {
             EMIT(u, B.n_mate[u], EK_ORF, B.o_weight[B.n_orf[u]]);
@@ -1071,16 +1164,19 @@ PB_HDN void edges_of(const Batch& B, i32 u, bool fill) {
         for (u32 k = B.br_cnt[B.cnode[c]]; k < B.br_cnt[ne]; k++)
             if (B.br_src[k] == u)
                 EMIT(u, B.br_dst[k], EK_BRIDGE, gap_score(B, c, B.n_pos[B.br_dst[k]] - B.n_pos[u] - 3, false));
+        if (TR && (B.n_brs[u] & 2))
+            for (u32 k = teb; k < tee; k++)
+                if (B.te_src[k] == u) EMIT(u, B.te_dst[k], EK_GAP, gap_score(B, c, B.n_pos[B.te_dst[k]] - pu - 3, false));
         if (L - pu <= 2000) EMIT(u, -3, EK_TARGET, gap_score(B, c, L - pu, false));
     }
 #undef EMIT
     if (!fill) B.ed_cnt[u] = cnt;
 }
 PB_HDN void st_edge_count(const Batch& B, i64 u) {
-    if (u < B.nn) edges_of(B, (i32)u, false);
+    if (u < (i64)B.nn + 2 * B.nt) edges_of(B, (i32)u, false);
 }
 PB_HDN void st_edge_fill(const Batch& B, i64 u) {
-    if (u < B.nn) edges_of(B, (i32)u, true);
+    if (u < (i64)B.nn + 2 * B.nt) edges_of(B, (i32)u, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1188,7 +1284,20 @@ PB_HDN void pack_contig(const Batch& B, i64 c, ContigRec* out) {
     out[c] = r;
 }
 PB_HDN void pack_node(const Batch& B, i64 ni, NodeRec* out) {
-    if (ni >= B.nn) return;
+    if (ni >= (i64)B.nn + 2 * B.nt) return;
+    if (ni >= B.nn) {                            // a tRNA node: frame +-4 (functions.py:498-505), orf = -1 - hit index
+        NodeRec t;
+        t.contig = contig_of_node(B, (i32)ni);
+        t.position = B.n_pos[ni];
+        t.kind = B.n_kind[ni] & 3;
+        t.frame = 4;
+        t.mate = B.n_mate[ni];
+        t.orf = B.n_orf[ni];
+        t.other_end = B.n_oth[ni];
+        t.trigger = 0;
+        out[ni] = t;
+        return;
+    }
     NodeRec r;
     r.contig = contig_of_node(B, (i32)ni);
     r.position = B.n_pos[ni];

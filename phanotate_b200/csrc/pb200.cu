@@ -15,6 +15,7 @@
 #include "../../include/phanotate_b200.h"
 #include "graph.cuh"
 #include "chunk.cuh"
+#include "trna.cuh"
 #include "connect.cuh"
 #include "fast.cuh"
 
@@ -88,6 +89,10 @@ PB_KERNEL(st_rbs_weights)
 PB_KERNEL(st_edge_count)
 PB_KERNEL(st_edge_fill)
 PB_KERNEL(st_chunk_plan)
+PB_KERNEL(st_trna_nodes)
+PB_KERNEL(st_trna_tails)
+PB_KERNEL(st_trna_count)
+PB_KERNEL(st_trna_fill)
 PB_KERNEL(st_chunk_ids)
 PB_KERNEL(st_chunk_delta)
 PB_KERNEL(st_lv_init)
@@ -112,7 +117,8 @@ __global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
     const i64 ngroups = ((i64)gridDim.x * blockDim.x) / NL;
     for (i64 c = group; c < nc; c += ngroups)
         if (!contig_is_wide(B, (int)c) && !contig_chunked(B, (int)c)) {
-            if (NL == 32 && (B.flags & PB200_SOLVE_PLAIN)) solve_contig_t<D128>(B, (int)c, lane, 32);
+            // (contigs with tRNA nodes take the plain statement: it knows their explicit edge list, trna.cuh)
+            if (NL == 32 && ((B.flags & PB200_SOLVE_PLAIN) || contig_has_trna(B, (int)c))) solve_contig_t<D128>(B, (int)c, lane, 32);
             else solve_contig_win<NL>(B, (int)c, lane, mask);
         }
 }
@@ -216,7 +222,7 @@ __global__ void k_pack_contigs(const Batch B, ContigRec* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.nc; i += (i64)gridDim.x * blockDim.x) pack_contig(B, i, out);
 }
 __global__ void k_pack_nodes(const Batch B, NodeRec* out) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < B.nn; i += (i64)gridDim.x * blockDim.x) pack_node(B, i, out);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < (i64)B.nn + 2 * B.nt; i += (i64)gridDim.x * blockDim.x) pack_node(B, i, out);
 }
 __global__ void k_bf_literal(const BFArgs a) { bf_literal(a); }
 
@@ -317,6 +323,7 @@ struct pb200_ctx {
     int sm_count = 148;
     int contig_base = 0;
     bool scan_attr_set = false;
+    std::vector<i32> t_contig, t_start, t_stop, t_first;   // tRNA hits for the next runs (pb200_set_trnas)
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
     void* comm = nullptr;        // CommState (comm.inc) once pb200_comm_init ran
@@ -386,6 +393,7 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream));         \
         CK(ctx_sync(ctx));                                                  \
     } while (0)
+#define PB_UPLOAD(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
 #define PB_RUN(stage, n)                                                                         \
     do {                                                                                         \
         i64 n_ = (i64)(n);                                                                       \
@@ -582,6 +590,7 @@ struct pb200_ctx {
     int device = 0;
     int contig_base = 0;
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
+    std::vector<i32> t_contig, t_start, t_stop, t_first;
     std::string err;
     DevBuf ph[NPHASE];
     DevBuf in_seq, in_off, scratch, conn, conn_out;
@@ -621,6 +630,7 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
 #define PB_ALLOC(k, T, count) ((T*)buf_take(ctx->ph[k], (size_t)(count) * sizeof(T)))
 #define PB_ZERO(ptr, bytes) memset((ptr), 0, (bytes))
 #define PB_FETCH(dst, src, bytes) memcpy((dst), (src), (bytes))
+#define PB_UPLOAD(dst, src, bytes) memcpy((dst), (src), (bytes))
 #define PB_TO_HOST(dst, src, bytes) memcpy((dst), (src), (bytes))
 #define PB_RUN(stage, n)                                  \
     do {                                                  \
@@ -933,6 +943,19 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     B.nc = n_contigs;
     B.flags = (i32)flags;
     B.contig_base = ctx->contig_base;
+    B.nt = (i32)ctx->t_contig.size();
+    if (B.nt > 0) {
+        ctx->t_first.assign((size_t)n_contigs + 1, 0);
+        for (i32 k = 0; k < B.nt; k++) {
+            const i32 c = ctx->t_contig[k];
+            if (c < 0 || c >= n_contigs || (k > 0 && c < ctx->t_contig[k - 1])) {
+                ctx->err = "pb200_set_trnas: contig indices must be sorted and inside the batch";
+                return -2;
+            }
+            ctx->t_first[(size_t)c + 1]++;
+        }
+        for (i32 c = 0; c < n_contigs; c++) ctx->t_first[(size_t)c + 1] += ctx->t_first[c];
+    }
     B.ch_core = ctx->ch_core;
     B.ch_warm = ctx->ch_warm;
     B.ch_margin = ctx->ch_margin;
@@ -1045,6 +1068,17 @@ int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margi
     return 0;
 }
 
+// tRNA hits for the following runs (functions.py:457-509): hit k lies on contig contig[k] (index inside the batch, sorted
+// ascending) from start[k] to stop[k], 1-based as aragorn / tRNAscan-SE report them, start > stop on the reverse strand --
+// the [start, stop] pairs add_trnas collects, in its order.  n = 0 clears the list.
+int pb200_set_trnas(pb200_ctx* ctx, const int32_t* contig, const int32_t* start, const int32_t* stop, int32_t n) {
+    if (!ctx || n < 0 || (n > 0 && (!contig || !start || !stop))) return -2;
+    ctx->t_contig.assign(contig, contig + n);
+    ctx->t_start.assign(start, start + n);
+    ctx->t_stop.assign(stop, stop + n);
+    return 0;
+}
+
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {
     if (!ctx) return -2;
     ctx->contig_base = base;
@@ -1142,6 +1176,7 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
     out[0] = B.lit_all ? B.no : B.n_lit_pre;
     out[1] = B.lit_all ? 0 : B.n_lit_post;
     out[2] = (B.flags & PB200_LITERAL) ? B.nov : B.n_ovlit;
+    out[5] = B.nt;                                    // tRNA hits of the run
     out[3] = B.nch;                                   // chunks the long contigs were solved in
     if (B.nch > 0) {                                  // long contigs that failed the check and were solved by one sweep
         u32 fb = 0;
@@ -1226,15 +1261,16 @@ int pb200_get_nodes(pb200_ctx* ctx, pb200_node* out) {
     if (!ctx || !ctx->have) return -2;
     Batch& B = ctx->B;
     if (B.nn < 1) return 0;
-    PB_PHASE(6, (size_t)B.nn * sizeof(NodeRec) + 1024);
-    NodeRec* tmp = PB_ALLOC(6, NodeRec, B.nn);
+    const i64 nall = (i64)B.nn + 2 * B.nt;            // (the tRNA nodes follow the regular ones)
+    PB_PHASE(6, (size_t)nall * sizeof(NodeRec) + 1024);
+    NodeRec* tmp = PB_ALLOC(6, NodeRec, nall);
 #ifndef PB_HOSTSIM
-    k_pack_nodes<<<grid_for(ctx, B.nn, 128), 128, 0, ctx->stream>>>(B, tmp);
+    k_pack_nodes<<<grid_for(ctx, nall, 128), 128, 0, ctx->stream>>>(B, tmp);
     CK(cudaGetLastError());
 #else
-    for (i64 i = 0; i < B.nn; i++) pack_node(B, i, tmp);
+    for (i64 i = 0; i < nall; i++) pack_node(B, i, tmp);
 #endif
-    PB_TO_HOST(out, tmp, (size_t)B.nn * sizeof(NodeRec));
+    PB_TO_HOST(out, tmp, (size_t)nall * sizeof(NodeRec));
     return 0;
 }
 
@@ -1246,16 +1282,17 @@ int pb200_build_edges(pb200_ctx* ctx) {
     if (ensure_literal_orfs(ctx)) return -1;
     if (ensure_literal_overlaps(ctx)) return -1;
     if (gap_tables(ctx)) return -1;
-    PB_PHASE(7, ((size_t)B.nn + 2) * 4 + 1024);
-    B.ed_cnt = PB_ALLOC(7, u32, (size_t)B.nn + 1);
-    PB_RUN(st_edge_count, B.nn);
-    PB_SCAN32(B.ed_cnt, B.nn);
+    const i64 nall = (i64)B.nn + 2 * B.nt;
+    PB_PHASE(7, ((size_t)nall + 2) * 4 + 1024);
+    B.ed_cnt = PB_ALLOC(7, u32, (size_t)nall + 1);
+    PB_RUN(st_edge_count, nall);
+    PB_SCAN32(B.ed_cnt, nall);
     u32 tot;
-    PB_FETCH(&tot, B.ed_cnt + B.nn, 4);
+    PB_FETCH(&tot, B.ed_cnt + nall, 4);
     // the counts live in phase 7's buffer; the records go to phase 6 (shared with the pack views)
     PB_PHASE(6, ((size_t)tot + 1) * sizeof(EdgeRec) + 1024);
     B.edges = PB_ALLOC(6, EdgeRec, (size_t)tot + 1);
-    PB_RUN(st_edge_fill, B.nn);
+    PB_RUN(st_edge_fill, nall);
     B.nedges = (i32)tot;
 #ifndef PB_HOSTSIM
     CK(ctx_sync(ctx));

@@ -93,7 +93,7 @@ struct EdgeRec {          // = pb200_edge
     i32 contig, src, dst, kind;
     Dec weight;
 };
-enum { EK_ORF = 0, EK_GAP = 1, EK_OVERLAP = 2, EK_BRIDGE = 3, EK_SOURCE = 4, EK_TARGET = 5 };
+enum { EK_ORF = 0, EK_GAP = 1, EK_OVERLAP = 2, EK_BRIDGE = 3, EK_SOURCE = 4, EK_TARGET = 5, EK_TRNA = 6 };
 
 struct Batch {
     Params P;
@@ -216,7 +216,18 @@ struct Batch {
     i32 contig_base;      // added to the contig column of the call rows (a caller that splits a batch over contexts)
     i32 gap_dec;          // the Decimal gap tables gap_same / gap_diff are built
     i32 lit_done;         // every ORF has its literal weight (lazy completion ran)
-    u8* n_brs;            // [nn] 1 where an exit node is the source of a bridge
+    u8* n_brs;            // [nn] bit 0: the exit node is the source of a bridge, bit 1: of an edge into a tRNA node
+    // tRNA masking (trna.cuh): hits as add_trnas lists them; nodes nn + 2k (entry), nn + 2k + 1 (exit)
+    i32 nt;               // tRNAs in the batch
+    const i32* t_contig;  // [nt] sorted by contig
+    const i32* t_start;
+    const i32* t_stop;    // start > stop: reverse strand
+    const i32* ctrna;     // [nc+1] first tRNA of every contig
+    u32* te_cnt;          // [2nt+1] edges found by each tRNA node, then offsets
+    i32* te_src;
+    i32* te_dst;
+    i64* te_w;
+    i32 nte;
     // chunked solve of long contigs (chunk.cuh)
     u32* ch_cnt;          // [nc+1] chunks per contig, then exclusive offsets (0 chunks: the contig is solved by one sweep)
     i32 nch;              // chunks in the batch

@@ -83,7 +83,7 @@ class Result:
         st = np.zeros(8, dtype=np.int64)
         engine._ck(engine.lib.pb200_stats(engine.ctx, st.ctypes.data))
         self.n_literal_presolve, self.n_literal_postsolve, self.n_literal_overlaps = (int(v) for v in st[:3])
-        self.n_chunks, self.n_chunk_fallbacks = int(st[3]), int(st[4])
+        self.n_chunks, self.n_chunk_fallbacks, self.n_trnas = int(st[3]), int(st[4]), int(st[5])
         self.launches = int(engine.lib.pb200_launch_count(engine.ctx))
         self.stage_ms = engine._stage_times()
 
@@ -105,7 +105,7 @@ class Result:
     def nodes(self):
         if self._nodes is None:
             self._live("nodes")
-            self._nodes = np.zeros(self.n_nodes, dtype=N.NODE)
+            self._nodes = np.zeros(self.n_nodes + 2 * self.n_trnas, dtype=N.NODE)     # tRNA node pairs follow the regular nodes
             self._e._ck(self._e.lib.pb200_get_nodes(self._e.ctx, self._nodes.ctypes.data))
         return self._nodes
 
@@ -201,6 +201,11 @@ class Result:
             rows.append((int(r["left"]), int(r["right"]), "+" if r["strand"] > 0 else "-", "%E" % float(r["score"])))
         return rows
 
+    def call_genes(self, contig: int):
+        """'CDS' / 'tRNA' per call row (a tRNA hit on the path: strand column +-2)"""
+        c = self.contigs[contig]
+        return ["tRNA" if abs(int(s)) == 2 else "CDS" for s in self.calls["strand"][c["call_off"]:c["call_off"] + c["n_calls"]]]
+
 
 class Engine:
     def __init__(self, device: int = 0, lib_path: str | None = None):
@@ -237,6 +242,14 @@ class Engine:
             k = names[i].decode()
             out[k] = out.get(k, 0.0) + float(ms[i])
         return out
+
+    def set_trnas(self, trnas=None):
+        """tRNA hits for the following runs (functions.py:457-509): [(contig index, start, stop)], start > stop on the
+        reverse strand, as add_trnas collects them; sorted by contig here (order inside a contig kept).  None / [] clears."""
+        rows = sorted(trnas or [], key=lambda r: r[0])
+        arr = np.asarray(rows, dtype=np.int32).reshape(-1, 3)
+        c, a, b = (np.ascontiguousarray(arr[:, k]) for k in range(3))
+        self._ck(self.lib.pb200_set_trnas(self.ctx, c.ctypes.data, a.ctypes.data, b.ctypes.data, len(arr)))
 
     def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False, flags=0,
                    call_weights=False):
@@ -280,12 +293,19 @@ class Engine:
         return self.lib.pb200_unpin_host(arr.ctypes.data) == 0
 
     def run(self, seqs: Sequence[bytes] | Iterable[bytes], params=None, names=None, literal=False, flags=0,
-            call_weights=False) -> Result:
+            call_weights=False, trnas=None) -> Result:
+        """trnas: [(contig index, start, stop)] hits of aragorn / tRNAscan-SE for THIS batch (see set_trnas)"""
         seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         offs = np.zeros(len(seqs) + 1, dtype=np.int64)
         np.cumsum([len(s) for s in seqs], out=offs[1:])
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
-        return self.run_packed(bases, offs, params, names, literal=literal, flags=flags, call_weights=call_weights)
+        if trnas:
+            self.set_trnas(trnas)
+        try:
+            return self.run_packed(bases, offs, params, names, literal=literal, flags=flags, call_weights=call_weights)
+        finally:
+            if trnas:
+                self.set_trnas(None)
 
 
 class MergedResult:

@@ -29,9 +29,9 @@ def orf_order(orfs: np.ndarray) -> np.ndarray:
     return np.lexsort((sec, orfs["trigger"]))
 
 
-def node_repr(kind: int, frame: int, position: int) -> str:
+def node_repr(kind: int, frame: int, position: int, gene: str = "CDS") -> str:
     f = frame if kind in (0, 1) else -frame
-    return "Node('CDS','%s',%d,%d)" % (KIND_TYPE[kind], f, position)
+    return "Node('%s','%s',%d,%d)" % (gene, KIND_TYPE[kind], f, position)
 
 
 class ContigGraph:
@@ -56,23 +56,45 @@ class ContigGraph:
         seq[0::2], seq[1::2] = entry, exit_
         _, first = np.unique(seq, return_index=True)
         ins_order = seq[np.sort(first)]                       # local node ids in insertion order
-        self.ins = np.full(n + 2, -1, dtype=np.int64)
+        # tRNA node pairs (add_trnas, functions.py:457-509): behind the regular nodes of the whole batch, inserted into the
+        # graph after every CDS node and before source / target, entry then exit per hit
+        n_reg_all = res.n_nodes
+        tnodes = res.nodes[n_reg_all:] if getattr(res, "n_trnas", 0) else res.nodes[:0]
+        tsel = np.nonzero(tnodes["contig"] == k)[0]            # (batch-tail indices of this contig's tRNA nodes, in hit order)
+        nt2 = len(tsel)
+        self.ins = np.full(n + nt2 + 2, -1, dtype=np.int64)
         self.ins[ins_order] = np.arange(len(ins_order))
-        self.ins[n], self.ins[n + 1] = n, n + 1               # source, target come last (functions.py:440-443)
+        self.ins[n:n + nt2] = len(ins_order) + np.arange(nt2)
+        self.ins[n + nt2], self.ins[n + nt2 + 1] = n + nt2, n + nt2 + 1      # source, target come last (functions.py:440-443)
         self.node_names = [node_repr(int(nodes["kind"][i]), int(nodes["frame"][i]), int(nodes["position"][i]))
                            for i in ins_order]
+        self.node_names += [node_repr(int(tnodes["kind"][i]), 4, int(tnodes["position"][i]), "tRNA") for i in tsel]
         self.node_names += ["Node('source','source',0,0)", "Node('target','target',0,%d)" % (self.length + 1)]
+        if len(ins_order) < n:                                  # (cannot happen: every node belongs to an ORF)
+            raise ValueError("node without an ORF")
         self.local_nodes = nodes
         # edges of this contig
         e = res.edges
         e = e[e["contig"] == k]
-        src = np.where(e["src"] == N.NODE_SOURCE, n, e["src"] - nn0)
-        dst = np.where(e["dst"] == N.NODE_TARGET, n + 1, e["dst"] - nn0)
+        tmap = {int(n_reg_all + g): n + j for j, g in enumerate(tsel)}      # global tRNA node index -> local
+
+        def local(col, special, special_to):
+            out = np.empty(len(col), dtype=np.int64)
+            for i, v in enumerate(col.tolist()):
+                out[i] = special_to if v == special else (tmap[v] if v >= n_reg_all else v - nn0)
+            return out
+        if nt2:
+            src = local(e["src"], N.NODE_SOURCE, n + nt2)
+            dst = local(e["dst"], N.NODE_TARGET, n + nt2 + 1)
+        else:
+            src = np.where(e["src"] == N.NODE_SOURCE, n, e["src"] - nn0)
+            dst = np.where(e["dst"] == N.NODE_TARGET, n + 1, e["dst"] - nn0)
         isrc, idst = self.ins[src], self.ins[dst]
         kind = e["kind"]
         orf_rank = np.empty(len(orfs), dtype=np.int64)
         orf_rank[self.order] = np.arange(len(orfs))
-        phase = np.select([kind == 0, kind == 3, (kind == 1) | (kind == 2)], [0, 1, 2], 3)
+        # order inside a node's group: ORF edges, bridges, the tRNA edge (add_trnas runs after the bridges), connect loop, terminals
+        phase = np.select([kind == 0, kind == 3, kind == 6, (kind == 1) | (kind == 2)], [0, 1, 2, 3], 4)
         k1 = np.zeros(len(e), dtype=np.int64)
         k2 = np.zeros(len(e), dtype=np.int64)
         m = kind == 0                                          # ORF edge: rank of its ORF

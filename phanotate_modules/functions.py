@@ -40,12 +40,49 @@ def rev_comp(seq):
     return "".join(_COMP[b] for b in reversed(seq))
 
 
+def find_trnas(dna):
+    """functions.py:457-489: the hits of aragorn (`-t -w`) and tRNAscan-SE (`-B -q --brief`) on one contig as add_trnas
+    collects them -- [start, stop] pairs, start > stop on the reverse strand; a tRNAscan-SE hit is kept only where aragorn
+    found nothing.  None when neither program can be started (the reference then warns and skips the masking)."""
+    import tempfile
+    from subprocess import PIPE, Popen
+    hits, covered, ran = [], set(), 0
+    with tempfile.NamedTemporaryFile(mode='wt') as f:
+        f.write(">temp\n")
+        f.write(dna)
+        f.flush()
+        try:
+            text = Popen(["aragorn", "-t", "-w", f.name], stdout=PIPE, stdin=PIPE, stderr=PIPE).stdout.read().decode()
+            ran += 1
+            for line in text.splitlines():
+                if line.startswith('>') or line.endswith('found'):
+                    continue
+                where = line.split()[2]                    # "[a,b]" or "c[a,b]"
+                a, b = (int(x) for x in where.lstrip('c').strip('[]').split(','))
+                hits.append([b, a] if where.startswith('c') else [a, b])
+                covered.update(range(a, b))
+        except Exception:                                  # (the reference swallows everything here: a missing tool, odd output)
+            pass
+        try:
+            text = Popen(["tRNAscan-SE", "-B", "-q", "--brief", f.name], stdout=PIPE, stdin=PIPE, stderr=PIPE).stdout.read().decode()
+            ran += 1
+            for line in text.splitlines():
+                a, b = (int(x) for x in line.split('\t')[2:4])
+                if a != b and not covered & set(range(min(a, b), max(a, b))):
+                    hits.append([a, b])
+        except Exception:
+            pass
+    return hits if ran else None
+
+
 def get_orfs(locus):
-    """functions.py:143-303: six-frame scan + scoring of one locus -> Orfs (stop -> {start -> Orf})."""
+    """functions.py:143-303: six-frame scan + scoring of one locus -> Orfs (stop -> {start -> Orf}).  The device run also
+    builds the graph, so the tRNA programs (functions.py:457-509) are started here and their hits go into the same run."""
     dna = locus.seq().lower()
     params = make_params(locus.start_codons, locus.stop_codons, locus.min_orf_len)
+    trnas = find_trnas(dna)
     # literal=True: the reference's Decimal chain for every ORF inside the run, which also keeps Orf.hold (orfs.py:84)
-    res = engine().run([dna.encode()], params, literal=True).fetch_all()
+    res = engine().run([dna.encode()], params, literal=True, trnas=[(0, a, b) for a, b in trnas or []]).fetch_all()
     res.check(0)
     holds = res.orf_holds()
     my_orfs = Orfs(locus)
@@ -72,6 +109,7 @@ def get_orfs(locus):
         o.weight_rbs = float(c["training_rbs"][o.rbs_score]) / float(c["background_rbs"][o.rbs_score])
         my_orfs._insert(o)
     my_orfs._pb200 = res
+    my_orfs._trnas = trnas
     return my_orfs
 
 
@@ -87,9 +125,17 @@ def get_graph(my_orfs):
                 return my_orfs.seq
         res = get_orfs(_L)._pb200
     cg = mirror.ContigGraph(res, 0)
-    # no tRNA tools are driven from here (functions.py:457-509 needs aragorn / tRNAscan-SE); the reference
-    # prints this and carries on when they are missing (functions.py:493-495)
-    sys.stderr.write("Warning: tRNAscan or Aragorn were not found, proceding without tRNA masking.\n")
+    trnas = getattr(my_orfs, "_trnas", None)
+    if trnas is None:
+        # neither aragorn nor tRNAscan-SE could be started: the reference prints this and carries on (functions.py:493-495)
+        sys.stderr.write("Warning: tRNAscan or Aragorn were not found, proceding without tRNA masking.\n")
+    for start, stop in trnas or []:                        # the other_end entries add_trnas leaves behind (functions.py:496-507)
+        if start < stop:
+            my_orfs.other_end['t' + str(stop - 2)] = start
+            my_orfs.other_end['t' + str(start)] = stop - 2
+        else:
+            my_orfs.other_end['t' + str(start - 2)] = stop
+            my_orfs.other_end['t' + str(stop)] = start - 2
     G = Graph(directed=True)
     nodes = [eval(name) for name in cg.node_names]
     for n in nodes[:-2]:

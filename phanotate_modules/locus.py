@@ -51,8 +51,8 @@ class Locus:
     def genbank(self, outfile=sys.stdout):                   # README.md:40-54
         outfile.write("LOCUS       %s %20d bp \n" % (self.name(), self.length()))
         outfile.write("FEATURES             Location/Qualifiers\n")
-        for f in self.features(include=['CDS']):
-            outfile.write("     CDS             %s\n" % self._location(f))
+        for f in self.features():                            # CDS calls and tRNA hits on the path (phanotate.py:71: left.gene)
+            outfile.write("     %-16s%s\n" % (f.type, self._location(f)))
             for k, vals in f.tags.items():
                 for v in vals:
                     outfile.write("                     /%s=%s\n" % (k, v))
