@@ -434,3 +434,196 @@ PB_HDN void reach_chunk_prefix(const Batch& B, int c, int lane, int NL) {
         if (tot > run) run = tot;
     }
 }
+
+#ifdef __CUDACC__
+// ---- the chunk sweep out of shared memory.  A chunk's sweep is a serial chain of node visits, each a few dependent
+// memory round trips: from HBM/L2 that is ~1 us per visit whatever the GPU does beside it.  One warp per block stages
+// everything its visits read -- per node: distance, packed word, mate, the weight of the node's own ORF edge, overlap
+// range, dirty flag; per overlap edge: weight and target -- in shared memory once (coalesced), sweeps there, and writes
+// the distances back.  Same visits, same relaxations as solve_contig_win<32, true>.
+#define CHS_WIDE ((i64)0x8000000000000000ll)       /* marker: the ORF weight does not fit 62 bits -> o_wint[] */
+PB_HD size_t chunk_smem_bytes(int stride, int ecap) {
+    return (size_t)stride * (16 + 8 + 4 + 4 + 4) + 16 + (size_t)ecap * 12 + (size_t)stride + 64;
+}
+__device__ __forceinline__ void chs_relax(I128* sd, u8* sdirty, i32 v, const I128& cur, const I128& cand) {
+    if (D128::less(cand, cur)) {
+        sd[v] = cand;
+        sdirty[v] = 1;
+    }
+}
+__device__ void solve_chunk_smem(const Batch& B, const ChunkGeo& g, int lane, unsigned char* smem, int stride, int ecap) {
+    typedef D128 D;
+    typedef I128 T;
+    const int c = g.c;
+    const i32 s = g.s, n = g.e - g.s;                 // local index = node - s
+    T* sd = (T*)smem;
+    i64* sw = (i64*)(sd + stride);
+    u32* spk = (u32*)(sw + stride);
+    i32* smate = (i32*)(spk + stride);
+    u32* sov = (u32*)(smate + stride);                // [stride + 1]
+    i64* ew = (i64*)(((size_t)(sov + stride + 1) + 15) & ~(size_t)15);
+    i32* ed = (i32*)(ew + ecap);
+    u8* sdirty = (u8*)(ed + ecap);
+    const int base = g.s == g.nb ? 0 : (int)(B.n_pk[g.s] >> 4);
+    const u32 ov0 = B.ov_cnt[s];
+    // ---- stage
+    for (i32 i = lane; i < n; i += 32) {
+        const i32 gi = s + i;
+        const u32 w = B.n_pk[gi];
+        const int kind = (int)(w & 3);
+        spk[i] = w;
+        smate[i] = B.n_mate[gi];
+        sov[i] = B.ov_cnt[gi] - ov0;
+        i64 ow = 0;
+        if (kind == K_FSTART || kind == K_RSTART) {
+            const U4 q = *(const U4*)(B.o_wint + B.n_orf[gi]);
+            const i64 lo = (i64)(((u64)q.y << 32) | q.x), hi = (i64)(((u64)q.w << 32) | q.z);
+            ow = (hi == (lo >> 63) && lo != CHS_WIDE) ? lo : CHS_WIDE;
+        }
+        sw[i] = ow;
+        T d0 = D::inf();
+        u8 f0 = 0;
+        if ((int)(w >> 4) - base <= 2000 && kind_is_entry(kind)) {       // source -> entry (functions.py:444-447)
+            bool o;
+            d0 = D::from_i64(gap_w64(B, c, (int)(w >> 4) - base, false, &o));
+            f0 = 1;
+        }
+        sd[i] = d0;
+        sdirty[i] = f0;
+    }
+    if (lane == 0) sov[n] = B.ov_cnt[s + n] - ov0;
+    const u32 ne_ov = B.ov_cnt[s + n] - ov0;
+    for (u32 k = lane; k < ne_ov && k < (u32)ecap; k += 32) {
+        ew[k] = B.ov_w64[ov0 + k];
+        ed[k] = B.ov_dst[ov0 + k];
+    }
+    __syncwarp();
+    const u32 brb = B.br_cnt[g.nb], bre = B.br_cnt[g.ne];
+    i32 i = 0;
+    int budget = 64 * n + 1024;
+    CStat* cs = B.cs + c;
+    while (i < n) {
+        const i32 j0 = i + lane;
+        const bool in = j0 < n;
+        u8 dj = 0;
+        u32 wj = 0, cj = 0;
+        i32 mj = -1;
+        T Tj = D::inf();
+        if (in) {
+            dj = sdirty[j0];
+            wj = spk[j0];
+            Tj = sd[j0];
+            mj = smate[j0];
+            cj = sov[j0];
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, dj != 0);
+        if (!m) {
+            i += 32;
+            continue;
+        }
+        if (--budget < 0) {
+            if (lane == 0) atomicOr(&cs->err, (u32)ERR_INTERNAL);
+            break;
+        }
+        const int f = __ffs((int)m) - 1;
+        const i32 u = i + f;                              // local
+        const u32 wu = __shfl_sync(0xFFFFFFFFu, wj, f);
+        const T Du = shfl128<32>(0xFFFFFFFFu, Tj, f);
+        const i32 mate_u = __shfl_sync(0xFFFFFFFFu, mj, f) - s;          // local (may lie outside [0, n))
+        const int kind = (int)(wu & 3), pu = (int)(wu >> 4);
+        if (lane == 0) sdirty[u] = 0;
+        i32 rewind = 0x7FFFFFFF;
+        const bool behind = in && lane > f;
+        if (kind == K_FSTART) {
+            if (lane == 0 && mate_u < n) {
+                const i64 ow = sw[u];
+                const T w = ow != CHS_WIDE ? D::from_i64(ow) : D::load_w(B.o_wint + B.n_orf[s + u]);
+                chs_relax(sd, sdirty, mate_u, sd[mate_u], D::add(Du, w));
+            }
+        } else if (kind == K_RSTOP) {
+            // the starts of this reverse family: nodes up to its farthest start (the stop-key node's mate)
+            const i32 last = mate_u >= n ? n - 1 : mate_u;
+            for (i32 j = u + 1 + lane; j <= last; j += 32) {
+                if ((int)(spk[j] & 3) == K_RSTART && smate[j] - s == u) {
+                    const i64 ow = sw[j];
+                    const T w = ow != CHS_WIDE ? D::from_i64(ow) : D::load_w(B.o_wint + B.n_orf[s + j]);
+                    chs_relax(sd, sdirty, j, sd[j], D::add(Du, w));
+                }
+            }
+        } else {
+            const u32 ovb = __shfl_sync(0xFFFFFFFFu, cj, f);
+            const u32 ove = sov[u + 1];
+            // gap edges to entries within 500 bp downstream (functions.py:360-438)
+            {
+                const int kj = (int)(wj & 3), d = (int)(wj >> 4) - pu;
+                if (behind && d > 0 && d < 500 && kind_is_entry(kj) && !(kind == K_RSTART && kj == K_FSTART && d <= 2)) {
+                    const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+                    bool o;
+                    chs_relax(sd, sdirty, j0, Tj, D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))));
+                }
+            }
+            const u32 wlast = __shfl_sync(0xFFFFFFFFu, wj, 31);
+            if (i + 32 < n && (int)(wlast >> 4) - pu < 500) {
+                for (i32 j = i + 32 + lane; j < n; j += 32) {
+                    const u32 w2 = spk[j];
+                    const int kj = (int)(w2 & 3), d = (int)(w2 >> 4) - pu;
+                    if (d >= 500) break;
+                    if (d <= 0 || !kind_is_entry(kj)) continue;
+                    const bool diff = (kind == K_FSTOP) ? (kj == K_RSTOP) : (kj == K_FSTART);
+                    if (kind == K_RSTART && kj == K_FSTART && d <= 2) continue;      // functions.py:431
+                    bool o;
+                    chs_relax(sd, sdirty, j, sd[j], D::add(Du, D::from_i64(gap_w64(B, c, d - 3, diff, &o))));
+                }
+            }
+            // overlap edges (backwards)
+            if (ove > ovb) {
+                for (u32 k = ovb + lane; k < ove; k += 32) {
+                    i64 w64;
+                    i32 v;
+                    if (k < (u32)ecap) {
+                        w64 = ew[k];
+                        v = ed[k] - s;
+                    } else {
+                        w64 = B.ov_w64[ov0 + k];
+                        v = B.ov_dst[ov0 + k] - s;
+                    }
+                    if (v < 0) continue;
+                    const T cur = sd[v];
+                    const T cand = D::add(Du, w64 != OV_W64_WIDE ? D::from_i64(w64) : D::load_w(B.ov_wint + ov0 + k));
+                    if (D::less(cand, cur)) {
+                        sd[v] = cand;
+                        sdirty[v] = 1;
+                        if (v < rewind) rewind = v;
+                    }
+                }
+                rewind = (i32)__reduce_min_sync(0xFFFFFFFFu, (unsigned)rewind);
+            }
+            // bridges (rare: n_brs flags the exit nodes that have any)
+            if (bre > brb && (B.n_brs[s + u] & 1)) {
+                for (u32 k = brb + lane; k < bre; k += 32) {
+                    if (B.br_src[k] != s + u) continue;
+                    const i32 v = B.br_dst[k] - s;
+                    if (v < 0 || v >= n) continue;
+                    chs_relax(sd, sdirty, v, sd[v], D::add(Du, D::load_w(B.br_wint + k)));
+                }
+            }
+        }
+        __syncwarp();
+        i = (rewind < u) ? rewind : u + 1;
+    }
+    __syncwarp();
+    // ---- the distances back to the chunk's private array
+    T* out = B.ch_dist + g.slot;
+    for (i32 k = lane; k < n; k += 32) out[k] = sd[k];
+}
+__global__ void __launch_bounds__(32) k_chunk_solve_smem(const Batch B, int stride, int ecap) {
+    extern __shared__ __align__(16) unsigned char chs_smem[];
+    const int lane = threadIdx.x;
+    for (i64 id = blockIdx.x; id < B.nch; id += gridDim.x) {
+        const ChunkGeo g = chunk_geo(B, (i32)id);
+        if (contig_is_wide(B, g.c)) continue;
+        solve_chunk_smem(B, g, lane, chs_smem, stride, ecap);
+        __syncwarp();
+    }
+}
+#endif

@@ -324,6 +324,7 @@ struct pb200_ctx {
     int contig_base = 0;
     bool scan_attr_set = false;
     std::vector<i32> t_contig, t_start, t_stop, t_first;   // tRNA hits for the next runs (pb200_set_trnas)
+    bool ch_default = true;      // geometry never set by the caller: a small batch may shorten it (driver.inc)
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
     void* comm = nullptr;        // CommState (comm.inc) once pb200_comm_init ran
@@ -454,7 +455,26 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
         k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
         if (B.nch > 0) {                                                                         \
-            k_chunk_solve<<<grid_for(ctx, (i64)B.nch * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B); \
+            /* one warp per chunk: out of shared memory when a chunk's tables fit (chunk.cuh), else out of HBM/L2 */ \
+            const int stride_ = B.ch_warm + B.ch_core + B.ch_margin;                             \
+            const int ecap_ = stride_ + stride_ / 4;                                             \
+            const size_t smem_ = chunk_smem_bytes(stride_, ecap_);                               \
+            /* (a lone warp sweeping out of shared memory is bound by instruction latency, ~0.4 us per visit against ~1 us \
+               out of L2: it wins while all chunks are resident at once -- one or a few genomes -- and loses to the L2 \
+               kernel's 9 warps per SM once the chunks need several rounds of the 3-9 blocks per SM that fit) */ \
+            i64 fit_ = (i64)(227 * 1024 / (smem_ + 1024));                                       \
+            if (fit_ > 32) fit_ = 32;                                                            \
+            const char* force_ = getenv("PB200_CHUNK_KERNEL");                                   \
+            const bool smem_ok_ = smem_ <= 200 * 1024 && !(B.flags & PB200_SOLVE_PLAIN);         \
+            const bool use_smem_ = force_ ? (smem_ok_ && force_[0] == 's') : (smem_ok_ && (i64)B.nch <= fit_ * ctx->sm_count); \
+            if (use_smem_) {                                                                     \
+                cudaFuncSetAttribute(k_chunk_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
+                i64 gb_ = B.nch;                                                                 \
+                if (gb_ > (i64)ctx->sm_count * 32) gb_ = (i64)ctx->sm_count * 32;                \
+                k_chunk_solve_smem<<<(int)gb_, 32, smem_, ctx->stream2>>>(B, stride_, ecap_);    \
+            } else {                                                                             \
+                k_chunk_solve<<<grid_for(ctx, (i64)B.nch * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B); \
+            }                                                                                    \
             ctx->launches++;                                                                     \
         }                                                                                        \
         cudaEventRecord(ctx->join_ev, ctx->stream2);                                             \
@@ -590,6 +610,7 @@ struct pb200_ctx {
     int device = 0;
     int contig_base = 0;
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
+    bool ch_default = true;
     std::vector<i32> t_contig, t_start, t_stop, t_first;
     std::string err;
     DevBuf ph[NPHASE];
@@ -1061,6 +1082,7 @@ int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, i
 // again by one sweep); it only moves the time.  Environment PB200_CHUNK="core,warm,margin,long" sets it at pb200_create.
 int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margin, int32_t long_nodes) {
     if (!ctx || core < 1 || warm < 0 || margin < 0 || long_nodes < 0) return -2;
+    ctx->ch_default = false;
     ctx->ch_core = core;
     ctx->ch_warm = warm;
     ctx->ch_margin = margin;

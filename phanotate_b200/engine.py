@@ -275,7 +275,8 @@ class Engine:
         return Result(self, names) if fetch else None
 
     def set_chunking(self, core=256, warm=768, margin=64, long_nodes=4096):
-        """Geometry (in graph nodes) of the chunked solve of long contigs; results do not depend on it."""
+        """Geometry (in graph nodes) of the chunked solve of long contigs; results do not depend on it.  (Until this is
+        called the library picks it: 256/768/64 for contigs above 4096 nodes, 128/384/32 for a run of one or a few genomes.)"""
         self._ck(self.lib.pb200_set_chunking(self.ctx, int(core), int(warm), int(margin), int(long_nodes)))
 
     def last_run_ms(self) -> float:
