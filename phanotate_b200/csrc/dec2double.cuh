@@ -32,8 +32,15 @@ PB_HDNI double dec_to_double(const Dec& d, bool* ok) {
     double r;
     if (d.e >= 0) {
         if (d.e > 100) {
-            *ok = false;
-            return 0.0;
+            // astronomically large weights (an ORF of many kb in AT-rich sequence): exact up to the largest double, inf beyond
+            // (float(Decimal('1E+400')) is inf in CPython too)
+            if (d.e > 330) r = HUGE_VAL;
+            else {
+                Wide<48> n = w_resize<48>(d.c);
+                w_mul_pow10(n, d.e);
+                r = wide_to_double_rne(n, false, 0);
+            }
+            return d.neg ? -r : r;
         }
         Wide<16> n = w_resize<16>(d.c);
         w_mul_pow10(n, d.e);

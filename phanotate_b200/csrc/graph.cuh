@@ -320,6 +320,7 @@ struct D256 {
     }
     static PB_HD T from_i64(i64 v) { return wint_from_i64(v); }
     static PB_HD T load_w(const WInt* p) { return *p; }
+    static PB_HD T orf_w(const Batch& B, i32 orf) { return B.o_wint[orf]; }
     static PB_HD T* dist(const Batch& B) { return B.dist; }
     static PB_HD WInt to_wint(const T& a) { return a; }
     static PB_HD void tie(const Batch& B, int c, i32 v, i32 from, const T& cand) {
@@ -360,6 +361,7 @@ struct D128 {
         r.hi = (i64)(((u64)q.w << 32) | q.z);
         return r;
     }
+    static PB_HD T orf_w(const Batch& B, i32 orf) { return load_w(B.o_wint + orf); }
     static PB_HD T* dist(const Batch& B) { return B.dist128; }
     static PB_HD WInt to_wint(const T& a) {
         WInt r;
@@ -380,6 +382,63 @@ struct D128 {
             u64* w = (u64*)&e->cand;
             w[0] = cand.lo;
             w[1] = (u64)cand.hi;
+        }
+    }
+};
+// 2048-bit distances: contigs with an ORF weight beyond 2^240 (CStat.huge; score.cuh).  Same algorithm, values in local
+// memory; rare by construction (an ORF of many kb in AT-rich sequence), so nothing here is tuned.
+struct DHuge {
+    typedef HInt T;
+    static PB_HD T inf() {
+        T r;
+        for (int i = 0; i < WH; i++) r.w[i] = 0xFFFFFFFFu;
+        r.w[WH - 1] = 0x7FFFFFFFu;
+        return r;
+    }
+    static PB_HD bool is_inf(const T& a) { return a.w[WH - 1] == 0x7FFFFFFFu; }
+    static PB_HD bool less(const T& a, const T& b) {
+        const u32 sa = a.w[WH - 1] >> 31, sb = b.w[WH - 1] >> 31;
+        if (sa != sb) return sa > sb;
+        return w_cmp(a, b) < 0;
+    }
+    static PB_HD bool eq(const T& a, const T& b) { return w_cmp(a, b) == 0; }
+    static PB_HD T add(T a, const T& b) {
+        w_add(a, b);
+        return a;
+    }
+    static PB_HD T from_i64(i64 v) {
+        T r;
+        const u32 ext = v < 0 ? 0xFFFFFFFFu : 0u;
+        r.w[0] = (u32)(u64)v;
+        r.w[1] = (u32)((u64)v >> 32);
+        for (int i = 2; i < WH; i++) r.w[i] = ext;
+        return r;
+    }
+    static PB_HD T load_w(const WInt* p) {         // sign-extended
+        T r;
+        const u32 ext = (p->w[WN - 1] >> 31) ? 0xFFFFFFFFu : 0u;
+        for (int i = 0; i < WN; i++) r.w[i] = p->w[i];
+        for (int i = WN; i < WH; i++) r.w[i] = ext;
+        return r;
+    }
+    static PB_HDN T orf_w(const Batch& B, i32 orf) {
+        if (!wint_is_huge_marker(B.o_wint[orf])) return load_w(B.o_wint + orf);
+        T r;
+        dec_to_hint(B.o_weight[orf], r);          // (checked when the marker was set)
+        return r;
+    }
+    static PB_HD T* dist(const Batch& B) { return B.dist_huge; }
+    static PB_HD WInt to_wint(const T& a) {       // the low 256 bits (the tie records and the target compare on those)
+        WInt r;
+        for (int i = 0; i < WN; i++) r.w[i] = a.w[i];
+        if (is_inf(a)) r = wint_inf();
+        return r;
+    }
+    static PB_HD void tie(const Batch& B, int c, i32 v, i32 from, const T& cand) {
+        TieEv* e = tie_slot(B, c, v, from);
+        if (e) {
+            e->pad = 0;
+            for (int i = 0; i < WN; i++) e->cand.w[i] = cand.w[i];
         }
     }
 };
@@ -511,7 +570,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveR
                 const i32 v = B.n_mate[u], orf = B.n_orf[u];
                 if (!CH || v < ne) {
                     const T cur = dist[v];
-                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::load_w(B.o_wint + orf)), u, dirty);
+                    relax<D, CH>(B, ties, dist, v, cur, D::add(Du, D::orf_w(B, orf)), u, dirty);
                 }
             }
         } else if (kind == K_RSTOP) {
@@ -523,7 +582,7 @@ PB_HDN void solve_contig_t(const Batch& B, int c, int lane, int NL, const SolveR
                 if ((int)(wj & 3) == K_RSTART && mj == u) {
                     const i32 orf = B.n_orf[j];
                     const T cur = dist[j];
-                    relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::load_w(B.o_wint + orf)), u, dirty);
+                    relax<D, CH>(B, ties, dist, j, cur, D::add(Du, D::orf_w(B, orf)), u, dirty);
                 }
             }
         } else {
@@ -828,10 +887,12 @@ __device__ void solve_contig_win(const Batch& B, int c, int lane, unsigned mask,
 }
 #endif
 PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.flags & PB200_SOLVE_WIDE); }
+PB_HD bool contig_is_huge(const Batch& B, int c) { return B.cs[c].huge != 0; }
 // a long contig whose solve runs as chunks (chunk.cuh) instead of one sweep
 PB_HD bool contig_chunked(const Batch& B, int c) { return B.ch_cnt && B.ch_cnt[c + 1] > B.ch_cnt[c] && !contig_is_wide(B, c); }
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
-    if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
+    if (contig_is_huge(B, c)) solve_contig_t<DHuge>(B, c, lane, NL);
+    else if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
     else if (!contig_chunked(B, c)) solve_contig_t<D128>(B, c, lane, NL);
 }
 
@@ -943,7 +1004,9 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
     int n = 0;
     for (i32 k = cs->tie_head; k;) {
         const TieEv* e = B.tie_ev + (k - 1);
-        const WInt fin = (e->v == -3) ? B.tdist[c] : (wide ? B.dist[e->v] : D128::to_wint(B.dist128[e->v]));
+        const WInt fin = (e->v == -3) ? B.tdist[c]
+                         : contig_is_huge(B, c) ? DHuge::to_wint(B.dist_huge[e->v])
+                         : (wide ? B.dist[e->v] : D128::to_wint(B.dist128[e->v]));
         if (w_cmp(fin, e->cand) == 0) {           // the tie is at the node's FINAL distance: a second tight in-edge
             if (n == TIE_MAXN) {
                 cs->err |= ERR_TIES;

@@ -402,7 +402,17 @@ PB_HDN void st_orf_finish(const Batch& B, i64 sl) {
     sc.neg ^= 1;
     B.o_weight[oi] = sc;
     WInt wi;
-    if (!dec_to_wint(sc, wi)) PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+    if (!dec_to_wint(sc, wi)) {
+        // beyond 256 bits: the contig is solved with 2048-bit distances, this weight formed from the Decimal on demand
+        HInt h;
+        if (dec_to_hint(sc, h)) {
+            wi = wint_huge_marker();
+            cs->huge = 1;
+            PB_ATOMIC_ADD(B.lit_cnt + 5, 1u);
+        } else {
+            PB_ATOMIC_OR(&cs->err, (u32)ERR_OVERFLOW);
+        }
+    }
     B.o_wint[oi] = wi;
     if (!wint_is_narrow(wi)) cs->wide = 1;         // (benign race: every writer stores 1)
     B.o_lit[oi] = 1;

@@ -34,6 +34,9 @@ static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
 // ================================================================================================
 #include <cuda_runtime.h>
 #define PB_BLOCK 128
+#ifndef PB_SOLVE_MINB
+#define PB_SOLVE_MINB 10
+#endif
 #define CK(x)                                                                                   \
     do {                                                                                        \
         cudaError_t e_ = (x);                                                                   \
@@ -110,7 +113,7 @@ PB_KERNEL(st_pj_calls)
 // one warp per contig; the 128-bit instantiation is kept small enough for 12 blocks per SM (the solve is a chain of
 // dependent memory round trips per contig: throughput comes from the number of contigs in flight)
 template <int NL>
-__global__ void __launch_bounds__(PB_BLOCK, 10) k_solve(const Batch B, i32 nc) {
+__global__ void __launch_bounds__(PB_BLOCK, PB_SOLVE_MINB) k_solve(const Batch B, i32 nc) {
     const int lane = threadIdx.x & (NL - 1);
     const unsigned mask = NL == 32 ? 0xFFFFFFFFu : (((1u << (NL & 31)) - 1u) << ((threadIdx.x & 31) - lane));
     const i64 group = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / NL;
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) 
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 c = warp; c < nc; c += nwarps)
-        if (contig_is_wide(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
+        if (contig_is_huge(B, (int)c)) solve_contig_t<DHuge>(B, (int)c, lane, 32);
+        else if (contig_is_wide(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
 }
 // Overlap enumeration (st_ov_count / st_ov_fill) with the exit nodes compacted inside the warp: only exit nodes have
 // work, and they are about every second node, so a warp takes 64 consecutive nodes and hands the k-th exit node among them
@@ -797,6 +801,11 @@ static int bridge_tables(pb200_ctx* ctx) {
         B.br_wint = PB_ALLOC(3, WInt, nbr);
     }
     if (B.nbr > 0) PB_RUN(st_br_fill, B.nn);
+    {   // (behind the literal chain on this stream: ORF weights beyond 256 bits, hold.cuh)
+        u32 hg;
+        PB_FETCH(&hg, B.lit_cnt + 5, 4);
+        B.n_huge = (i32)hg;
+    }
     return 0;
 }
 static int literal_chain(pb200_ctx* ctx, i32 nlit) {
@@ -1199,6 +1208,7 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
     out[1] = B.lit_all ? 0 : B.n_lit_post;
     out[2] = (B.flags & PB200_LITERAL) ? B.nov : B.n_ovlit;
     out[5] = B.nt;                                    // tRNA hits of the run
+    out[6] = B.n_huge;                                // ORF weights beyond 256 bits (their contigs solved at 2048 bits)
     out[3] = B.nch;                                   // chunks the long contigs were solved in
     if (B.nch > 0) {                                  // long contigs that failed the check and were solved by one sweep
         u32 fb = 0;

@@ -73,6 +73,8 @@ struct CStat {
     i32 fast_ok;            // fe[] and the per-bin RBS weights converted to fixed point without loss of range
     DD fe[6];               // pos_max[im] * pos_min[il] of the six GC-frame factor classes (exponent of 1-pstop per codon)
     i64 gap_hi3, gap_hi4;   // trunc((g**100 + len)*1000) - len*1000 for 3- and 4-digit len (functions.py:40-41)
+    i32 huge;               // some ORF weight needs more than 256 bits: 2048-bit distances in the solve (score.cuh: HInt)
+    i32 huge_pad;
     u32 chunk_viol;         // chunked solve (chunk.cuh): some node failed the Bellman check -> the contig is solved again by one sweep
     u32 chunk_pad;
 };
@@ -148,6 +150,8 @@ struct Batch {
     WInt* br_wint;
     // solve
     WInt* dist;
+    Wide<64>* dist_huge;  // [nn] distances of the contigs solved at 2048 bits (allocated only when a batch has one)
+    i32 n_huge;           // ORF weights beyond 256 bits in the batch
     struct I128* dist128; // [nn] distances of the contigs solved at 128 bits
     i32* parent;
     u8* dirty;

@@ -209,6 +209,36 @@ PB_HD bool wint_is_narrow(const WInt& w) {
     const u32 top = w.w[3] ^ ext;               // bits 96..127 relative to the sign
     return ok && (top >> 14) == 0;
 }
+// Weights beyond 2^240 (hold.cuh: an ORF of ~9 kb in AT-rich sequence already weighs 1e108; the reference's Decimal and
+// the GMP-backed fastpathz have no limit): o_wint holds a marker, the value is formed from the Decimal weight when the solve
+// needs it, as a 2048-bit integer (|w| < ~1e560; a double overflows at 1.8e308).
+#define WH 64
+typedef Wide<WH> HInt;
+PB_HD WInt wint_huge_marker() {
+    WInt r;
+#pragma unroll
+    for (int i = 0; i < WN; i++) r.w[i] = 0x48554745u;
+    r.w[WN - 1] = 0x7FFFFFFEu;
+    return r;
+}
+PB_HD bool wint_is_huge_marker(const WInt& a) { return a.w[WN - 1] == 0x7FFFFFFEu; }
+// trunc(d * 1000) as a two's complement 1280-bit integer; false if even that is too narrow
+PB_HDNI bool dec_to_hint(const Dec& d, HInt& out) {
+    HInt mag = w_resize<WH>(d.c);
+    const int e = d.e + 3;
+    if (e < 0 || w_ndigits(d.c) + e > 9 * WH - 12) return false;
+    w_mul_pow10(mag, e);
+    if (d.neg && !w_is_zero(mag)) {
+        u64 carry = 1;
+        for (int i = 0; i < WH; i++) {
+            carry += (u64)(~mag.w[i]);
+            mag.w[i] = (u32)carry;
+            carry >>= 32;
+        }
+    }
+    out = mag;
+    return true;
+}
 PB_HDNI bool dec_to_wint(const Dec& d, WInt& out) {
     Wide<WN> mag;
     bool ok = dec_to_milli_int<WN>(d, mag);

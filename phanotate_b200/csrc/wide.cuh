@@ -164,7 +164,7 @@ PB_HD Wide<N> w_shr(const Wide<N>& a, int s) {     // logical right shift, 0 <= 
     Wide<N> r = a;
     const int ws = s >> 5, bs = s & 31;
 #pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) {
+    for (int k = 32; k >= 1; k >>= 1) {
         if (k < N && (ws & k)) {
 #pragma unroll
             for (int i = 0; i < N; i++) r.w[i] = (i + k < N) ? r.w[(i + k < N) ? i + k : 0] : 0u;
@@ -184,7 +184,7 @@ PB_HD Wide<N> w_shl(const Wide<N>& a, int s) {     // left shift, bits shifted o
     Wide<N> r = a;
     const int ws = s >> 5, bs = s & 31;
 #pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) {
+    for (int k = 32; k >= 1; k >>= 1) {
         if (k < N && (ws & k)) {
 #pragma unroll
             for (int i = N - 1; i >= 0; i--) r.w[i] = (i - k >= 0) ? r.w[(i - k >= 0) ? i - k : 0] : 0u;

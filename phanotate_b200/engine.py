@@ -167,8 +167,8 @@ class Result:
     def check(self, contig: int | None = None):
         """Raise what the reference would have raised for a contig (or for any contig): KeyError for a letter outside
         the IUPAC alphabet (functions.py:20-24), ValueError for parallel edges (graphs.py:73-74) and for the Orfs.get_orf
-        lookup (orfs.py:62-69).  Anything else this implementation cannot finish (edge weights beyond 256 bits, see
-        DESIGN.md: known limits) raises PhanotateError."""
+        lookup (orfs.py:62-69).  Anything else this implementation cannot finish (edge weights beyond 2048 bits, more than 256
+        exact ties in one contig; DESIGN.md: known limits) raises PhanotateError."""
         cs = self.contigs if contig is None else self.contigs[contig:contig + 1]
         for i, c in enumerate(cs):
             err = int(c["err"])
@@ -182,8 +182,8 @@ class Result:
             if err & N.ERR_LOOKUP:
                 raise ValueError("contig %d: orf not found (Orfs.get_orf)" % k)
             if err & (N.ERR_OVERFLOW | N.ERR_RANGE):
-                raise PhanotateError("contig %d: an edge weight is beyond this build's 256-bit exact range (~1e74; an ORF "
-                                     "of several kb in AT-rich sequence) -- the reference has no such limit "
+                raise PhanotateError("contig %d: an edge weight is beyond this build's 2048-bit exact range (~1e560; an ORF "
+                                     "of tens of kb of pure A/T) -- the reference has no such limit "
                                      "(device error bits 0x%x)" % (k, err))
             if err & N.ERR_NOPATH and not (err & ~N.ERR_NOPATH):
                 continue                        # no source->target path: no calls (undefined in the reference)

@@ -50,14 +50,47 @@ def test_contig_without_a_path_prints_its_header_and_the_run_goes_on(sim, tmp_pa
     assert out["genbank"].count("LOCUS") == 3
 
 
-def test_contig_beyond_the_exact_range_is_left_out_not_fatal(sim, tmp_path, capsys):
-    """a 9-kb AT-rich ORF weighs ~1e108: beyond the 256-bit integers of the solve (the reference is unbounded).  The contig is
-    flagged, Result.check raises PhanotateError for it, and the CLI reports it and still prints the other contigs."""
-    import phanotate
-    rng = np.random.default_rng(3)
+def _giant_orf_contig(ncodons, seed=3):
+    """phiX174 flanks around one ORF of `ncodons` A/T-only codons: its weight grows like 1e58 per kb"""
+    rng = np.random.default_rng(seed)
     codons = [c for c in (a + b + c for a in "at" for b in "at" for c in "at") if c not in ("taa", "tta")]
-    giant = "atg" + "".join(codons[i] for i in rng.integers(0, len(codons), 3000)) + "taa"
-    big = seq_of("phiX174")[:1500] + giant + seq_of("phiX174")[1500:3000]
+    giant = "atg" + "".join(codons[i] for i in rng.integers(0, len(codons), ncodons)) + "taa"
+    return seq_of("phiX174")[:1500] + giant + seq_of("phiX174")[1500:3000]
+
+
+def check_astronomic_weights(e):
+    """ORF weights beyond the 256-bit integers of the ordinary solve (the reference's Decimal and the GMP-backed fastpathz
+    have no limit): a 9-kb A/T-only ORF weighs 7.5e174, an 18-kb one 2.5e348 (its %E score is -INF in the reference as
+    well: float() overflows).  Such contigs are solved with 2048-bit distances; calls and scores equal the oracle's."""
+    from oracle import phanotate_oracle as O
+    seqs = [_giant_orf_contig(3000), seq_of("phiX174"), _giant_orf_contig(6000)]
+    res = e.run(seqs)
+    assert [int(v) for v in res.contigs["err"]] == [0, 0, 0] and [int(v) for v in res.contigs["wide"]] == [1, 0, 1]
+    for k in (0, 2):
+        want = [tuple(r[:4]) for r in O.call_contig(seqs[k])[3]]
+        assert res.call_rows(k) == want, k
+    assert any(r[3] == "-7.525584E+174" for r in res.call_rows(0)) and any(r[3] == "-INF" for r in res.call_rows(2))
+    res.check()
+
+
+def test_astronomic_orf_weights_are_solved_exactly(sim):
+    check_astronomic_weights(sim)
+
+
+@pytest.mark.gpu
+def test_astronomic_orf_weights_are_solved_exactly_on_gpu():
+    e = engine.Engine(0)
+    try:
+        check_astronomic_weights(e)
+    finally:
+        e.close()
+
+
+def test_contig_beyond_the_exact_range_is_left_out_not_fatal(sim, tmp_path, capsys):
+    """a 60-kb A/T-only ORF weighs ~1e1160: beyond even the 2048-bit integers.  The contig is flagged, Result.check raises
+    PhanotateError for it, and the CLI reports it and still prints the other contigs."""
+    import phanotate
+    big = _giant_orf_contig(20000)
     res = sim.run([big])
     assert int(res.contigs[0]["err"]) & (N.ERR_OVERFLOW | N.ERR_RANGE)
     with pytest.raises(engine.PhanotateError):
