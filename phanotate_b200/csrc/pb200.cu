@@ -173,8 +173,14 @@ __global__ void __launch_bounds__(PB_BLOCK) k_solve_wide(const Batch B, i32 nc) 
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 c = warp; c < nc; c += nwarps)
+        if (contig_is_wide(B, (int)c) && !contig_is_huge(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
+}
+// contigs with an ORF weight beyond 256 bits: 2048-bit distances (a large local-memory frame per thread: its own kernel,
+// launched only when a batch has such a contig)
+__global__ void __launch_bounds__(32) k_solve_huge(const Batch B, i32 nc) {
+    const int lane = threadIdx.x & 31;
+    for (i64 c = blockIdx.x; c < nc; c += gridDim.x)
         if (contig_is_huge(B, (int)c)) solve_contig_t<DHuge>(B, (int)c, lane, 32);
-        else if (contig_is_wide(B, (int)c)) solve_contig_t<D256>(B, (int)c, lane, 32);
 }
 // Overlap enumeration (st_ov_count / st_ov_fill) with the exit nodes compacted inside the warp: only exit nodes have
 // work, and they are about every second node, so a warp takes 64 consecutive nodes and hands the k-th exit node among them
@@ -458,6 +464,10 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
         cudaEventRecord(ctx->fork_ev, ctx->stream);                                              \
         cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
         k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
+        if (B.n_huge > 0) {                                                                      \
+            k_solve_huge<<<(nc_) < 1024 ? (nc_) : 1024, 32, 0, ctx->stream2>>>(B, (nc_));       \
+            ctx->launches++;                                                                     \
+        }                                                                                        \
         if (B.nch > 0) {                                                                         \
             /* one warp per chunk: out of shared memory when a chunk's tables fit (chunk.cuh), else out of HBM/L2 */ \
             const int stride_ = B.ch_warm + B.ch_core + B.ch_margin;                             \
