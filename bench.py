@@ -413,7 +413,8 @@ def main():
     from phanotate_b200.engine import Engine, PipelinedEngine, make_params
     from phanotate_b200 import _native as N
     from phanotate_b200.dist import Comm, bind_near_gpu, shard_contigs
-    numa = bind_near_gpu(local, world)                            # before the pinned buffers and the lane threads exist
+    # before the pinned buffers and the lane threads exist (PB200_NO_BIND=1: leave the process unbound)
+    numa = {"gpu": local, "bound": False, "how": "PB200_NO_BIND"} if os.environ.get("PB200_NO_BIND") else bind_near_gpu(local, world)
     eng = Engine(local)
     comm = Comm(eng, rank, world) if world > 1 else None
     params = make_params()
@@ -472,18 +473,28 @@ def main():
         if comm is not None:
             # every rank has its rows on its host; the cross-rank gather goes device to device over NCCL straight from the
             # lanes' tables, and rank 0 copies the other ranks' rows to its host
+            # (that copy runs on its own stream beside the next step's batch; the previous step's is collected here, the
+            # last one before the clock stops)
+            if rank == 0:
+                comm.fetch_wait()
             counts, total = comm.gather_calls(peng.engines)
             if rank == 0 and total > counts[0]:
-                moved += comm.fetch(counts[0], total - counts[0]).nbytes
+                comm.fetch_begin(counts[0], total - counts[0])
+                moved += (total - counts[0]) * N.CALL.itemsize
         return res, moved
 
     res, _ = e2e_step()                                            # warm-up: sizes the lanes' device buffers
     res, _ = e2e_step()
+    res, _ = e2e_step()
+    if comm is not None and rank == 0:
+        comm.fetch_wait()
     barrier()
     t1 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
         res, d2h = e2e_step()
+    if comm is not None and rank == 0:
+        comm.fetch_wait()                                          # the last step's rows of the other ranks are on the host
     wall_e2e = time.perf_counter() - t1
     barrier()
     errs = int((res.contigs["err"] != 0).sum())

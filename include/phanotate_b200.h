@@ -241,6 +241,10 @@ int pb200_comm_gather_calls(pb200_ctx* ctx, const void* const* parts, const int6
                             int64_t* counts_out, const pb200_call** rows_dev, int64_t* total);
 /* rank 0: rows [first, first+n) of the last gather -> host */
 int pb200_comm_fetch_gathered(pb200_ctx* ctx, int64_t first, int64_t n, pb200_call* out);
+/* rank 0: the same copy on its own stream, beside whatever the context runs next: _begin returns at once (page-locked
+ * `out`), _wait blocks until the rows are there; the next gather waits for a pending copy by itself */
+int pb200_comm_fetch_begin(pb200_ctx* ctx, int64_t first, int64_t n, pb200_call* out);
+int pb200_comm_fetch_wait(pb200_ctx* ctx);
 /* in-place reduction of n <= 64 doubles over the ranks (op 0 sum, 1 max); barrier */
 int pb200_comm_allreduce(pb200_ctx* ctx, double* vals, int32_t n, int32_t op);
 int pb200_comm_barrier(pb200_ctx* ctx);

@@ -110,6 +110,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_comm_destroy.argtypes = [vp]
     lib.pb200_comm_gather_calls.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.pb200_comm_fetch_gathered.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
+    lib.pb200_comm_fetch_begin.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
+    lib.pb200_comm_fetch_wait.argtypes = [vp]
     lib.pb200_comm_allreduce.argtypes = [vp, vp, i32, i32]
     lib.pb200_comm_barrier.argtypes = [vp]
     lib.pb200_comm_nccl_version.argtypes = []
@@ -127,5 +129,5 @@ EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb
            "pb200_bellman_ford", "pb200_connect", "pb200_stage_times", "pb200_stage_gaps", "pb200_launch_count", "pb200_last_run_ms",
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes", "pb200_fasta_count",
            "pb200_fasta_parse", "pb200_format_tabular", "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_destroy",
-           "pb200_comm_gather_calls", "pb200_comm_fetch_gathered", "pb200_comm_allreduce", "pb200_comm_barrier",
+           "pb200_comm_gather_calls", "pb200_comm_fetch_gathered", "pb200_comm_fetch_begin", "pb200_comm_fetch_wait", "pb200_comm_allreduce", "pb200_comm_barrier",
            "pb200_comm_nccl_version", "pb200_mark", "pb200_elapsed_ms"]

@@ -96,6 +96,8 @@ class Comm:
         self.counts = [0] * self.world
         self.total = 0
         self._host = np.zeros(0, dtype=N.CALL)
+        self._async = [np.zeros(0, dtype=N.CALL), np.zeros(0, dtype=N.CALL)]
+        self._flip, self._pending = 0, None
 
     def gather_calls(self, engines=None):
         """Call tables -> rank 0's device memory.  engines: the contexts whose tables make up this rank's rows, in order
@@ -135,6 +137,29 @@ class Comm:
             self.e._ck(self.lib.pb200_comm_fetch_gathered(self.e.ctx, first, n, out.ctypes.data))
         return out
 
+    def fetch_begin(self, first=0, n=None):
+        """rank 0: start copying rows [first, first+n) of the last gather to the host on a stream of its own (it runs beside
+        the next batch); fetch_wait() returns them.  Two page-locked buffers alternate, so the rows of one gather stay valid
+        while the next one is on its way."""
+        n = self.total - first if n is None else n
+        self._flip ^= 1
+        buf = self._async[self._flip]
+        if n > len(buf):
+            if len(buf):
+                self.e.unpin(buf)
+            buf = np.zeros(n + n // 4 + 1024, dtype=N.CALL)
+            self.e.pin(buf)
+            self._async[self._flip] = buf
+        self._pending = buf[:n]
+        self.e._ck(self.lib.pb200_comm_fetch_begin(self.e.ctx, first, n, buf.ctypes.data))
+
+    def fetch_wait(self):
+        if self._pending is None:
+            return None
+        self.e._ck(self.lib.pb200_comm_fetch_wait(self.e.ctx))
+        out, self._pending = self._pending, None
+        return out
+
     def allreduce(self, values, op="sum"):
         v = np.asarray(values, dtype=np.float64).copy()
         self.e._ck(self.lib.pb200_comm_allreduce(self.e.ctx, v.ctypes.data, len(v), 1 if op == "max" else 0))
@@ -144,6 +169,11 @@ class Comm:
         self.e._ck(self.lib.pb200_comm_barrier(self.e.ctx))
 
     def close(self):
+        self.fetch_wait()
+        for b in self._async:
+            if len(b):
+                self.e.unpin(b)
+        self._async = [np.zeros(0, dtype=N.CALL), np.zeros(0, dtype=N.CALL)]
         if len(self._host):
             self.e.unpin(self._host)
             self._host = np.zeros(0, dtype=N.CALL)
@@ -216,7 +246,7 @@ def bind_near_gpu(index: int, world: int = 1) -> dict:
         # topology unknown: disjoint equal slices of the allowed cores per rank
         cores = sorted(allowed)
         per = len(cores) // max(world, 1)
-        if world > 1 and per >= 4:
+        if world > 1 and per >= 8:               # (fewer cores than a rank has host threads: binding would only hurt)
             ids, info["how"] = set(cores[index * per:(index + 1) * per]), "equal slices (topology hidden)"
     if len(ids) >= 4 and len(ids) < len(allowed):
         try:
