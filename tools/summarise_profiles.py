@@ -36,7 +36,8 @@ with open(P + tag + "_ncu_full_top_kernels.csv", "w") as fh:
         rd = float(d["dram__bytes_read.sum"]) * scale[uu[hh.index("dram__bytes_read.sum")]]
         wr = float(d["dram__bytes_write.sum"]) * scale[uu[hh.index("dram__bytes_write.sum")]]
         traffic[name] = rd + wr
-json.dump({"contigs": 10000, "contig_bp": 50000, "source": tag + "_ncu_full_top_kernels.csv (ncu --set full, one launch each, bench workload)",
+commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+json.dump({"contigs": 10000, "contig_bp": 50000, "commit": commit, "source": tag + "_ncu_full_top_kernels.csv (ncu --set full, one launch each, bench workload)",
            "kernels": traffic}, open(P + "dram_traffic.json", "w"), indent=1)
 if os.path.exists(G + tag + "_metrics_table.txt"):
     shutil.copy(G + tag + "_metrics_table.txt", P + tag + "_kernel_metrics_table.txt")
