@@ -184,6 +184,7 @@ PB_HDN void st_lv_init(const Batch& B, i64 v64) {
     const I128 rel = B.ch_dist[g.slot + (v - g.s)];
     B.dist128[v] = D128::is_inf(rel) ? rel : D128::add(rel, B.ch_off[id]);
     B.parent[v] = -1;
+    B.dirty[v] = 0;                          // (the one-warp sweep leaves them clear; st_tie_fix borrows them as node flags)
 }
 // a tight in-edge u -> v beside the parent: the tie record st_tie_fix works from (pad bit 1: made by this stage)
 // (v = -3 - c: the contig's target)

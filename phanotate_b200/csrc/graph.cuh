@@ -905,7 +905,8 @@ PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
 // and the reference's parent of v is the tight in-edge with the smallest (pass, sigma(x)).  The tight in-edges of v are
 // the sweep's parent plus the recorded ties whose value is the final distance.  Only contigs with ties do any work.
 // (Checked against the oracle's edge-order Bellman-Ford: tests/test_certified.py, tests/tie_audit.py.)
-#define TIE_MAXN 256
+#define TIE_MAXN 256          /* ties of one contig settled out of thread-local arrays */
+#define TIE_BIGN 16384        /* ... out of the batch-wide scratch; beyond this (an exact repeat over megabases) ERR_TIES */
 // insertion index of node a inside its family's run of the node order: forward family = nearest start, stop, then the
 // other starts by descending position; reverse family = stop-key node, then the starts by ascending position
 PB_HDN int tie_sigma_idx(const Batch& B, i32 a, i32 fam) {
@@ -938,13 +939,17 @@ PB_HDN bool tie_sigma_less(const Batch& B, i32 a, i32 b) {
 }
 // pass in which the edge x -> (some node) offers x's final distance; -1: an unsettled tie node lies on the chain,
 // -2: the chain is broken
-PB_HDN int tie_chain_pass(const Batch& B, i32 x, const i32* tv, const bool* done, int n, i32 limit) {
+// (flag != null: flag[y] says "y is an unsettled tie node" instead of the scan over the arrays)
+PB_HDN int tie_chain_pass(const Batch& B, i32 x, const i32* tv, const u8* done, int n, i32 limit, const u8* flag) {
     if (x == -2) return 1;
     int cnt = 1;
     i32 y = x;
     for (i32 steps = 0; steps <= limit; steps++) {
-        for (int a = 0; a < n; a++)
-            if (!done[a] && tv[a] == y) return -1;
+        if (flag) {
+            if (flag[y]) return -1;
+        } else
+            for (int a = 0; a < n; a++)
+                if (!done[a] && tv[a] == y) return -1;
         const i32 py = B.parent[y];
         if (py == -2) return cnt + 1;             // sigma(y) < sigma(source) always
         if (py < 0) return -2;
@@ -959,7 +964,7 @@ PB_HDN int tie_chain_pass(const Batch& B, i32 x, const i32* tv, const bool* done
 //   node[i] and x.  Returns the length, -1 if an unsettled tie node lies on the walked part, -2 if the chain is broken.
 #define TIE_K 48
 #define TIE_K_SHORT 6
-PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, const bool* done, int n, int kmax) {
+PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, const u8* done, int n, int kmax, const u8* flag) {
     int len = 0, c = 0;
     i32 y = x;
     while (len < kmax) {
@@ -967,8 +972,11 @@ PB_HDN int tie_walk(const Batch& B, i32 x, i32* node, int* cum, const i32* tv, c
         cum[len] = c;
         len++;
         if (y == -2) break;
-        for (int a = 0; a < n; a++)
-            if (!done[a] && tv[a] == y) return -1;
+        if (flag) {
+            if (flag[y]) return -1;
+        } else
+            for (int a = 0; a < n; a++)
+                if (!done[a] && tv[a] == y) return -1;
         const i32 py = B.parent[y];
         if (py < 0 && py != -2) return -2;
         if (tie_sigma_less(B, y, py)) c++;
@@ -999,25 +1007,62 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
     if (!cs->tie_head) return;
     const bool wide = contig_is_wide(B, c);
     const i32 nodes = B.cnode[c + 1] - B.cnode[c] + (B.nt > 0 ? 2 * (B.ctrna[c + 1] - B.ctrna[c]) : 0);
-    i32 tv[TIE_MAXN], tf[TIE_MAXN];
-    bool done[TIE_MAXN];
+    // the events at FINAL distances are the second (third ...) tight in-edges: counted first, then laid out oldest first --
+    // the sweep records in position order, so a tie node's chain mostly runs over nodes settled before it
     int n = 0;
     for (i32 k = cs->tie_head; k;) {
-        const TieEv* e = B.tie_ev + (k - 1);
+        TieEv* e = B.tie_ev + (k - 1);
         const WInt fin = (e->v == -3) ? B.tdist[c]
                          : contig_is_huge(B, c) ? DHuge::to_wint(B.dist_huge[e->v])
                          : (wide ? B.dist[e->v] : D128::to_wint(B.dist128[e->v]));
-        if (w_cmp(fin, e->cand) == 0) {           // the tie is at the node's FINAL distance: a second tight in-edge
-            if (n == TIE_MAXN) {
-                cs->err |= ERR_TIES;
-                return;
-            }
-            tv[n] = e->v;
-            tf[n] = e->from;
-            done[n] = false;
-            n++;
-        }
+        e->pad = (w_cmp(fin, e->cand) == 0) ? 8 : 0;               // (pad is free from here on: 8 = tight at the final distance)
+        n += e->pad ? 1 : 0;
         k = e->next;
+    }
+    if (n == 0) return;
+    i32 tvl[TIE_MAXN], tfl[TIE_MAXN];
+    u8 donel[TIE_MAXN];
+    i32* tv = tvl;
+    i32* tf = tfl;
+    u8* done = donel;
+    u8* flag = nullptr;
+    if (n <= TIE_MAXN) {
+        // small (every ordinary contig): thread-local arrays, filled oldest first
+        int at = n;
+        for (i32 k = cs->tie_head; k;) {
+            const TieEv* e = B.tie_ev + (k - 1);
+            if (e->pad == 8) {
+                --at;
+                tvl[at] = e->v;
+                tfl[at] = e->from;
+                donel[at] = 0;
+            }
+            k = e->next;
+        }
+    } else {
+        // large (exact tandem repeats over tens of kb: a tie per repeat unit): a region of the batch-wide scratch, and a
+        // per-node flag "unsettled tie node" (the solve's dirty flags: all clear once a sweep has ended) instead of scans
+        const u32 base = n <= TIE_BIGN ? PB_ATOMIC_ADD_RET(B.tie_n + 1, (u32)n) : 0u;
+        if (n > TIE_BIGN || base + (u32)n > (u32)B.tie_cap) {
+            cs->err |= ERR_TIES;
+            return;
+        }
+        tv = B.tie_tv + base;
+        tf = B.tie_tf + base;
+        done = B.tie_done + base;
+        flag = B.dirty;
+        int at = n;
+        for (i32 k = cs->tie_head; k;) {
+            const TieEv* e = B.tie_ev + (k - 1);
+            if (e->pad == 8) {
+                --at;
+                tv[at] = e->v;
+                tf[at] = e->from;
+                done[at] = 0;
+                if (e->v >= 0) B.dirty[e->v] = 1;
+            }
+            k = e->next;
+        }
     }
     i32 ynode[TIE_K], znode[TIE_K];
     int ycum[TIE_K], zcum[TIE_K];
@@ -1035,8 +1080,8 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
                 const i32 x = tf[b];
                 int dy = -1, dz = -1;             // descents of both chains below their first common node
                 for (int kmax = TIE_K_SHORT; dy < 0 && kmax <= TIE_K && !wait && !broken; kmax = (kmax == TIE_K ? TIE_K + 1 : TIE_K)) {
-                    const int ylen = tie_walk(B, best, ynode, ycum, tv, done, n, kmax);
-                    const int zlen = ylen < 0 ? ylen : tie_walk(B, x, znode, zcum, tv, done, n, kmax);
+                    const int ylen = tie_walk(B, best, ynode, ycum, tv, done, n, kmax, flag);
+                    const int zlen = ylen < 0 ? ylen : tie_walk(B, x, znode, zcum, tv, done, n, kmax, flag);
                     if (ylen == -1 || zlen == -1) wait = true;
                     else if (ylen == -2 || zlen == -2) broken = true;
                     else
@@ -1050,8 +1095,8 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
                 }
                 if (wait || broken) break;
                 if (dy < 0) {                     // no common node within TIE_K: the absolute pass numbers
-                    dy = tie_chain_pass(B, best, tv, done, n, nodes);
-                    dz = tie_chain_pass(B, x, tv, done, n, nodes);
+                    dy = tie_chain_pass(B, best, tv, done, n, nodes, flag);
+                    dz = tie_chain_pass(B, x, tv, done, n, nodes, flag);
                     if (dy == -1 || dz == -1) {
                         wait = true;
                         break;
@@ -1065,7 +1110,7 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
             }
             if (broken) {
                 cs->err |= ERR_TIES;
-                return;
+                break;
             }
             if (wait) {
                 open = true;
@@ -1073,12 +1118,16 @@ PB_HDN void st_tie_fix(const Batch& B, i64 c64) {
             }
             if (v == -3) B.tparent[c] = best;
             else B.parent[v] = best;
+            if (flag && v >= 0) B.dirty[v] = 0;
             for (int b = a; b < n; b++)
-                if (tv[b] == v) done[b] = true;
+                if (tv[b] == v) done[b] = 1;
         }
-        if (!open) return;
+        if (!open || (cs->err & ERR_TIES)) break;
+        if (round == n) cs->err |= ERR_TIES;      // ties that wait on each other (a zero-weight cycle of tight edges)
     }
-    cs->err |= ERR_TIES;                          // ties that wait on each other (a zero-weight cycle of tight edges)
+    if (flag)                                     // leave the flags as the sweep left them
+        for (int a = 0; a < n; a++)
+            if (tv[a] >= 0) B.dirty[tv[a]] = 0;
 }
 
 // Stage 13: walk the parent pointers back from the target; the ORF edges on the path are the calls

@@ -158,7 +158,10 @@ struct Batch {
     WInt* tdist;          // [nc] distance of the target
     i32* tparent;         // [nc]
     TieEv* tie_ev;        // [tie_cap] per-contig lists (CStat.tie_head)
-    u32* tie_n;           // [1] events recorded
+    u32* tie_n;           // [0] events recorded, [1] scratch rows handed out by st_tie_fix
+    i32* tie_tv;          // [tie_cap] scratch of st_tie_fix for contigs with more than TIE_MAXN exact ties: node,
+    i32* tie_tf;          //           source of the tight edge,
+    u8* tie_done;         //           settled flag
     i32 tie_cap;
     // calls
     i32* call_tmp;        // [no] ORF ids on the path, per contig region

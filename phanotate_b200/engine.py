@@ -167,7 +167,7 @@ class Result:
     def check(self, contig: int | None = None):
         """Raise what the reference would have raised for a contig (or for any contig): KeyError for a letter outside
         the IUPAC alphabet (functions.py:20-24), ValueError for parallel edges (graphs.py:73-74) and for the Orfs.get_orf
-        lookup (orfs.py:62-69).  Anything else this implementation cannot finish (edge weights beyond 2048 bits, more than 256
+        lookup (orfs.py:62-69).  Anything else this implementation cannot finish (edge weights beyond 2048 bits, more than 16,384
         exact ties in one contig; DESIGN.md: known limits) raises PhanotateError."""
         cs = self.contigs if contig is None else self.contigs[contig:contig + 1]
         for i, c in enumerate(cs):
@@ -189,7 +189,7 @@ class Result:
                 continue                        # no source->target path: no calls (undefined in the reference)
             if err & N.ERR_TIES:
                 raise PhanotateError("contig %d: more exact ties in the shortest path than this build settles in the "
-                                     "reference's edge order (256 per contig; exact tandem repeats) -- no calls rather "
+                                     "reference's edge order (16,384 per contig; an exact repeat over megabases) -- no calls rather "
                                      "than calls that might differ (device error bits 0x%x)" % (k, err))
             raise PhanotateError("contig %d: device error bits 0x%x" % (k, err))
 
