@@ -153,14 +153,17 @@ int pb200_set_contig_base(pb200_ctx* ctx, int32_t base);
  * nodes): a contig with more than `long_nodes` graph nodes (~28 bp per node; default 4096) is solved as chunks of `core`
  * nodes (256), one warp each, swept from `warm` nodes upstream (768) to `margin` nodes downstream (64); the chunks'
  * distances are put together and EVERY node's Bellman equation is checked, so the result is the exact solve whatever
- * the geometry (a contig that fails the check is solved again by one sweep).  The geometry only moves the time. */
+ * the geometry (a contig that fails the check is tried once more with four times the warm-up -- only while the library
+ * picks the geometry itself -- and then solved again by one sweep).  The geometry only moves the time. */
 int pb200_set_chunking(pb200_ctx* ctx, int32_t core, int32_t warm, int32_t margin, int32_t long_nodes);
 
 /* out[0..7] = n_contigs, n_bases, n_nodes, n_orfs, n_overlap_edges, n_bridge_edges, n_calls, n_edges */
 int pb200_sizes(pb200_ctx* ctx, int64_t out[8]);
 /* out[0] = ORFs whose weight went through the literal Decimal chain before the solve, out[1] = after
  * it (called CDS), out[2] = overlap edges through the literal power, out[3] = chunks the long contigs were solved
- * in, out[4] = long contigs whose chunked solve failed its check and was redone by one sweep, out[5] = tRNA hits; rest reserved */
+ * in, out[4] = long contigs whose chunked solve failed its check and was redone by one sweep, out[5] = tRNA hits, out[6] = ORF weights beyond 256 bits (their contigs solved
+ * with 2048-bit distances), out[7] = 1 if some long contig needed the second attempt of the chunked solve (four times the
+ * warm-up) */
 int pb200_stats(pb200_ctx* ctx, int64_t out[8]);
 /* the integer weight the solver used for every ORF edge: trunc(Orf.weight * 1000) (edges.py:22) as
  * 8 little-endian 32-bit limbs, two's complement, per ORF */

@@ -93,7 +93,7 @@ PB_HD SolveRange chunk_range(const Batch& B, const ChunkGeo& g) {
 // 1. the sweep of one chunk (host statement; the kernel runs solve_contig_win<32, true>)
 PB_HDN void chunk_solve(const Batch& B, i32 id, int lane, int NL) {
     const ChunkGeo g = chunk_geo(B, id);
-    if (contig_is_wide(B, g.c)) return;
+    if (!chunk_active(B, g.c)) return;
     const SolveRange R = chunk_range(B, g);
     solve_contig_t<D128, true>(B, g.c, lane, NL, &R);
 }
@@ -104,9 +104,9 @@ PB_HDN void st_chunk_delta(const Batch& B, i64 id64) {
     if (id64 >= B.nch) return;
     const i32 id = (i32)id64;
     const ChunkGeo g = chunk_geo(B, id);
+    if (!chunk_active(B, g.c)) return;
     I128 zero = D128::from_i64(0);
     B.ch_off[id] = zero;
-    if (contig_is_wide(B, g.c)) return;
     if (g.s == g.nb) {
         B.ch_flag[id] = 1;                 // swept from the contig's real source: absolute distances
         return;
@@ -143,7 +143,7 @@ PB_HDN void st_chunk_delta(const Batch& B, i64 id64) {
 // item = contig (a warp: each lane sums a run of consecutive chunks, the lanes' totals are combined, then every lane
 // writes its run)
 PB_HDN void chunk_prefix(const Batch& B, int c, int lane, int NL) {
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const i32 ib = (i32)B.ch_cnt[c], ie = (i32)B.ch_cnt[c + 1];
     const i32 per = (ie - ib + NL - 1) / NL;
     const i32 a = ib + lane * per, b = a + per < ie ? a + per : ie;
@@ -178,7 +178,7 @@ PB_HDN void st_lv_init(const Batch& B, i64 v64) {
     if (v64 >= B.nn) return;
     const i32 v = (i32)v64;
     const int c = B.n_contig[v];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const i32 id = (i32)B.ch_cnt[c] + (v - B.cnode[c]) / B.ch_core;
     const ChunkGeo g = chunk_geo(B, id);
     const I128 rel = B.ch_dist[g.slot + (v - g.s)];
@@ -192,7 +192,7 @@ PB_HD void lv_tie(const Batch& B, int c, i32 v, i32 from, const I128& cand) {
     PB_ATOMIC_ADD(&B.cs[c].n_ties, 1u);
     TieEv* e = tie_slot(B, c, v, from);
     if (e) {
-        e->pad = 3;
+        e->pad = 3 | (B.ch_round << 4);
         u64* w = (u64*)&e->cand;
         w[0] = cand.lo;
         w[1] = (u64)cand.hi;
@@ -204,7 +204,7 @@ PB_HDN void st_lv_node(const Batch& B, i64 v64) {
     if (v64 >= B.nn) return;
     const i32 v = (i32)v64;
     const int c = B.n_contig[v];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const u32 wv = B.n_pk[v];
     const int kv = (int)(wv & 3), pv = (int)(wv >> 4);
     if (!kind_is_entry(kv)) return;
@@ -251,7 +251,7 @@ PB_HD void lv_edge(const Batch& B, int c, i32 u, i32 v, const I128& w) {
 PB_HDN void st_lv_orf(const Batch& B, i64 oi) {
     if (oi >= B.no) return;
     const int c = B.o_contig[oi];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const i32 sn = B.o_node[oi], kn = B.n_mate[sn];            // start node, stop-key node
     const bool fwd = B.o_frame[oi] > 0;
     lv_edge(B, c, fwd ? sn : kn, fwd ? kn : sn, D128::load_w(B.o_wint + oi));
@@ -261,7 +261,7 @@ PB_HDN void st_lv_ov(const Batch& B, i64 k) {
     if (k >= B.nov) return;
     const i32 u = B.ov_src[k];
     const int c = B.n_contig[u];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const i64 w64 = B.ov_w64[k];
     lv_edge(B, c, u, B.ov_dst[k], w64 != OV_W64_WIDE ? D128::from_i64(w64) : D128::load_w(B.ov_wint + k));
 }
@@ -270,7 +270,7 @@ PB_HDN void st_lv_br(const Batch& B, i64 k) {
     if (k >= B.nbr) return;
     const i32 u = B.br_src[k];
     const int c = B.n_contig[u];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     lv_edge(B, c, u, B.br_dst[k], D128::load_w(B.br_wint + k));
 }
 // 3d. a reachable node must have a tight in-edge.  item = node
@@ -278,14 +278,14 @@ PB_HDN void st_lv_check(const Batch& B, i64 v64) {
     if (v64 >= B.nn) return;
     const i32 v = (i32)v64;
     const int c = B.n_contig[v];
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     if (!D128::is_inf(B.dist128[v]) && B.parent[v] == -1) chunk_viol(B, c);
 }
 // 3e. exit -> target within 2000 bp of the right end (functions.py:448-451).  item = contig
 PB_HDN void st_lv_target(const Batch& B, i64 c64) {
     if (c64 >= B.nc) return;
     const int c = (int)c64;
-    if (!contig_chunked(B, c)) return;
+    if (!chunk_active(B, c)) return;
     const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
     const int L = B.cs[c].L;
     I128 td = D128::inf();
@@ -311,6 +311,22 @@ PB_HDN void st_lv_target(const Batch& B, i64 c64) {
         }
     B.tdist[c] = D128::to_wint(td);
     B.tparent[c] = tp;
+}
+// 3f. between the attempts: contigs whose check failed.  item = contig
+PB_HDN void st_chunk_viol_count(const Batch& B, i64 c) {
+    if (c >= B.nc) return;
+    if (contig_chunked(B, (int)c) && B.cs[c].chunk_viol) PB_ATOMIC_ADD(B.lit_cnt + 6, 1u);
+}
+// ... they go into the second attempt: a four times longer warm-up forgets the stand-in source where the first did not
+// (sequence with few stops -- GC >= 70 % -- coalesces over 30-60 kb instead of 5-10)
+PB_HDN void st_chunk_retry_mark(const Batch& B, i64 c) {
+    if (c >= B.nc) return;
+    CStat* cs = B.cs + c;
+    if (contig_chunked(B, (int)c) && cs->chunk_viol) {
+        cs->chunk_retry = 1;
+        cs->chunk_viol = 0;
+        cs->n_ties = 0;
+    }
 }
 // 4. contigs whose assembled distances failed a check: the one-warp sweep (host statement; the kernel runs
 // solve_contig_win<32>)
@@ -622,7 +638,7 @@ __global__ void __launch_bounds__(32) k_chunk_solve_smem(const Batch B, int stri
     const int lane = threadIdx.x;
     for (i64 id = blockIdx.x; id < B.nch; id += gridDim.x) {
         const ChunkGeo g = chunk_geo(B, (i32)id);
-        if (contig_is_wide(B, g.c)) continue;
+        if (!chunk_active(B, g.c)) continue;
         solve_chunk_smem(B, g, lane, chs_smem, stride, ecap);
         __syncwarp();
     }

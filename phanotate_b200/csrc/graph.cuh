@@ -890,6 +890,8 @@ PB_HD bool contig_is_wide(const Batch& B, int c) { return B.cs[c].wide || (B.fla
 PB_HD bool contig_is_huge(const Batch& B, int c) { return B.cs[c].huge != 0; }
 // a long contig whose solve runs as chunks (chunk.cuh) instead of one sweep
 PB_HD bool contig_chunked(const Batch& B, int c) { return B.ch_cnt && B.ch_cnt[c + 1] > B.ch_cnt[c] && !contig_is_wide(B, c); }
+// ... and taking part in the current attempt (the second one is only for the contigs whose first failed its check)
+PB_HD bool chunk_active(const Batch& B, int c) { return contig_chunked(B, c) && (B.ch_round == 0 || B.cs[c].chunk_retry); }
 PB_HDN void solve_contig(const Batch& B, int c, int lane, int NL) {
     if (contig_is_huge(B, c)) solve_contig_t<DHuge>(B, c, lane, NL);
     else if (contig_is_wide(B, c)) solve_contig_t<D256>(B, c, lane, NL);
@@ -992,8 +994,9 @@ PB_HDN void st_tie_link(const Batch& B, i64 k) {
     TieEv* e = B.tie_ev + k;
     const int c = (e->v <= -3) ? (-3 - e->v) : B.n_contig[e->v];
     if (e->v <= -3) e->v = -3;
-    // (pad bit 1: recorded by the chunked solve's check -- void once the contig fell back to the one-warp sweep)
-    if ((e->pad & 2) && B.cs[c].chunk_viol) return;
+    // (pad bit 1: recorded by the chunked solve's check, bit 4 = in its second attempt -- void once the contig fell back to
+    // the one-warp sweep, or when it belongs to an attempt that was repeated)
+    if ((e->pad & 2) && (B.cs[c].chunk_viol || ((e->pad >> 4) & 1) != (B.cs[c].chunk_retry ? 1 : 0))) return;
     if (e->pad & 1) {
         const u32 ext = (e->cand.w[3] >> 31) ? 0xFFFFFFFFu : 0u;
         for (int i = 4; i < WN; i++) e->cand.w[i] = ext;

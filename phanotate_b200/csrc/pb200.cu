@@ -26,7 +26,7 @@ static_assert(sizeof(pb200_orf) == sizeof(OrfRec), "OrfRec layout");
 static_assert(sizeof(pb200_node) == sizeof(NodeRec), "NodeRec layout");
 static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
 
-#define NPHASE 12
+#define NPHASE 14
 
 #ifndef PB_HOSTSIM
 // ================================================================================================
@@ -105,6 +105,8 @@ PB_KERNEL(st_lv_ov)
 PB_KERNEL(st_lv_br)
 PB_KERNEL(st_lv_check)
 PB_KERNEL(st_lv_target)
+PB_KERNEL(st_chunk_viol_count)
+PB_KERNEL(st_chunk_retry_mark)
 PB_KERNEL(st_pj_init)
 PB_KERNEL(st_pj_round)
 PB_KERNEL(st_pj_calls)
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_chunk_solve(const Batch B) {
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 id = warp; id < B.nch; id += nwarps) {
         const ChunkGeo g = chunk_geo(B, (i32)id);
-        if (contig_is_wide(B, g.c)) continue;
+        if (!chunk_active(B, g.c)) continue;
         const SolveRange R = chunk_range(B, g);
         if (B.flags & PB200_SOLVE_PLAIN) solve_contig_t<D128, true>(B, g.c, lane, 32, &R);
         else solve_contig_win<32, true>(B, g.c, lane, 0xFFFFFFFFu, &R);
@@ -453,22 +455,8 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
             CK(cudaGetLastError());                                                              \
         }                                                                                        \
     } while (0)
-#define PB_RUN_SOLVE(nc_)                                                                        \
+#define PB_LAUNCH_CHUNKS(stream_)                                                                \
     do {                                                                                         \
-        StageTime t_;                                                                            \
-        t_.name = "solve";                                                                       \
-        t_.a = ev_get(ctx);                                                                      \
-        t_.b = ev_get(ctx);                                                                      \
-        cudaEventRecord(t_.a, ctx->stream);                                                      \
-        /* the few contigs that need 256-bit distances run beside the others on a second stream */ \
-        cudaEventRecord(ctx->fork_ev, ctx->stream);                                              \
-        cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
-        k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
-        if (B.n_huge > 0) {                                                                      \
-            k_solve_huge<<<(nc_) < 1024 ? (nc_) : 1024, 32, 0, ctx->stream2>>>(B, (nc_));       \
-            ctx->launches++;                                                                     \
-        }                                                                                        \
-        if (B.nch > 0) {                                                                         \
             /* one warp per chunk: out of shared memory when a chunk's tables fit (chunk.cuh), else out of HBM/L2 */ \
             const int stride_ = B.ch_warm + B.ch_core + B.ch_margin;                             \
             const int ecap_ = stride_ + stride_ / 4;                                             \
@@ -485,12 +473,40 @@ static int dev_scan(pb200_ctx* ctx, T* data, i64 n) {   // exclusive, total -> d
                 cudaFuncSetAttribute(k_chunk_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
                 i64 gb_ = B.nch;                                                                 \
                 if (gb_ > (i64)ctx->sm_count * 32) gb_ = (i64)ctx->sm_count * 32;                \
-                k_chunk_solve_smem<<<(int)gb_, 32, smem_, ctx->stream2>>>(B, stride_, ecap_);    \
+                k_chunk_solve_smem<<<(int)gb_, 32, smem_, (stream_)>>>(B, stride_, ecap_);    \
             } else {                                                                             \
-                k_chunk_solve<<<grid_for(ctx, (i64)B.nch * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B); \
+                k_chunk_solve<<<grid_for(ctx, (i64)B.nch * 32, PB_BLOCK), PB_BLOCK, 0, (stream_)>>>(B); \
             }                                                                                    \
             ctx->launches++;                                                                     \
+    } while (0)
+#define PB_RUN_CHUNKS()                                                                          \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = "chunk_solve_retry";                                                           \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        PB_LAUNCH_CHUNKS(ctx->stream);                                                           \
+        cudaEventRecord(t_.b, ctx->stream);                                                      \
+        ctx->times.push_back(t_);                                                                \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
+#define PB_RUN_SOLVE(nc_)                                                                        \
+    do {                                                                                         \
+        StageTime t_;                                                                            \
+        t_.name = "solve";                                                                       \
+        t_.a = ev_get(ctx);                                                                      \
+        t_.b = ev_get(ctx);                                                                      \
+        cudaEventRecord(t_.a, ctx->stream);                                                      \
+        /* the few contigs that need 256-bit distances run beside the others on a second stream */ \
+        cudaEventRecord(ctx->fork_ev, ctx->stream);                                              \
+        cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0);                                      \
+        k_solve_wide<<<grid_for(ctx, (i64)(nc_) * 32, PB_BLOCK), PB_BLOCK, 0, ctx->stream2>>>(B, (nc_)); \
+        if (B.n_huge > 0) {                                                                      \
+            k_solve_huge<<<(nc_) < 1024 ? (nc_) : 1024, 32, 0, ctx->stream2>>>(B, (nc_));       \
+            ctx->launches++;                                                                     \
         }                                                                                        \
+        if (B.nch > 0) PB_LAUNCH_CHUNKS(ctx->stream2);                                            \
         cudaEventRecord(ctx->join_ev, ctx->stream2);                                             \
         /* PB200_SOLVE_HALF=1 (environment): two contigs per warp, 16 lanes each -- twice the sweeps in flight at the   \
            same register cost.  Measured SLOWER on the bench workload (7.6 against 6.8 ms: the two halves' divergent    \
@@ -679,6 +695,11 @@ static int dev_scan(pb200_ctx*, T* data, i64 n) {
         for (i32 c_ = 0; c_ < (nc_); c_++) solve_contig(B, c_, 0, 1);  \
         for (i32 id_ = 0; id_ < B.nch; id_++) chunk_solve(B, id_, 0, 1); \
         ctx->launches++;                                               \
+    } while (0)
+#define PB_RUN_CHUNKS()                                                  \
+    do {                                                                 \
+        for (i32 id_ = 0; id_ < B.nch; id_++) chunk_solve(B, id_, 0, 1); \
+        ctx->launches++;                                                 \
     } while (0)
 #define PB_RUN_FALLBACK(nc_)                                             \
     do {                                                                 \
@@ -1218,6 +1239,7 @@ int pb200_stats(pb200_ctx* ctx, int64_t out[8]) {
     out[1] = B.lit_all ? 0 : B.n_lit_post;
     out[2] = (B.flags & PB200_LITERAL) ? B.nov : B.n_ovlit;
     out[5] = B.nt;                                    // tRNA hits of the run
+    out[7] = B.ch_round;                              // 1: some long contig needed the second attempt of the chunked solve
     out[6] = B.n_huge;                                // ORF weights beyond 256 bits (their contigs solved at 2048 bits)
     out[3] = B.nch;                                   // chunks the long contigs were solved in
     if (B.nch > 0) {                                  // long contigs that failed the check and were solved by one sweep

@@ -76,7 +76,7 @@ struct CStat {
     i32 huge;               // some ORF weight needs more than 256 bits: 2048-bit distances in the solve (score.cuh: HInt)
     i32 huge_pad;
     u32 chunk_viol;         // chunked solve (chunk.cuh): some node failed the Bellman check -> the contig is solved again by one sweep
-    u32 chunk_pad;
+    u32 chunk_retry;        // ... after a second attempt with a four times longer warm-up (1: this contig is in it)
 };
 
 // an equal-distance relaxation seen by the sweep: edge from -> v offered `cand` when dist[v] was already `cand`
@@ -238,6 +238,7 @@ struct Batch {
     // chunked solve of long contigs (chunk.cuh)
     u32* ch_cnt;          // [nc+1] chunks per contig, then exclusive offsets (0 chunks: the contig is solved by one sweep)
     i32 nch;              // chunks in the batch
+    i32 ch_round;         // 0: first attempt of the chunked solve, 1: second attempt (longer warm-up) of the contigs that failed
     i32 ch_core, ch_warm, ch_margin, ch_long;   // nodes per chunk / of warm-up before it / of margin behind it; contigs above ch_long nodes are chunked
     struct I128* ch_dist; // [nch * (ch_warm + ch_core + ch_margin)] private distances of every chunk (relative to its stand-in source)
     u8* ch_dirty;         // same shape

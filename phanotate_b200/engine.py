@@ -84,6 +84,7 @@ class Result:
         engine._ck(engine.lib.pb200_stats(engine.ctx, st.ctypes.data))
         self.n_literal_presolve, self.n_literal_postsolve, self.n_literal_overlaps = (int(v) for v in st[:3])
         self.n_chunks, self.n_chunk_fallbacks, self.n_trnas = int(st[3]), int(st[4]), int(st[5])
+        self.n_huge_weights, self.chunk_second_attempt = int(st[6]), bool(st[7])
         self.launches = int(engine.lib.pb200_launch_count(engine.ctx))
         self.stage_ms = engine._stage_times()
 

@@ -122,6 +122,38 @@ def test_chunked_equals_one_sweep_on_adversarial_contigs(sim):
         assert [int(v) for v in one.contigs["err"]] == [int(v) for v in ch.contigs["err"]]
 
 
+def check_second_attempt(e):
+    """sequence with few stops (GC 70-85 %) forgets the stand-in source over 30-60 kb, not 5-10: the default geometry fails
+    its check there, the second attempt (four times the warm-up) passes -- no contig falls back to the one-warp sweep"""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"acgt", dtype=np.uint8)
+    seqs = [bytes(acgt[rng.choice(4, 400000, p=[(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])]) for gc in (.5, .75, .85)]
+    seqs.append(synth.long_contig(6))
+    one = e.run(seqs, flags=N.SOLVE_NOCHUNK)
+    res = e.run(seqs)
+    assert res.n_chunks > 0 and res.chunk_second_attempt and res.n_chunk_fallbacks == 0
+    assert np.array_equal(one.calls, res.calls) and int((res.contigs["err"] != 0).sum()) == 0
+    res = e.run(seqs[:1] + seqs[3:])                       # nothing fails here: one attempt
+    assert res.n_chunks > 0 and not res.chunk_second_attempt and res.n_chunk_fallbacks == 0
+
+
+def test_second_attempt_with_longer_warm_up(tmp_path):
+    e = engine.Engine(0, lib_path=hostsim_path())          # (a fresh context: the library picks the geometry)
+    try:
+        check_second_attempt(e)
+    finally:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_second_attempt_with_longer_warm_up_on_gpu():
+    e = engine.Engine(0)
+    try:
+        check_second_attempt(e)
+    finally:
+        e.close()
+
+
 def test_mixed_batch_of_short_and_long_contigs(sim):
     """long contigs in the middle of a batch of short ones: only they are chunked, every contig's calls stay what they are alone"""
     seqs = [seq_of("phiX174").encode(), synth.long_contig(3), seq_of("lambda").encode(), seq_of("T4").encode(), seq_of(STRESS[5]).encode()]
