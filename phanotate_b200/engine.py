@@ -385,6 +385,10 @@ class PipelinedEngine:
         lanes = min(len(self.engines), max(n, 1))
         # consecutive groups of contigs; the first is half as large as the others so that kernels start early
         weights = [1.0] + [2.0] * (lanes - 1)
+        import os
+        if os.environ.get("PB200_LANE_WEIGHTS"):                  # experiments: relative sizes of the groups, e.g. "1,3,4,4"
+            w = [float(x) for x in os.environ["PB200_LANE_WEIGHTS"].split(",")]
+            weights = (w + [w[-1]] * lanes)[:lanes]
         acc, total, cuts = 0.0, sum(weights), [0]
         for k in range(lanes - 1):
             acc += weights[k]

@@ -316,3 +316,41 @@ def test_cli_tabular_fast_path_equals_per_locus_writer(sim_engine, capsys, tmp_p
             f.weight = '%E' % float(r["score"])
         locus.tabular(slow)
     assert fast == slow.getvalue() and "\t-\t" in fast
+
+
+@pytest.mark.gpu
+def test_cli_on_the_gpu_tabular_dump_and_genbank(capsys, tmp_path):
+    """The command line itself on the CUDA path (no engine injected): a three-record FASTA (T4, lambda, phiX174, one of them
+    gzipped away from the others) -> tabular rows == the reference goldens; --dump == the reference's edge text; the other
+    formats carry the same calls."""
+    import gzip
+    import hashlib
+    import fastpathz
+    import phanotate
+    from phanotate_modules import functions
+    functions.set_engine(None)
+    fastpathz._engine = None
+    data = os.path.join(ROOT, "tests", "data")
+    names = [("T4", "NC_000866.1.fasta"), ("lambda", "NC_001416.1.fasta"), ("phiX174", "phiX174.fasta")]
+    text = "".join(open(os.path.join(data, f)).read() for _, f in names)
+    p = tmp_path / "three.fasta"
+    p.write_text(text)
+    gz = tmp_path / "three.fasta.gz"
+    gz.write_bytes(gzip.compress(text.encode()))
+    for path in (p, gz):
+        phanotate.main([str(path)])
+        out = capsys.readouterr().out
+        blocks = out.split("#id:\t")[1:]
+        assert len(blocks) == 3
+        for (nm, _), b in zip(names, blocks):
+            rows = [l.split("\t") for l in b.splitlines()[2:]]
+            got = "".join("%s\t%s\t%s\t%s\n" % (((r[0], r[1]) if r[2] == "+" else (r[1], r[0])) + (r[2], r[4])) for r in rows)
+            assert got == golden_text(nm, "calls.tsv"), nm
+    px = tmp_path / "phix.fasta"
+    px.write_text(open(os.path.join(data, "phiX174.fasta")).read())
+    phanotate.main([str(px), "--dump"])
+    assert hashlib.md5(capsys.readouterr().out.encode()).hexdigest() == INDEX["phiX174"]["edges_md5"]
+    phanotate.main([str(p), "-f", "genbank"])
+    gb = capsys.readouterr().out
+    assert gb.count("LOCUS") == 3 and gb.count("     CDS             ") == sum(INDEX[n]["n_calls"] for n, _ in names)
+    functions.set_engine(None)
