@@ -354,3 +354,69 @@ def test_cli_on_the_gpu_tabular_dump_and_genbank(capsys, tmp_path):
     gb = capsys.readouterr().out
     assert gb.count("LOCUS") == 3 and gb.count("     CDS             ") == sum(INDEX[n]["n_calls"] for n, _ in names)
     functions.set_engine(None)
+
+
+def _comm_worker_script():
+    return r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+from phanotate_b200 import _native as N, engine, dist as pdist
+from helpers import STRESS, seq_of
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+names = ["phiX174"] + STRESS[:9] + ["lambda", "T4"]
+seqs = [seq_of(n).encode() for n in names]
+e = engine.Engine(int(os.environ.get("LOCAL_RANK", "0")))
+comm = pdist.Comm(e, rank, world)
+parts = pdist.shard_contigs([len(s) for s in seqs], world)
+for rep in range(3):                                  # (the gather buffer and the pinned host buffers are reused)
+    mine = e.run([seqs[i] for i in parts[rank]])
+    counts, total = comm.gather_calls()
+    assert counts[rank] == mine.n_calls and total == sum(counts)
+    s = comm.allreduce([mine.n_calls, rank], "sum")
+    assert int(s[0]) == total and int(s[1]) == world * (world - 1) // 2
+    assert comm.allreduce([float(rank)], "max")[0] == world - 1
+    if rank == 0:
+        rows = np.array(comm.fetch(0, total), copy=True)
+        comm.fetch_begin(0, total)
+        assert np.array_equal(comm.fetch_wait(), rows)
+comm.barrier()
+if rank == 0:
+    whole = e.run(seqs).calls
+    got = pdist.unshard_calls(rows, counts, parts)
+    assert len(got) == len(whole) and np.array_equal(got, whole)
+    print("NCCL_GATHER_OK", world, counts, e.lib.pb200_comm_nccl_version())
+comm.close()
+e.close()
+''' % (ROOT, ROOT)
+
+
+def _gpu_count():
+    try:
+        import ctypes
+        cuda = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        if cuda.cuInit(0) != 0:
+            return 0
+        cuda.cuDeviceGetCount(ctypes.byref(n))
+        return n.value
+    except OSError:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_nccl_gather_inside_the_library(tmp_path, world):
+    """The library's own communicator (csrc/comm.inc: raw NCCL, no PyTorch): every rank runs its LPT shard of a batch on its
+    GPU, the call tables are gathered to rank 0 (exact row counts), copied to the host both ways (blocking, and on the copy
+    stream), reductions and barrier work; the re-assembled table equals the whole batch run by one process.  One rank on
+    any GPU box; two ranks where the box has two GPUs."""
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    script = tmp_path / "w.py"
+    script.write_text(_comm_worker_script())
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29540 + world))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+                        "--master-addr", "127.0.0.1", "--master-port", str(29540 + world), str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert "NCCL_GATHER_OK %d" % world in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
