@@ -16,8 +16,9 @@ M=$M,dram__bytes_read.sum,dram__bytes_write.sum
 ncu --metrics $M --clock-control none -c 120 --csv --log-file gpurun_out/${TAG}_metrics.csv \
     python tools/prof_run.py 10000 1 > gpurun_out/${TAG}_metrics.log 2>&1
 python tools/ncu_table.py gpurun_out/${TAG}_metrics.csv > gpurun_out/${TAG}_metrics_table.txt
-ncu --metrics $M --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_long_metrics.csv \
-    python tools/long_contig.py 200 > gpurun_out/${TAG}_long_under_ncu.log 2>&1
+ncu --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_long_metrics.csv \
+    python tools/prof_long.py > gpurun_out/${TAG}_long_under_ncu.log 2>&1
 python tools/ncu_table.py gpurun_out/${TAG}_long_metrics.csv > gpurun_out/${TAG}_long_metrics_table.txt
 python tools/long_contig.py 200 > gpurun_out/${TAG}_long_contig_10Mb.json 2>/dev/null
+python tools/cli_throughput.py > gpurun_out/${TAG}_cli_file_to_text.json 2>/dev/null
 tail -c 600 gpurun_out/${TAG}_bench.json
