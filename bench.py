@@ -483,6 +483,31 @@ def main():
                 moved += (total - counts[0]) * N.CALL.itemsize
         return res, moved
 
+    def timed_resident_lanes(steps, warm):
+        """the same resident batch through the PipelinedEngine (its lanes still hold their groups of contigs: no copy in, no
+        copy out): the groups' kernels overlap on the GPU -- the tail of one group's solve runs beside the next group's scan.
+        Timed from a mark on lane 0's idle stream to the last mark of any lane (or of the gather's stream)."""
+        for _ in range(warm):
+            peng.run_packed(bases, offs, params, resident=True, fetch=False)
+            if comm is not None:
+                comm.gather_calls(peng.engines)
+        barrier()
+        n_launch = 0
+        for e in peng.engines:
+            e.lib.pb200_mark(e.ctx, 0)
+        for _ in range(steps):
+            peng.run_packed(bases, offs, params, resident=True, fetch=False)
+            n_launch += sum(int(e.lib.pb200_launch_count(e.ctx)) for e in peng.engines)
+            if comm is not None:
+                comm.gather_calls(peng.engines)
+        ends = list(peng.engines) + ([eng] if comm is not None else [])
+        for e in ends:
+            e.lib.pb200_mark(e.ctx, 1)
+        first = peng.engines[0]
+        ms = max(float(first.lib.pb200_elapsed_between_ms(first.ctx, 0, e.ctx, 1)) for e in ends)
+        barrier()
+        return ms, n_launch
+
     res, _ = e2e_step()                                            # warm-up: sizes the lanes' device buffers
     res, _ = e2e_step()
     res, _ = e2e_step()
@@ -499,6 +524,7 @@ def main():
     barrier()
     errs = int((res.contigs["err"] != 0).sum())
     e2e_calls = res.n_calls
+    lanes_ms, lanes_launches = timed_resident_lanes(args.steps, 2)
 
     # ---- every rank: a few of ITS contigs against the oracle port (the checker of this run's GPU result, never its source)
     nchk = 4 if world > 1 else 0
@@ -521,8 +547,8 @@ def main():
         eng.unpin(sb)
         strong = {"contigs_total": args.contigs, "contigs_this_rank": int(len(mine)), "ms": sms}
 
-    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0], "max")
-    dev_s, wall_e2e, strong_s = vals
+    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0, lanes_ms / 1e3], "max")
+    dev_s, wall_e2e, strong_s, lanes_s = vals
     sums = reduce([total_bp, ncalls, errs, mism, e2e_calls], "sum")
     job_bp, job_calls, errs, mism, job_e2e_calls = (int(round(x)) for x in sums)
 
@@ -532,7 +558,12 @@ def main():
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     if rank == 0:
-        value = job_bp * args.steps / dev_s / 1e9
+        value_one = job_bp * args.steps / dev_s / 1e9              # one context: one batch = one chain of kernels
+        value_lanes = job_bp * args.steps / lanes_s / 1e9          # PipelinedEngine: the batch as `lanes` overlapping groups
+        use_lanes = lanes_s > 0 and value_lanes > value_one
+        value = value_lanes if use_lanes else value_one
+        if use_lanes:
+            dev_s, launches = lanes_s, lanes_launches
         e2e = job_bp * args.steps / wall_e2e / 1e9
         # roofline of the dominant kernel (largest share of the step), algorithmic bytes = 1 B/bp + 24 B/CDS
         peak, peak_src = measured_peak_gbs()
@@ -563,8 +594,13 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "decimal28+f64x2+int128", "data": "synthetic",
                 "config": dict(workload_config(args, world), numa=numa), "clocks": clocks,
-                "timing": "value: CUDA events on the library's stream around the K steps (runs + NCCL gathers), max over ranks; "
-                          "e2e: wall clock around K PipelinedEngine runs from pinned host buffers, max over ranks",
+                "timing": "value: CUDA events around the K steps (runs + NCCL gathers), max over ranks, batch resident in HBM -- "
+                          "through %s; e2e: wall clock around K PipelinedEngine runs from pinned host buffers, max over ranks" % (
+                              "PipelinedEngine (%d overlapping groups of contigs, marks on the lanes' streams)" % args.lanes if use_lanes
+                              else "one context (marks on its stream)"),
+                "value_one_context": {"value": value_one, "unit": UNIT, "note": "one context = one chain of kernels per batch; the "
+                                      "stage table and the roofline below are from this run"},
+                "value_pipelined": {"value": value_lanes, "unit": UNIT, "lanes": args.lanes},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps,
                         "headline": "pinned host bases -> call tables on rank 0's host (SURVEY.md 8d)"},

@@ -226,6 +226,8 @@ int pb200_launch_count(pb200_ctx* ctx);
  * waits for mark b and returns the device time between marks a and b (a region of several runs and gathers) */
 int pb200_mark(pb200_ctx* ctx, int32_t k);
 float pb200_elapsed_ms(pb200_ctx* ctx, int32_t a, int32_t b);
+/* ... between mark a of one context and mark b of another context on the same device */
+float pb200_elapsed_between_ms(pb200_ctx* from, int32_t a, pb200_ctx* to, int32_t b);
 
 /* ---- multi-GPU: one process per GPU, contigs sharded over the ranks (they are independent:
  * phanotate.py:40-56 is a loop over loci), and ONE collective -- the gather of the ranks' call tables to rank 0.  Raw NCCL

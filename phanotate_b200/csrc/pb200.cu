@@ -1174,6 +1174,23 @@ float pb200_elapsed_ms(pb200_ctx* ctx, int32_t a, int32_t b) {
 #endif
 }
 
+// ... between mark a of one context and mark b of another on the same device (several contexts working on one batch)
+float pb200_elapsed_between_ms(pb200_ctx* from, int32_t a, pb200_ctx* to, int32_t b) {
+#ifndef PB_HOSTSIM
+    float v = -1.f;
+    if (!from || !to || a < 0 || a > 3 || b < 0 || b > 3 || !from->marks[a] || !to->marks[b] || from->device != to->device) return -1.f;
+    if (cudaEventSynchronize(to->marks[b]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&v, from->marks[a], to->marks[b]) != cudaSuccess) return -1.f;
+    return v;
+#else
+    (void)from;
+    (void)a;
+    (void)to;
+    (void)b;
+    return -1.f;
+#endif
+}
+
 float pb200_last_run_ms(pb200_ctx* ctx) {
 #ifndef PB_HOSTSIM
     float v = -1.f;
