@@ -134,7 +134,11 @@ class Result:
         raw = np.zeros((self.n_orfs, 8), dtype=np.uint32)
         self._e._ck(self._e.lib.pb200_get_orf_int_weights(self._e.ctx, raw.ctypes.data))
         out = []
-        for row in raw:
+        for i, row in enumerate(raw):
+            if int(row[7]) == 0x7FFFFFFE:        # marker: beyond 256 bits, the solve formed it from the Decimal weight
+                w = N.dec_to_decimal(self.orfs[i]["weight"]) * 1000
+                out.append(int(w))               # (truncation toward zero, like fastpathz: phanotate.py:55)
+                continue
             v = 0
             for k in range(7, -1, -1):
                 v = (v << 32) | int(row[k])
