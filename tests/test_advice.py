@@ -71,9 +71,9 @@ def check_astronomic_weights(e):
         assert res.call_rows(k) == want, k
     assert any(r[3] == "-7.525584E+174" for r in res.call_rows(0)) and any(r[3] == "-INF" for r in res.call_rows(2))
     res.check()
-    assert res.n_huge_weights == 2
+    assert res.n_huge_weights >= 2                         # (every start of the giant reading frame is such an ORF)
     ws = res.orf_int_weights()                             # the integers the solve used, the 2048-bit ones included
-    assert min(ws) < -(1 << 1000) and sum(1 for w in ws if abs(w) >> 240) == 2
+    assert min(ws) < -(1 << 1000) and sum(1 for w in ws if abs(w) >> 240) == res.n_huge_weights
 
 
 def test_astronomic_orf_weights_are_solved_exactly(sim):
