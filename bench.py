@@ -467,8 +467,17 @@ def main():
     #      `lanes` groups of contigs so that the copies of one group overlap the kernels of the others
     peng = PipelinedEngine(local, lanes=args.lanes)
 
-    def e2e_step():
-        res = peng.run_packed(bases, offs, params)                 # H2D bases+offsets, kernels, D2H calls+contig table
+    # input of the end-to-end leg: the batch as 4-bit letters (two bases per byte), the format a FASTA reader hands to the
+    # engine when the host link matters (pb200_pack4; packing is parsing, outside the metric like the rest of the parser:
+    # SURVEY.md 8d) -- half the bytes per step over PCIe.  The same leg from 1-byte letters is reported beside it.
+    packed = peng.pack4(bases)
+    peng.pin(packed)
+
+    def e2e_step(ascii_input=False):
+        if ascii_input:
+            res = peng.run_packed(bases, offs, params)             # H2D letters+offsets, kernels, D2H calls+contig table
+        else:
+            res = peng.run_packed(packed, offs, params, packed4=True)
         moved = res.calls.nbytes + res.contigs.nbytes
         if comm is not None:
             # every rank has its rows on its host; the cross-rank gather goes device to device over NCCL straight from the
@@ -522,6 +531,16 @@ def main():
         comm.fetch_wait()                                          # the last step's rows of the other ranks are on the host
     wall_e2e = time.perf_counter() - t1
     barrier()
+    # ... and from 1-byte letters
+    e2e_step(True)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step(True)
+    if comm is not None and rank == 0:
+        comm.fetch_wait()
+    wall_e2e_ascii = time.perf_counter() - t1
+    barrier()
     errs = int((res.contigs["err"] != 0).sum())
     e2e_calls = res.n_calls
     lanes_ms, lanes_launches = timed_resident_lanes(args.steps, 2)
@@ -547,11 +566,12 @@ def main():
         eng.unpin(sb)
         strong = {"contigs_total": args.contigs, "contigs_this_rank": int(len(mine)), "ms": sms}
 
-    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0, lanes_ms / 1e3], "max")
-    dev_s, wall_e2e, strong_s, lanes_s = vals
+    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0, lanes_ms / 1e3, wall_e2e_ascii], "max")
+    dev_s, wall_e2e, strong_s, lanes_s, wall_e2e_ascii = vals
     sums = reduce([total_bp, ncalls, errs, mism, e2e_calls], "sum")
     job_bp, job_calls, errs, mism, job_e2e_calls = (int(round(x)) for x in sums)
 
+    peng.unpin(packed)
     peng.close()
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -601,9 +621,13 @@ def main():
                 "value_one_context": {"value": value_one, "unit": UNIT, "note": "one context = one chain of kernels per batch; the "
                                       "stage table and the roofline below are from this run"},
                 "value_pipelined": {"value": value_lanes, "unit": UNIT, "lanes": args.lanes},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes + offs.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps,
-                        "headline": "pinned host bases -> call tables on rank 0's host (SURVEY.md 8d)"},
+                        "headline": "pinned host bases -> call tables on rank 0's host (SURVEY.md 8d)",
+                        "input": "4-bit letters, two bases per byte (pb200_pack4 / PB200_INPUT_PACKED4), expanded on the device"},
+                "e2e_ascii_input": {"value": job_bp * args.steps / wall_e2e_ascii / 1e9, "unit": UNIT,
+                                    "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes), "ms_per_step": 1e3 * wall_e2e_ascii / args.steps,
+                                    "input": "one byte per base (any case, IUPAC)"},
                 "gpu_launches": launches, "roofline": roof,
                 "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in sorted(stage.items(), key=lambda x: -x[1])},
                 "calls_per_step": job_calls, "contig_errors": errs,

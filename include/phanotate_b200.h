@@ -107,6 +107,8 @@ enum {
 enum {
     PB200_INPUT_DEVICE = 1,   /* flags of pb200_run: bases/offsets are device pointers */
     PB200_REUSE_INPUT = 2,    /* the batch uploaded by the previous pb200_run is still resident: skip the copy */
+    PB200_INPUT_PACKED4 = 256, /* `bases` holds 4-bit letters, two per byte (pb200_pack4): half the bytes over the host link;
+                                 the library expands them on the device.  Results are those of the lower-cased letters. */
     PB200_CALL_WEIGHTS = 16,  /* also fill pb200_call.weight with the 28-digit Decimal of every call (otherwise it is
                                  filled only where the Decimal chain ran anyway and is 0 elsewhere; pb200_call.score,
                                  the float that Locus.tabular prints with '%E', is always exact) */
@@ -144,6 +146,14 @@ int pb200_upload(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, i
  * to every exit / entry node within 500 bp.  A tRNA on the shortest path comes back as a call row with strand +-2 and
  * score -20.  pb200_get_nodes returns the tRNA nodes behind the regular ones (orf = -1 - k).  n = 0 clears the list. */
 int pb200_set_trnas(pb200_ctx* ctx, const int32_t* contig, const int32_t* start, const int32_t* stop, int32_t n);
+
+/* 4-bit letters.  pb200_pack4: letters -> codes (a c g t n r y s w k m b v d h, either case; 15 = any other byte, flagged by
+ * the run like the letter itself), two per byte, low nibble first, into out[(n + 1) / 2]; host threads, no context.
+ * pb200_run(..., PB200_INPUT_PACKED4) takes such a buffer for `bases` (offsets stay in bases);
+ * pb200_upload_packed4 = pb200_upload for it, `skip` (0 / 1) = the nibble of packed[0] the batch starts at (a group of
+ * contigs cut out of a larger packed batch may start in the middle of a byte). */
+int64_t pb200_pack4(const uint8_t* bases, int64_t n, uint8_t* out);
+int pb200_upload_packed4(pb200_ctx* ctx, const uint8_t* packed, int32_t skip, const int64_t* offsets, int32_t n_contigs);
 
 /* number added to the contig column of the call rows of the following runs (default 0): for a caller that cuts one
  * batch into groups for several contexts and wants the rows numbered in the whole batch */

@@ -238,6 +238,31 @@ __global__ void k_pack_nodes(const Batch B, NodeRec* out) {
 }
 __global__ void k_bf_literal(const BFArgs a) { bf_literal(a); }
 
+// 4-bit letters -> the lower-case letters the stages read (PB200_INPUT_PACKED4): 16 bases (8 bytes) per thread
+__constant__ unsigned char k_nib2chr[16] = {'a', 'c', 'g', 't', 'n', 'r', 'y', 's', 'w', 'k', 'm', 'b', 'v', 'd', 'h', '?'};
+__global__ void __launch_bounds__(256) k_unpack4(const unsigned char* __restrict__ packed, int skip, unsigned char* __restrict__ out, i64 nb) {
+    // base g of the batch is nibble g + skip of `packed` (low nibble first)
+    for (i64 g0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16; g0 < nb; g0 += (i64)gridDim.x * blockDim.x * 16) {
+        unsigned char o[16];
+        const i64 n0 = g0 + skip;
+        const i64 b0 = n0 >> 1;
+        unsigned char in[9];
+        const i64 nbytes = (nb + skip + 1) >> 1;
+#pragma unroll
+        for (int k = 0; k < 9; k++) in[k] = (b0 + k < nbytes) ? packed[b0 + k] : 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int nib = (int)(n0 & 1) + k;
+            o[k] = k_nib2chr[(in[nib >> 1] >> ((nib & 1) * 4)) & 15];
+        }
+        if (g0 + 16 <= nb) {
+            *(uint4*)(out + g0) = *(const uint4*)o;
+        } else {
+            for (int k = 0; k < 16 && g0 + k < nb; k++) out[g0 + k] = o[k];
+        }
+    }
+}
+
 // ---- exclusive prefix sums (three passes; T = u32 or u64 with two packed 32-bit counters)
 #define SCAN_TILE 2048
 template <typename T>
@@ -325,7 +350,7 @@ struct pb200_ctx {
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, side_ev = nullptr;
     std::string err;
     DevBuf ph[NPHASE];
-    DevBuf in_seq, in_off, scratch, scratch2, conn, conn_out;
+    DevBuf in_seq, in_off, in_pack, scratch, scratch2, conn, conn_out;
     Batch B;
     bool have = false;
     std::vector<StageTime> times;
@@ -644,7 +669,7 @@ struct pb200_ctx {
     std::vector<i32> t_contig, t_start, t_stop, t_first;
     std::string err;
     DevBuf ph[NPHASE];
-    DevBuf in_seq, in_off, scratch, conn, conn_out;
+    DevBuf in_seq, in_off, in_pack, scratch, conn, conn_out;
     Batch B;
     bool have = false;
     int launches = 0;
@@ -913,6 +938,34 @@ static int ensure_literal_orfs(pb200_ctx* ctx) {
     return 0;
 }
 
+// PB200_INPUT_PACKED4: two bases per byte (low nibble first), base g of the batch = nibble g + skip of `packed`.
+// Copies the packed letters to the device and expands them into the context's letter buffer (lower case, '?' for the
+// code of a letter outside the IUPAC alphabet -> ERR_CHAR like the letter itself would have given).
+static const char PB_NIB2CHR[17] = "acgtnryswkmbvdh?";
+static int stage_packed4(pb200_ctx* ctx, const uint8_t* packed, int skip, const int64_t* offsets, int32_t n_contigs) {
+    const i64 nb = offsets[n_contigs];
+    const size_t pbytes = (size_t)((nb + skip + 1) >> 1);
+    if (buf_ensure(ctx, ctx->in_seq, (size_t)nb + 64)) return -1;
+    if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
+    if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
+#ifndef PB_HOSTSIM
+    CK(cudaMemcpyAsync(ctx->in_pack.p, packed, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    i64 g = (nb / 16 + 255) / 256;
+    if (g > (i64)ctx->sm_count * 16) g = (i64)ctx->sm_count * 16;
+    if (g < 1) g = 1;
+    k_unpack4<<<(int)g, 256, 0, ctx->stream>>>((const unsigned char*)ctx->in_pack.p, skip, (unsigned char*)ctx->in_seq.p, nb);
+    CK(cudaGetLastError());
+#else
+    memcpy(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8);
+    for (i64 k = 0; k < nb; k++) {
+        const i64 nib = k + skip;
+        ctx->in_seq.p[k] = PB_NIB2CHR[(packed[nib >> 1] >> ((nib & 1) * 4)) & 15];
+    }
+#endif
+    return 0;
+}
+
 static int run_pipeline(pb200_ctx* ctx) {
     Batch& B = ctx->B;
 #include "driver.inc"
@@ -962,6 +1015,7 @@ void pb200_destroy(pb200_ctx* ctx) {
     for (int k = 0; k < NPHASE; k++) cudaFree(ctx->ph[k].p);
     cudaFree(ctx->in_seq.p);
     cudaFree(ctx->in_off.p);
+    cudaFree(ctx->in_pack.p);
     cudaFree(ctx->scratch.p);
     cudaFree(ctx->scratch2.p);
     cudaFree(ctx->conn.p);
@@ -981,6 +1035,7 @@ void pb200_destroy(pb200_ctx* ctx) {
     for (int k = 0; k < NPHASE; k++) free(ctx->ph[k].p);
     free(ctx->in_seq.p);
     free(ctx->in_off.p);
+    free(ctx->in_pack.p);
     free(ctx->scratch.p);
     free(ctx->conn.p);
     free(ctx->conn_out.p);
@@ -1048,6 +1103,15 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
         }
         B.seq = (const u8*)ctx->in_seq.p;
         B.coff = (const i64*)ctx->in_off.p;
+    } else if (flags & PB200_INPUT_PACKED4) {
+        B.nb = offsets[n_contigs];
+        if (B.nb < 1 || !bases) {
+            ctx->err = "empty batch";
+            return -2;
+        }
+        if (stage_packed4(ctx, bases, 0, offsets, n_contigs)) return -1;
+        B.seq = (const u8*)ctx->in_seq.p;
+        B.coff = (const i64*)ctx->in_off.p;
     } else {
         B.nb = offsets[n_contigs];
         if (B.nb < 1 || !bases) {
@@ -1065,6 +1129,10 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
     ctx->launches = 0;
     B.nb = offsets[n_contigs];
     if (flags & PB200_REUSE_INPUT) {
+        B.seq = (const u8*)ctx->in_seq.p;
+        B.coff = (const i64*)ctx->in_off.p;
+    } else if (flags & PB200_INPUT_PACKED4) {
+        if (stage_packed4(ctx, bases, 0, offsets, n_contigs)) return -1;
         B.seq = (const u8*)ctx->in_seq.p;
         B.coff = (const i64*)ctx->in_off.p;
     } else {
@@ -1138,6 +1206,24 @@ int pb200_set_trnas(pb200_ctx* ctx, const int32_t* contig, const int32_t* start,
     ctx->t_contig.assign(contig, contig + n);
     ctx->t_start.assign(start, start + n);
     ctx->t_stop.assign(stop, stop + n);
+    return 0;
+}
+
+// pb200_upload for 4-bit letters (see pb200_pack4): base g of the batch = nibble g + skip of `packed` (skip = 0 or 1: a
+// group of contigs cut out of a larger packed batch may start in the middle of a byte)
+int pb200_upload_packed4(pb200_ctx* ctx, const uint8_t* packed, int32_t skip, const int64_t* offsets, int32_t n_contigs) {
+    if (!ctx || !packed || !offsets || n_contigs < 1 || skip < 0 || skip > 1) return -2;
+    if (offsets[n_contigs] < 1) {
+        ctx->err = "empty batch";
+        return -2;
+    }
+#ifndef PB_HOSTSIM
+    CK(cudaSetDevice(ctx->device));
+#endif
+    if (stage_packed4(ctx, packed, skip, offsets, n_contigs)) return -1;
+#ifndef PB_HOSTSIM
+    CK(ctx_sync(ctx));
+#endif
     return 0;
 }
 
@@ -1495,6 +1581,34 @@ static int host_threads(int64_t work_bytes, int64_t min_per_thread = 4 << 20) {
     if (t > by_size) t = (int)by_size;
     return t < 1 ? 1 : t;
 }
+// letters -> 4-bit codes, two per byte, low nibble first (a c g t n r y s w k m b v d h, any case; 15 = anything else, which
+// the run flags like the letter itself: KeyError in the reference, functions.py:20-24).  Host threads; no context needed.
+// `out` holds (n + 1) / 2 bytes.  What pb200_run(..., PB200_INPUT_PACKED4) and pb200_upload_packed4 take: half the bytes
+// over the host link.
+int64_t pb200_pack4(const uint8_t* bases, int64_t n, uint8_t* out) {
+    if (!bases || !out || n < 0) return -2;
+    unsigned char code[256];
+    memset(code, 15, sizeof code);
+    for (int k = 0; k < 15; k++) {
+        code[(unsigned char)PB_NIB2CHR[k]] = (unsigned char)k;
+        code[(unsigned char)(PB_NIB2CHR[k] - 32)] = (unsigned char)k;
+    }
+    const int T = host_threads(n, 8 << 20);
+    const int64_t pairs = (n + 1) / 2;
+    auto work = [&](int t) {
+        const int64_t a = pairs / T * t, b = (t == T - 1) ? pairs : pairs / T * (t + 1);
+        for (int64_t k = a; k < b; k++) {
+            const unsigned lo = code[bases[2 * k]], hi = (2 * k + 1 < n) ? code[bases[2 * k + 1]] : 0u;
+            out[k] = (uint8_t)(lo | (hi << 4));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return pairs;
+}
+
 static int64_t fa_count_range(const char* p, const char* end) {
     int64_t rec = 0;
     while (p < end) {

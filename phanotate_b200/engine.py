@@ -256,9 +256,18 @@ class Engine:
         c, a, b = (np.ascontiguousarray(arr[:, k]) for k in range(3))
         self._ck(self.lib.pb200_set_trnas(self.ctx, c.ctypes.data, a.ctypes.data, b.ctypes.data, len(arr)))
 
+    def pack4(self, bases):
+        """letters (uint8) -> 4-bit codes, two per byte (pb200_pack4): the input format that costs half the host link.
+        What run_packed(..., packed4=True) takes; a FASTA reader would emit it directly."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        out = np.zeros((len(bases) + 1) // 2, dtype=np.uint8)
+        if self.lib.pb200_pack4(bases.ctypes.data, len(bases), out.ctypes.data) < 0:
+            raise PhanotateError("pb200_pack4 failed")
+        return out
+
     def run_packed(self, bases, offsets, params=None, names=None, resident=False, fetch=True, literal=False, flags=0,
-                   call_weights=False):
-        """bases: uint8 array of concatenated contigs, offsets: int64[n+1].
+                   call_weights=False, packed4=False):
+        """bases: uint8 array of concatenated contigs (packed4=True: their 4-bit codes from pack4), offsets: int64[n+1].
 
         resident=True reuses the batch the previous call uploaded (inputs already in HBM).
         fetch=False skips copying the result tables to the host (returns None).
@@ -276,7 +285,8 @@ class Engine:
         self._ck(self.lib.pb200_run(self.ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                     params.ctypes.data,
                                     (N.REUSE_INPUT if resident else 0) | (N.LITERAL if literal else 0) |
-                                    (N.CALL_WEIGHTS if call_weights else 0) | int(flags)))
+                                    (N.CALL_WEIGHTS if call_weights else 0) | (N.INPUT_PACKED4 if packed4 and not resident else 0) |
+                                    int(flags)))
         return Result(self, names) if fetch else None
 
     def set_chunking(self, core=256, warm=768, margin=64, long_nodes=4096):
@@ -377,10 +387,14 @@ class PipelinedEngine:
             setattr(self, name, buf)
         return buf
 
+    def pack4(self, bases):
+        return self.engines[0].pack4(bases)
+
     def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0, resident=False,
-                   fetch=True):
+                   fetch=True, packed4=False):
         """resident=True: every lane still holds its group of this same batch from the previous call (no copy-in).
-        fetch=False: leave the tables on the device (returns None)."""
+        fetch=False: leave the tables on the device (returns None).
+        packed4=True: `bases` holds the 4-bit codes of the batch (pack4): half the bytes over the host link."""
         if params is None:
             params = make_params()
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
@@ -431,7 +445,9 @@ class PipelinedEngine:
             a, b = cuts[k], cuts[k + 1]
             e = self.engines[k]
             try:
-                sub_b, sub_o = bases[offsets[a]:offsets[b]], np.ascontiguousarray(offsets[a:b + 1] - offsets[a])
+                sub_o = np.ascontiguousarray(offsets[a:b + 1] - offsets[a])
+                # (4-bit letters: the group's bytes, and which nibble of the first one it starts at)
+                sub_b = bases[offsets[a] // 2:(offsets[b] + 1) // 2] if packed4 else bases[offsets[a]:offsets[b]]
                 e._ck(e.lib.pb200_set_contig_base(e.ctx, a))
                 try:
                     if not resident:
@@ -439,7 +455,10 @@ class PipelinedEngine:
                         # others are still being copied, instead of all copies sharing the link and ending together
                         if j and not uploaded[j - 1].wait(timeout=600):
                             raise PhanotateError("an earlier group failed to upload")
-                        e._ck(e.lib.pb200_upload(e.ctx, sub_b.ctypes.data, sub_o.ctypes.data, len(sub_o) - 1))
+                        if packed4:
+                            e._ck(e.lib.pb200_upload_packed4(e.ctx, sub_b.ctypes.data, int(offsets[a]) & 1, sub_o.ctypes.data, len(sub_o) - 1))
+                        else:
+                            e._ck(e.lib.pb200_upload(e.ctx, sub_b.ctypes.data, sub_o.ctypes.data, len(sub_o) - 1))
                 finally:
                     uploaded[j].set()
                 e.run_packed(sub_b, sub_o, params, fetch=False, literal=literal, call_weights=call_weights, flags=flags,

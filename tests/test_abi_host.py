@@ -97,3 +97,43 @@ def test_literal_bellman_ford_entry_point(sim):
     rc = sim.lib.pb200_bellman_ford(sim.ctx, 4, 4, src.ctypes.data, dst.ctypes.data, w.ctypes.data, 0, 3,
                                     path.ctypes.data, ctypes.byref(n))
     assert rc == 0 and list(path[:n.value]) == [0, 1, 3]
+
+
+def check_packed4_input(e, make_pipelined):
+    """PB200_INPUT_PACKED4: the batch as 4-bit letters (pb200_pack4) gives the tables of the 1-byte letters -- mixed case,
+    IUPAC codes and N runs (the stress contigs), contigs starting on odd offsets (groups of a PipelinedEngine start in the
+    middle of a byte), a letter outside the alphabet flagged like the letter itself."""
+    names = ["phiX174"] + STRESS[:24] + ["lambda"]
+    seqs = [seq_of(n).encode() for n in names]
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    assert any(int(o) & 1 for o in offs)
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    a = e.run_packed(bases, offs)
+    pk = e.pack4(bases)
+    assert len(pk) == (len(bases) + 1) // 2
+    b = e.run_packed(pk, offs, packed4=True)
+    assert np.array_equal(a.calls, b.calls) and np.array_equal(a.contigs, b.contigs)
+    assert np.array_equal(e.run_packed(pk, offs, resident=True).calls, a.calls)       # the expanded letters stay resident
+    p = make_pipelined()
+    try:
+        c = p.run_packed(pk, offs, packed4=True)
+        assert np.array_equal(a.calls, c.calls) and np.array_equal(a.contigs["err"], c.contigs["err"])
+    finally:
+        p.close()
+    bad = seqs[0][:900] + b"x" + seqs[0][900:2000]
+    r = e.run_packed(e.pack4(np.frombuffer(bad, dtype=np.uint8)), np.array([0, len(bad)], dtype=np.int64), packed4=True)
+    assert int(r.contigs[0]["err"]) == N.ERR_CHAR
+
+
+def test_packed4_input_on_host(sim):
+    check_packed4_input(sim, lambda: engine.PipelinedEngine(0, lanes=4, lib_path=HOSTSIM))
+
+
+@pytest.mark.gpu
+def test_packed4_input_on_gpu():
+    e = engine.Engine(0)
+    try:
+        check_packed4_input(e, lambda: engine.PipelinedEngine(0, lanes=4))
+    finally:
+        e.close()
