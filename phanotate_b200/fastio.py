@@ -24,8 +24,9 @@ def _library(lib=None):
     return _lib
 
 
-def read_fasta_packed(path, lib=None):
-    """-> (names, bases uint8[total], offsets int64[n+1]).  Record name = first word of the '>' line (like the
+def read_fasta_packed(path, lib=None, pack4=False):
+    """-> (names, bases uint8[total], offsets int64[n+1]); pack4=True: bases as 4-bit letters, two per byte (pb200_pack4;
+    what Engine.run_packed(..., packed4=True) takes: half the bytes over the host link).  Record name = first word of the '>' line (like the
     reader in phanotate_modules/file.py); sequence = every non-blank byte of the record's other lines, case kept
     (the library lower-cases like functions.py:144)."""
     lib = _library(lib)
@@ -48,7 +49,12 @@ def read_fasta_packed(path, lib=None):
     if got != nrec:
         raise RuntimeError("FASTA parse failed")
     names = [data[a:b].tobytes().decode() for a, b in zip(nb[:nrec].tolist(), ne[:nrec].tolist())]
-    return names, bases[:int(offsets[-1])], offsets
+    total = int(offsets[-1])
+    if pack4:
+        packed = np.zeros((total + 1) // 2, dtype=np.uint8)
+        lib.pb200_pack4(bases.ctypes.data, total, packed.ctypes.data)
+        return names, packed, offsets
+    return names, bases[:total], offsets
 
 
 def tabular_text(res, names, lib=None) -> bytes:
