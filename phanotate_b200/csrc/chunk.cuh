@@ -8,16 +8,18 @@
 //   1. the node list of a long contig is cut into chunks of ch_core nodes; every chunk is swept by its own warp from a
 //      stand-in source ch_warm nodes (~20 kb) upstream, into private distance arrays (chunk_solve);
 //   2. chunk k's distances differ from the true ones by one constant: the difference to chunk k-1 is read off the nodes
-//      in front of the cut, which both chunks hold (st_chunk_delta), and summed along the contig (st_chunk_prefix);
+//      in front of the cut, which both chunks hold (st_chunk_delta), and summed along the contig (chunk_prefix);
 //   3. EVERY node's Bellman equation is then checked against the assembled distances, edge by edge and in parallel
 //      (st_lv_*): no in-edge may offer less, and a reachable node needs a tight in-edge.  With positive cycles only,
 //      the equations have exactly one solution, so distances that pass ARE the reference's distances -- the speculation
 //      in 1-2 is never trusted.  The same pass yields the parents (the tight in-edge) and the exact ties (further tight
 //      in-edges) that st_tie_fix settles in the reference's edge order;
-//   4. a contig with any violated equation is solved again by the one-warp sweep (solve_fallback).
+//   4. a contig with any violated equation is tried once more with four times the warm-up (st_chunk_retry_mark: sequence
+//      with few stops forgets its source over 30-60 kb, not 5-10), and solved by the one-warp sweep if that fails too
+//      (solve_fallback).
 //
 // The back-trace over the parents (st_backtrack: 2 dependent loads per call) becomes pointer jumping (st_pj_*), the
-// coverage prefix-maximum behind the bridges (reach_contig) a three-pass scan over the chunks (st_reach_*).
+// coverage prefix-maximum behind the bridges (reach_contig) a three-pass scan over the chunks (reach_chunk*).
 #pragma once
 #include "graph.cuh"
 
