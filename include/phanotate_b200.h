@@ -231,6 +231,9 @@ int pb200_stage_times(pb200_ctx* ctx, const char** names, float* ms, int cap);
  * ms[i] = gap in front of stage names[i] */
 int pb200_stage_gaps(pb200_ctx* ctx, const char** names, float* ms, int cap);
 /* number of kernels launched by the last pb200_run */
+/* "%E" of a score exactly as printf (and Python's '%E' % weight, phanotate.py:75-76) rounds it; what pb200_format_tabular
+ * writes per row.  out: at least 32 bytes.  Returns the length. */
+int pb200_format_score(double x, char* out);
 int pb200_launch_count(pb200_ctx* ctx);
 /* stopwatch on the context's stream: pb200_mark records event k (0..3) behind everything queued so far; pb200_elapsed_ms
  * waits for mark b and returns the device time between marks a and b (a region of several runs and gathers) */

@@ -106,6 +106,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_fasta_parse.restype = ctypes.c_int64
     lib.pb200_format_tabular.argtypes = [vp, vp, i32, vp, vp, vp, ctypes.c_int64]
     lib.pb200_format_tabular.restype = ctypes.c_int64
+    lib.pb200_format_score.argtypes = [ctypes.c_double, vp]
     lib.pb200_mark.argtypes = [vp, i32]
     lib.pb200_elapsed_ms.argtypes = [vp, i32, i32]
     lib.pb200_elapsed_ms.restype = ctypes.c_float
@@ -136,4 +137,4 @@ EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb
            "pb200_device_calls", "pb200_pin_host", "pb200_unpin_host", "pb200_struct_sizes", "pb200_fasta_count",
            "pb200_fasta_parse", "pb200_format_tabular", "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_destroy",
            "pb200_comm_gather_calls", "pb200_comm_fetch_gathered", "pb200_comm_fetch_begin", "pb200_comm_fetch_wait", "pb200_comm_allreduce", "pb200_comm_barrier",
-           "pb200_comm_nccl_version", "pb200_mark", "pb200_elapsed_ms", "pb200_elapsed_between_ms"]
+           "pb200_comm_nccl_version", "pb200_mark", "pb200_elapsed_ms", "pb200_elapsed_between_ms", "pb200_format_score"]

@@ -74,3 +74,27 @@ def test_threaded_tabular_equals_single_thread(lib, monkeypatch):
     for t in ("2", "7", "16"):
         monkeypatch.setenv("PB200_HOST_THREADS", t)
         assert fastio.tabular_text(r, names, lib) == ref, t
+
+
+def test_score_text_is_printf_E_exactly(lib):
+    """pb200_format_score (the tabular writer's own '%E': 128-bit integer arithmetic, half-even on the exact binary value)
+    against Python's '%E' -- what the reference prints (phanotate.py:75-76) -- on random magnitudes, short decimals,
+    integers, exact ties at the seventh digit, and the values that take the sprintf route (0, inf, 1e300, denormals)."""
+    import ctypes
+    import random
+    buf = ctypes.create_string_buffer(64)
+
+    def text(x):
+        return buf.raw[:lib.pb200_format_score(x, buf)].decode()
+    rnd = random.Random(7)
+    xs = [12345675.0, 1234567.5, 0.5, 1.0, 9.9999995, 99999995.0, 9999999.5, 1e-16, 1.69e38, 123456.75, 1e22, 1e23, 5e-324, 0.0,
+          -0.0, float("inf"), float("-inf"), 1e300, -7.525584e174, 2.5e-5, 1.0000005, 1.0000015, -4.827981e2, -20.0]
+    for _ in range(60000):
+        x = -(10 ** rnd.uniform(-20, 42)) * rnd.uniform(0.1, 1)
+        if rnd.random() < 0.3:
+            x = -round(abs(x), rnd.randint(0, 8))
+        xs.append(x)
+    for k in range(1000000, 1000200):
+        xs += [k + 0.5, (k + 0.5) * 8, (k + 0.5) / 1024, (k + 0.5) * 1e3]
+    bad = [x for x in xs if text(x) != "%E" % x]
+    assert bad == [], bad[:5]
