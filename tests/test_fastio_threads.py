@@ -85,7 +85,8 @@ def test_score_text_is_printf_E_exactly(lib):
     buf = ctypes.create_string_buffer(64)
 
     def text(x):
-        return buf.raw[:lib.pb200_format_score(x, buf)].decode()
+        n = lib.pb200_format_score(x, buf)
+        return buf.raw[:n].decode()
     rnd = random.Random(7)
     xs = [12345675.0, 1234567.5, 0.5, 1.0, 9.9999995, 99999995.0, 9999999.5, 1e-16, 1.69e38, 123456.75, 1e22, 1e23, 5e-324, 0.0,
           -0.0, float("inf"), float("-inf"), 1e300, -7.525584e174, 2.5e-5, 1.0000005, 1.0000015, -4.827981e2, -20.0]
