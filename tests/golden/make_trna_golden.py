@@ -46,6 +46,9 @@ CASES = {
     "stress10_three": ("stress10", [(1500, 1572, False), (1600, 1672, False), (1700, 1771, True)], []),
     "stress14_one": ("stress14", [(2500, 2573, False)], []),
     "stress26_two": ("stress26", [(800, 872, True), (3000, 3072, False)], []),
+    # a contig long enough for the chunked solve (5,517 nodes): with hits it takes the one-warp sweep that knows their edges
+    "T4_eight": ("T4", [(70120, 70195, False), (70203, 70278, False), (70400, 70474, True), (71012, 71088, False), (71600, 71672, False),
+                        (72303, 72378, False), (72411, 72484, True), (73000, 73075, False)], [(1200, 1273), (160100, 160030)]),
 }
 
 ARAGORN = """#!/bin/sh
@@ -89,6 +92,7 @@ def trna_list(aragorn, scan):
 
 
 def main():
+    only = sys.argv[1:]
     import make_golden as MG
     from helpers import seq_of
     d = tempfile.mkdtemp(prefix="pb200_stubs_")
@@ -99,8 +103,11 @@ def main():
     from phanotate_modules.edges import Edge
     from phanotate_modules.nodes import Node  # noqa: F401
     assert functions.__file__.startswith("/root/reference")
-    out = {}
+    path = os.path.join(HERE, "trna.json")
+    out = json.load(open(path)) if only and os.path.exists(path) else {}
     for case, (contig, aragorn, scan) in CASES.items():
+        if only and case not in only:
+            continue
         set_case(d, aragorn, scan)
         seq = seq_of(contig)
         orfs = functions.get_orfs(MG.LocusShim(contig, seq))
