@@ -66,13 +66,16 @@ def tabular_text(res, names, lib=None) -> bytes:
     blob = b"".join(enc) or b"\0"
     calls = np.ascontiguousarray(res.calls)
     contigs = np.ascontiguousarray(res.contigs)
-    cap = 1 << 16
-    while True:
-        out = ctypes.create_string_buffer(cap)
-        got = int(lib.pb200_format_tabular(calls.ctypes.data, contigs.ctypes.data, len(enc), blob, off.ctypes.data, out, cap))
-        if got >= 0:
-            return out.raw[:got]
-        cap = -got + 64
+    # first call: how many bytes at most (returned negated); then one buffer that is never zero-filled or copied twice
+    need = -int(lib.pb200_format_tabular(calls.ctypes.data, contigs.ctypes.data, len(enc), blob, off.ctypes.data, None, 0))
+    if need <= 0:
+        return b""
+    out = np.empty(need, dtype=np.uint8)
+    got = int(lib.pb200_format_tabular(calls.ctypes.data, contigs.ctypes.data, len(enc), blob, off.ctypes.data,
+                                       out.ctypes.data, need))
+    if got < 0:
+        raise RuntimeError("pb200_format_tabular: buffer too small")
+    return out[:got].tobytes()
 
 
 def write_tabular(res, names, out, check=False, lib=None, skipped=None):
