@@ -154,6 +154,10 @@ int pb200_set_trnas(pb200_ctx* ctx, const int32_t* contig, const int32_t* start,
  * contigs cut out of a larger packed batch may start in the middle of a byte). */
 int64_t pb200_pack4(const uint8_t* bases, int64_t n, uint8_t* out);
 int pb200_upload_packed4(pb200_ctx* ctx, const uint8_t* packed, int32_t skip, const int64_t* offsets, int32_t n_contigs);
+/* pb200_upload / pb200_upload_packed4 without blocking the host: the copy is queued on `via`'s copy stream -- contexts that
+ * pass the same `via` get their copies one after the other in call order -- and ctx's stream waits for it on the device.
+ * skip < 0: one byte per base; 0 / 1: 4-bit letters.  The host buffers stay untouched until the run has finished. */
+int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int32_t skip, const int64_t* offsets, int32_t n_contigs);
 
 /* number added to the contig column of the call rows of the following runs (default 0): for a caller that cuts one
  * batch into groups for several contexts and wants the rows numbered in the whole batch */

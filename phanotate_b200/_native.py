@@ -78,6 +78,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_pack4.argtypes = [vp, ctypes.c_int64, vp]
     lib.pb200_pack4.restype = ctypes.c_int64
     lib.pb200_upload_packed4.argtypes = [vp, vp, i32, i64p, i32]
+    lib.pb200_upload_async.argtypes = [vp, vp, vp, i32, i64p, i32]
     lib.pb200_set_contig_base.argtypes = [vp, i32]
     lib.pb200_set_chunking.argtypes = [vp, i32, i32, i32, i32]
     lib.pb200_set_trnas.argtypes = [vp, vp, vp, vp, i32]
@@ -130,7 +131,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
-EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_upload", "pb200_upload_packed4", "pb200_pack4", "pb200_set_contig_base", "pb200_set_chunking", "pb200_set_trnas", "pb200_sizes", "pb200_stats",
+EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_upload", "pb200_upload_packed4", "pb200_upload_async", "pb200_pack4", "pb200_set_contig_base", "pb200_set_chunking", "pb200_set_trnas", "pb200_sizes", "pb200_stats",
            "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_gap_int_weights", "pb200_get_calls",
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_connect", "pb200_stage_times", "pb200_stage_gaps", "pb200_launch_count", "pb200_last_run_ms",

@@ -365,6 +365,8 @@ struct pb200_ctx {
     int ch_core = 256, ch_warm = 768, ch_margin = 64, ch_long = 4096;
     cudaEvent_t run_a = nullptr, run_b = nullptr, sync_ev = nullptr;
     void* comm = nullptr;        // CommState (comm.inc) once pb200_comm_init ran
+    cudaStream_t copy_stream = nullptr;   // pb200_upload_async: the stream several contexts queue their copies on, in order
+    cudaEvent_t upload_ev = nullptr;      // ... this context's letters have arrived
     cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 // wait for the context's stream.  PB200_BLOCKING_SYNC=1 (environment, read at pb200_create) makes the host thread sleep on
@@ -1024,6 +1026,8 @@ void pb200_destroy(pb200_ctx* ctx) {
     if (ctx->run_a) cudaEventDestroy(ctx->run_a);
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int k = 0; k < 4; k++)
         if (ctx->marks[k]) cudaEventDestroy(ctx->marks[k]);
     if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
@@ -1225,6 +1229,54 @@ int pb200_upload_packed4(pb200_ctx* ctx, const uint8_t* packed, int32_t skip, co
     CK(ctx_sync(ctx));
 #endif
     return 0;
+}
+
+// pb200_upload without blocking the host: the copy is queued on `via`'s copy stream (several contexts that pass the same
+// `via` get their copies one after the other, in call order: the first group's letters arrive first and its kernels start
+// while the others are still on the link), and ctx's own stream waits for it on the device.  skip < 0: one byte per base;
+// skip = 0 / 1: 4-bit letters (pb200_upload_packed4).  The host buffers must stay untouched until the run that uses them
+// has finished.  Then pb200_run(ctx, ..., PB200_REUSE_INPUT).
+int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int32_t skip, const int64_t* offsets, int32_t n_contigs) {
+    if (!ctx || !via || !data || !offsets || n_contigs < 1 || skip > 1) return -2;
+    const i64 nb = offsets[n_contigs];
+    if (nb < 1) {
+        ctx->err = "empty batch";
+        return -2;
+    }
+#ifndef PB_HOSTSIM
+    if (ctx->device != via->device) {
+        ctx->err = "pb200_upload_async: contexts on different devices";
+        return -2;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (!via->copy_stream) CK(cudaStreamCreateWithFlags(&via->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->upload_ev) CK(cudaEventCreateWithFlags(&ctx->upload_ev, cudaEventDisableTiming));
+    if (buf_ensure(ctx, ctx->in_seq, (size_t)nb + 64)) return -1;
+    if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
+    // (the previous run of this context has finished: pb200_run returns synchronised, so its buffers are free)
+    if (skip < 0) {
+        CK(cudaMemcpyAsync(ctx->in_seq.p, data, (size_t)nb, cudaMemcpyHostToDevice, via->copy_stream));
+    } else {
+        const size_t pbytes = (size_t)((nb + skip + 1) >> 1);
+        if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
+        CK(cudaMemcpyAsync(ctx->in_pack.p, data, pbytes, cudaMemcpyHostToDevice, via->copy_stream));
+    }
+    CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, via->copy_stream));
+    CK(cudaEventRecord(ctx->upload_ev, via->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->upload_ev, 0));
+    if (skip >= 0) {
+        i64 g = (nb / 16 + 255) / 256;
+        if (g > (i64)ctx->sm_count * 16) g = (i64)ctx->sm_count * 16;
+        if (g < 1) g = 1;
+        k_unpack4<<<(int)g, 256, 0, ctx->stream>>>((const unsigned char*)ctx->in_pack.p, skip, (unsigned char*)ctx->in_seq.p, nb);
+        CK(cudaGetLastError());
+    }
+    return 0;
+#else
+    (void)via;
+    if (skip < 0) return pb200_upload(ctx, data, offsets, n_contigs);
+    return stage_packed4(ctx, data, skip, offsets, n_contigs);
+#endif
 }
 
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {

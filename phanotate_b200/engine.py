@@ -417,7 +417,6 @@ class PipelinedEngine:
         nlive = len(live)
         import threading
         sized = [threading.Event() for _ in range(nlive)]        # lane j knows its table sizes
-        uploaded = [threading.Event() for _ in range(nlive)]     # lane j's letters are on the device
         sizes, stats, launches = [None] * nlive, [None] * nlive, [0] * nlive
         late = [False] * nlive                                   # lane j did not fit the output buffer: fetched afterwards
         ncont_total = sum(cuts[k + 1] - cuts[k] for k in live)
@@ -440,27 +439,27 @@ class PipelinedEngine:
             ct["node_off"] += node_off
             ct["orf_off"] += orf_off
 
+        # The copies of all groups are queued up front on ONE copy stream, in group order, without blocking anybody: the
+        # first (small) group's letters arrive first and its kernels start while the others are still on the link; every
+        # lane's stream waits for its own letters on the device (pb200_upload_async).
+        subs = []
+        for j, k in enumerate(live):
+            a, b = cuts[k], cuts[k + 1]
+            sub_o = np.ascontiguousarray(offsets[a:b + 1] - offsets[a])
+            # (4-bit letters: the group's bytes, and which nibble of the first one it starts at)
+            sub_b = bases[offsets[a] // 2:(offsets[b] + 1) // 2] if packed4 else bases[offsets[a]:offsets[b]]
+            subs.append((sub_b, sub_o))
+            e = self.engines[k]
+            e._ck(e.lib.pb200_set_contig_base(e.ctx, a))
+            if not resident:
+                e._ck(e.lib.pb200_upload_async(e.ctx, self.engines[live[0]].ctx, sub_b.ctypes.data,
+                                               (int(offsets[a]) & 1) if packed4 else -1, sub_o.ctypes.data, len(sub_o) - 1))
+
         def lane(j):
             k = live[j]
-            a, b = cuts[k], cuts[k + 1]
             e = self.engines[k]
             try:
-                sub_o = np.ascontiguousarray(offsets[a:b + 1] - offsets[a])
-                # (4-bit letters: the group's bytes, and which nibble of the first one it starts at)
-                sub_b = bases[offsets[a] // 2:(offsets[b] + 1) // 2] if packed4 else bases[offsets[a]:offsets[b]]
-                e._ck(e.lib.pb200_set_contig_base(e.ctx, a))
-                try:
-                    if not resident:
-                        # copies go in lane order, one at a time: the first (small) group's kernels start while the
-                        # others are still being copied, instead of all copies sharing the link and ending together
-                        if j and not uploaded[j - 1].wait(timeout=600):
-                            raise PhanotateError("an earlier group failed to upload")
-                        if packed4:
-                            e._ck(e.lib.pb200_upload_packed4(e.ctx, sub_b.ctypes.data, int(offsets[a]) & 1, sub_o.ctypes.data, len(sub_o) - 1))
-                        else:
-                            e._ck(e.lib.pb200_upload(e.ctx, sub_b.ctypes.data, sub_o.ctypes.data, len(sub_o) - 1))
-                finally:
-                    uploaded[j].set()
+                sub_b, sub_o = subs[j]
                 e.run_packed(sub_b, sub_o, params, fetch=False, literal=literal, call_weights=call_weights, flags=flags,
                              resident=True)
                 st = np.zeros(8, dtype=np.int64)
