@@ -53,6 +53,7 @@ static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
 PB_KERNEL(st_zero_tails)
 PB_KERNEL(st_scan)
 PB_KERNEL(st_mark)
+PB_KERNEL(st_word_contig)
 PB_KERNEL(st_count64)
 PB_KERNEL(st_contig_offsets)
 PB_KERNEL(st_node_pos)
