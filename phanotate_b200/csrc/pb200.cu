@@ -1056,6 +1056,10 @@ int pb200_run(pb200_ctx* ctx, const uint8_t* bases, const int64_t* offsets, int3
         if (ctx) ctx->err = "bad arguments";
         return -2;
     }
+    if ((flags & PB200_INPUT_PACKED4) && (flags & PB200_INPUT_DEVICE)) {
+        ctx->err = "PB200_INPUT_PACKED4 takes a host buffer (not with PB200_INPUT_DEVICE)";
+        return -2;
+    }
     ctx->have = false;
     Batch& B = ctx->B;
     memset(&B, 0, sizeof(B));
