@@ -97,15 +97,39 @@ PB_HDN Dec overlap_score(const Batch& B, int c, i32 e, i32 x, bool diff) {
     return sc;
 }
 // Stage 9/10: overlap edges out of exit node ni.  fill=false counts, fill=true writes.
+// The counting pass evaluates the predicate over the entries within 500 bp upstream and leaves WHICH of them matched as a
+// bit mask (bit k = node ni-1-k; the window is ~18 nodes, 64 covers all but pathologically dense stretches), so the
+// filling pass only expands the mask: no second round of other_end loads and predicate tests.
 PB_HDN void overlaps_of(const Batch& B, i32 ni, bool fill) {
     const u32 wx = B.n_pk[ni];                      // position << 4 | kind | frame << 2
     const int kx = (int)(wx & 3), fx = (int)((wx >> 2) & 3), r = (int)(wx >> 4);
     u32 cnt = 0;
     if (!kind_is_entry(kx)) {
+        u32 k = fill ? B.ov_cnt[ni] : 0;
+        if (fill) {
+            const u32 have = B.ov_cnt[ni + 1] - k;
+            u64 m = B.ov_mask[ni];
+            if (have == 0) return;
+            if (m) {                                    // the counting pass's matches, nearest entry first (as it found them)
+                while (m) {
+                    const int b = pb_ctz64(m);
+                    m &= m - 1;
+                    const i32 j = ni - 1 - b;
+                    const int ke = (int)(B.n_pk[j] & 3);
+                    B.ov_dst[k] = j;
+                    B.ov_src[k] = ni;
+                    // 'diff' = the two ORFs lie on different strands (functions.py:419-438): stop-key/stop-key or start/start
+                    B.ov_diff[k] = (u8)((ke == K_RSTOP && kx == K_FSTOP) || (ke == K_FSTART && kx == K_RSTART));
+                    k++;
+                }
+                return;
+            }
+        }
         const int c = contig_of_node(B, ni);
         const i32 first = B.cnode[c];
         const int ro = B.n_oth[ni];
-        u32 k = fill ? B.ov_cnt[ni] : 0;
+        u64 mask = 0;
+        bool fits = true;
         for (i32 j = ni - 1; j >= first; j--) {
             const u32 we = B.n_pk[j];
             const int l = (int)(we >> 4), ke = (int)(we & 3), fe = (int)((we >> 2) & 3);
@@ -124,9 +148,14 @@ PB_HDN void overlaps_of(const Batch& B, i32 ni, bool fill) {
                 B.ov_src[k] = ni;
                 B.ov_diff[k] = (u8)(ok == 2);
                 k++;
+            } else {
+                const i32 d = ni - 1 - j;
+                if (d < 64) mask |= 1ull << d;
+                else fits = false;
             }
             cnt++;
         }
+        if (!fill) B.ov_mask[ni] = fits ? mask : 0ull;     // (0 with a non-zero count: the filling pass tests again)
     }
     if (!fill) B.ov_cnt[ni] = cnt;
 }

@@ -138,6 +138,7 @@ struct Batch {
     WInt* o_wint;
     // explicit connectors (overlaps) in CSR by source exit node, and bridges by contig
     u32* ov_cnt;          // [nn+1] counts then exclusive offsets
+    u64* ov_mask;         // [nn] which of the 64 nodes in front of an exit node are its overlap targets (counting pass -> filling pass)
     i32 nov;
     i32 nbr;
     i32* ov_dst;
