@@ -860,11 +860,6 @@ static int bridge_tables(pb200_ctx* ctx) {
         B.br_wint = PB_ALLOC(3, WInt, nbr);
     }
     if (B.nbr > 0) PB_RUN(st_br_fill, B.nn);
-    {   // (behind the literal chain on this stream: ORF weights beyond 256 bits, hold.cuh)
-        u32 hg;
-        PB_FETCH(&hg, B.lit_cnt + 5, 4);
-        B.n_huge = (i32)hg;
-    }
     return 0;
 }
 static int literal_chain(pb200_ctx* ctx, i32 nlit) {
