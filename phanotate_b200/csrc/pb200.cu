@@ -52,7 +52,9 @@ static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
     }
 PB_KERNEL(st_zero_tails)
 PB_KERNEL(st_scan)
-PB_KERNEL(st_mark)
+static_assert((int)FLAG_SCAN_REFERENCE == (int)PB200_SCAN_REFERENCE, "flag value");
+PB_KERNEL(st_mark_starts)
+PB_KERNEL(st_mark_stops)
 PB_KERNEL(st_word_contig)
 PB_KERNEL(st_count64)
 PB_KERNEL(st_contig_offsets)

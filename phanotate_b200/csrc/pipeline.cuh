@@ -20,6 +20,7 @@
 
 // ------------------------------------------------------------------------------------------------
 enum { CLS_NONE = 0, CLS_S = 1, CLS_s = 2, CLS_T = 3, CLS_t = 4 };
+enum { FLAG_SCAN_REFERENCE = 8 };   // = PB200_SCAN_REFERENCE of the public header (asserted in pb200.cu)
 enum { K_FSTART = 0, K_FSTOP = 1, K_RSTOP = 2, K_RSTART = 3 };   // entry: FSTART,RSTOP  exit: FSTOP,RSTART
 enum {
     ERR_CHAR = 1,        // letter outside the 15 IUPAC codes -> KeyError (functions.py:20-24,169)
