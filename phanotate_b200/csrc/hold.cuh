@@ -191,15 +191,10 @@ PB_HD void orf_base_counts(const Batch& B, i64 oi, u32& na, u32& nt, u32& ng, u3
     if (x0 < 0) x0 = 0;
     if (x1 > L) x1 = L;
     const i64 cb = B.coff[c];
-    if (!rev) {
-        na = count_bits(B.bA, cb + x0, cb + x1);
-        nt = count_bits(B.bT, cb + x0, cb + x1);
-        ng = count_bits(B.bG, cb + x0, cb + x1);
-    } else {
-        na = count_bits(B.bT, cb + x0, cb + x1);
-        nt = count_bits(B.bA, cb + x0, cb + x1);
-        ng = count_bits(B.bC, cb + x0, cb + x1);
-    }
+    u32 n4[4];
+    count_bases4(B, cb + x0, cb + x1, n4);
+    if (!rev) na = n4[0], nt = n4[3], ng = n4[2];
+    else na = n4[3], nt = n4[0], ng = n4[1];
     len = (u32)(x1 - x0);
 }
 // Orf.p_stop (orfs.py:162-173) in Decimal arithmetic, every operation rounded to 28 digits

@@ -53,6 +53,7 @@ static_assert(sizeof(pb200_contig) == sizeof(ContigRec), "ContigRec layout");
 PB_KERNEL(st_zero_tails)
 PB_KERNEL(st_scan)
 static_assert((int)FLAG_SCAN_REFERENCE == (int)PB200_SCAN_REFERENCE, "flag value");
+PB_KERNEL(st_base_prefix)
 PB_KERNEL(st_mark_starts)
 PB_KERNEL(st_mark_stops)
 PB_KERNEL(st_word_contig)

@@ -178,6 +178,7 @@ struct Batch {
     u64* mS;
     u64* ms;
     u64* mT;
+    u64* pre4;            // per 64-base word: letters a | c<<16 | g<<32 | t<<48 counted from the start of the word's group of 32 words
     u64* mt;
     u64* bA;
     u64* bC;
