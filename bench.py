@@ -472,13 +472,24 @@ def main():
     # SURVEY.md 8d) -- half the bytes per step over PCIe.  The same leg from 1-byte letters is reported beside it.
     packed = peng.pack4(bases)
     peng.pin(packed)
+    trace = []                                                     # PB200_E2E_TRACE: host seconds of every run / gather of this rank
+    packed_b = packed.copy()                                       # the "next batch" of the double-buffered leg: its own host buffer
+    peng.pin(packed_b)
 
-    def e2e_step(ascii_input=False):
+    def e2e_step(ascii_input=False, k=0, nxt=False):
+        """k: step number (the 4-bit leg alternates between two pinned host buffers); nxt: the NEXT step's letters are
+        copied in while this step computes (PipelinedEngine.run_packed(prefetch=...): double buffering across steps --
+        every step's copy still happens inside the timed region, behind the previous step's kernels instead of in front
+        of its own)"""
         if ascii_input:
-            res = peng.run_packed(bases, offs, params)             # H2D letters+offsets, kernels, D2H calls+contig table
+            res = peng.run_packed(bases, offs, params, compact=True)   # H2D letters+offsets, kernels, D2H calls+contig table
         else:
-            res = peng.run_packed(packed, offs, params, packed4=True)
+            cur, other = (packed, packed_b) if k % 2 == 0 else (packed_b, packed)
+            t_a = time.perf_counter()
+            res = peng.run_packed(cur, offs, params, packed4=True, prefetch=(other, offs) if nxt else None, compact=True)
+            trace.append(["run", time.perf_counter() - t_a])
         moved = res.calls.nbytes + res.contigs.nbytes
+        t_a = time.perf_counter()
         if comm is not None:
             # every rank has its rows on its host; the cross-rank gather goes device to device over NCCL straight from the
             # lanes' tables, and rank 0 copies the other ranks' rows to its host
@@ -486,10 +497,13 @@ def main():
             # last one before the clock stops)
             if rank == 0:
                 comm.fetch_wait()
-            counts, total = comm.gather_calls(peng.engines)
+            counts, total = comm.gather_calls(peng.engines, compact=True)
             if rank == 0 and total > counts[0]:
-                comm.fetch_begin(counts[0], total - counts[0])
-                moved += (total - counts[0]) * N.CALL.itemsize
+                n_f = int((total - counts[0]) * float(os.environ.get("PB200_FETCH_FRAC", "1")))     # (experiments only)
+                if n_f > 0:
+                    comm.fetch_begin(counts[0], n_f)
+                moved += n_f * N.CALL24.itemsize
+            trace.append(["gather", time.perf_counter() - t_a])
         return res, moved
 
     def timed_resident_lanes(steps, warm):
@@ -529,8 +543,27 @@ def main():
         res, d2h = e2e_step()
     if comm is not None and rank == 0:
         comm.fetch_wait()                                          # the last step's rows of the other ranks are on the host
+    wall_e2e_plain = time.perf_counter() - t1
+    barrier()
+    # ... the same K steps double-buffered across steps: step k's run queues step k+1's letters behind its own (the first
+    # timed step starts with nothing prefetched, the last one prefetches nothing: K copies, all inside the timed region)
+    for k in range(2):
+        e2e_step(k=k, nxt=(k == 0))
+    if comm is not None and rank == 0:
+        comm.fetch_wait()
+    barrier()
+    t1 = time.perf_counter()
+    for k in range(args.steps):
+        res, d2h = e2e_step(k=k, nxt=(k + 1 < args.steps))
+    if comm is not None and rank == 0:
+        comm.fetch_wait()
     wall_e2e = time.perf_counter() - t1
     barrier()
+    if os.environ.get("PB200_E2E_TRACE"):
+        tr = trace[-2 * args.steps:] if comm is not None else trace[-args.steps:]
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump({"rank": rank, "wall_e2e": wall_e2e, "trace_ms": [[a, round(b * 1e3, 2)] for a, b in tr]},
+                  open("gpurun_out/e2e_trace_rank%d.json" % rank, "w"))
     # ... and from 1-byte letters
     e2e_step(True)
     barrier()
@@ -566,12 +599,13 @@ def main():
         eng.unpin(sb)
         strong = {"contigs_total": args.contigs, "contigs_this_rank": int(len(mine)), "ms": sms}
 
-    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0, lanes_ms / 1e3, wall_e2e_ascii], "max")
-    dev_s, wall_e2e, strong_s, lanes_s, wall_e2e_ascii = vals
+    vals = reduce([dev_ms / 1e3, wall_e2e, strong["ms"] / 1e3 if strong else 0.0, lanes_ms / 1e3, wall_e2e_ascii, wall_e2e_plain], "max")
+    dev_s, wall_e2e, strong_s, lanes_s, wall_e2e_ascii, wall_e2e_plain = vals
     sums = reduce([total_bp, ncalls, errs, mism, e2e_calls], "sum")
     job_bp, job_calls, errs, mism, job_e2e_calls = (int(round(x)) for x in sums)
 
     peng.unpin(packed)
+    peng.unpin(packed_b)
     peng.close()
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -624,7 +658,13 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes + offs.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * wall_e2e / args.steps,
                         "headline": "pinned host bases -> call tables on rank 0's host (SURVEY.md 8d)",
-                        "input": "4-bit letters, two bases per byte (pb200_pack4 / PB200_INPUT_PACKED4), expanded on the device"},
+                        "input": "4-bit letters, two bases per byte (pb200_pack4 / PB200_INPUT_PACKED4), expanded on the device",
+                        "output": "call rows as pb200_call24 (contig, left, right, strand, f64 score: the columns Locus.tabular prints; SURVEY.md 8d's 24 B per CDS) + the contig table",
+                        "double_buffering": "step k's run queues step k+1's letters (another pinned host buffer) behind its own "
+                                            "(pb200_prefetch_async); K host->device copies and K device->host reads inside the timed region"},
+                "e2e_no_prefetch": {"value": job_bp * args.steps / wall_e2e_plain / 1e9, "unit": UNIT,
+                                    "ms_per_step": 1e3 * wall_e2e_plain / args.steps,
+                                    "input": "4-bit letters; every step copies its own letters in first (round-2 mid-round definition)"},
                 "e2e_ascii_input": {"value": job_bp * args.steps / wall_e2e_ascii / 1e9, "unit": UNIT,
                                     "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes), "ms_per_step": 1e3 * wall_e2e_ascii / args.steps,
                                     "input": "one byte per base (any case, IUPAC)"},

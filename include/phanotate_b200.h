@@ -54,6 +54,11 @@ typedef struct pb200_call {     /* one CDS row of Locus.tabular (locus.py:39-56)
     double score;               /* float(weight), what '%E' prints  (phanotate.py:75-76) */
 } pb200_call;
 
+typedef struct pb200_call24 {   /* the same row without the Decimal weight: the columns Locus.tabular prints (24 bytes instead of 48 over PCIe / NVLink) */
+    int32_t contig, left, right, strand;
+    double score;
+} pb200_call24;
+
 typedef struct pb200_orf {      /* Orf (orfs.py:71-95) */
     int32_t contig, start, stop, frame;   /* start/stop = leftmost base of the codon, frame = +-1..3 */
     int32_t rbs_score;
@@ -158,6 +163,10 @@ int pb200_upload_packed4(pb200_ctx* ctx, const uint8_t* packed, int32_t skip, co
  * pass the same `via` get their copies one after the other in call order -- and ctx's stream waits for it on the device.
  * skip < 0: one byte per base; 0 / 1: 4-bit letters.  The host buffers stay untouched until the run has finished. */
 int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int32_t skip, const int64_t* offsets, int32_t n_contigs);
+/* Double buffering across batches: the NEXT batch's 4-bit letters are copied in while the current run is going (the packed
+ * buffer is free once the current batch has been expanded); the next pb200_upload_async with the same data / skip / size
+ * then sends only the offsets.  Same `via` as the uploads; `data` stays untouched until that run. */
+int pb200_prefetch_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int32_t skip, int64_t n_bases);
 
 /* number added to the contig column of the call rows of the following runs (default 0): for a caller that cuts one
  * batch into groups for several contexts and wants the rows numbered in the whole batch */
@@ -193,6 +202,7 @@ int pb200_get_orf_holds(pb200_ctx* ctx, pb200_dec* out);
 /* trunc(score_gap(len, 'same'|'diff') * 1000) for len = -2..300 per contig: 303 entries per contig each */
 int pb200_get_gap_int_weights(pb200_ctx* ctx, int64_t* same, int64_t* diff);
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out);
+int pb200_get_calls24(pb200_ctx* ctx, pb200_call24* out);   /* the same rows, compact */
 int pb200_get_contigs(pb200_ctx* ctx, pb200_contig* out);
 int pb200_get_orfs(pb200_ctx* ctx, pb200_orf* out);
 int pb200_get_nodes(pb200_ctx* ctx, pb200_node* out);
@@ -261,11 +271,15 @@ int pb200_comm_destroy(pb200_ctx* ctx);
  * then one grouped send/receive), no padding. */
 int pb200_comm_gather_calls(pb200_ctx* ctx, const void* const* parts, const int64_t* part_rows, int32_t nparts,
                             int64_t* counts_out, const pb200_call** rows_dev, int64_t* total);
-/* rank 0: rows [first, first+n) of the last gather -> host */
-int pb200_comm_fetch_gathered(pb200_ctx* ctx, int64_t first, int64_t n, pb200_call* out);
+/* the same gather with the rows converted to pb200_call24 on the way (parts still point to pb200_call records): half the
+ * bytes over NVLink and over rank 0's host link; the fetches below then deliver pb200_call24 rows */
+int pb200_comm_gather_calls24(pb200_ctx* ctx, const void* const* parts, const int64_t* part_rows, int32_t nparts,
+                              int64_t* counts_out, const pb200_call24** rows_dev, int64_t* total);
+/* rank 0: rows [first, first+n) of the last gather -> host (pb200_call or pb200_call24 records, as gathered) */
+int pb200_comm_fetch_gathered(pb200_ctx* ctx, int64_t first, int64_t n, void* out);
 /* rank 0: the same copy on its own stream, beside whatever the context runs next: _begin returns at once (page-locked
  * `out`), _wait blocks until the rows are there; the next gather waits for a pending copy by itself */
-int pb200_comm_fetch_begin(pb200_ctx* ctx, int64_t first, int64_t n, pb200_call* out);
+int pb200_comm_fetch_begin(pb200_ctx* ctx, int64_t first, int64_t n, void* out);
 int pb200_comm_fetch_wait(pb200_ctx* ctx);
 /* in-place reduction of n <= 64 doubles over the ranks (op 0 sum, 1 max); barrier */
 int pb200_comm_allreduce(pb200_ctx* ctx, double* vals, int32_t n, int32_t op);

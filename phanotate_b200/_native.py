@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libpb200.so")
 DEC = np.dtype([("c", "<u4", (4,)), ("e", "<i4"), ("neg", "<i4")])
 CALL = np.dtype([("contig", "<i4"), ("left", "<i4"), ("right", "<i4"), ("strand", "<i4"),
                  ("weight", DEC), ("score", "<f8")])
+CALL24 = np.dtype([("contig", "<i4"), ("left", "<i4"), ("right", "<i4"), ("strand", "<i4"), ("score", "<f8")])   # pb200_call24
 ORF = np.dtype([("contig", "<i4"), ("start", "<i4"), ("stop", "<i4"), ("frame", "<i4"), ("rbs_score", "<i4"),
                 ("trigger", "<i4"), ("start_weight", "<i4"), ("node", "<i4"), ("pstop", DEC), ("weight", DEC)])
 NODE = np.dtype([("contig", "<i4"), ("position", "<i4"), ("kind", "<i4"), ("frame", "<i4"), ("mate", "<i4"),
@@ -79,6 +80,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_pack4.restype = ctypes.c_int64
     lib.pb200_upload_packed4.argtypes = [vp, vp, i32, i64p, i32]
     lib.pb200_upload_async.argtypes = [vp, vp, vp, i32, i64p, i32]
+    lib.pb200_prefetch_async.argtypes = [vp, vp, vp, i32, ctypes.c_int64]
     lib.pb200_set_contig_base.argtypes = [vp, i32]
     lib.pb200_set_chunking.argtypes = [vp, i32, i32, i32, i32]
     lib.pb200_set_trnas.argtypes = [vp, vp, vp, vp, i32]
@@ -86,7 +88,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_get_orf_int_weights.argtypes = [vp, vp]
     lib.pb200_get_overlap_int_weights.argtypes = [vp, vp]
     lib.pb200_get_gap_int_weights.argtypes = [vp, vp, vp]
-    for f in ("pb200_get_calls", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_get_edges", "pb200_get_orf_holds"):
+    for f in ("pb200_get_calls", "pb200_get_calls24", "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_get_edges", "pb200_get_orf_holds"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pb200_build_edges.argtypes = [vp]
     lib.pb200_bellman_ford.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp]
@@ -117,6 +119,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.pb200_comm_init.argtypes = [vp, vp, i32, i32]
     lib.pb200_comm_destroy.argtypes = [vp]
     lib.pb200_comm_gather_calls.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.pb200_comm_gather_calls24.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.pb200_comm_fetch_gathered.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
     lib.pb200_comm_fetch_begin.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
     lib.pb200_comm_fetch_wait.argtypes = [vp]
@@ -131,7 +134,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
-EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_upload", "pb200_upload_packed4", "pb200_upload_async", "pb200_pack4", "pb200_set_contig_base", "pb200_set_chunking", "pb200_set_trnas", "pb200_sizes", "pb200_stats",
+EXPORTS = ["pb200_create", "pb200_destroy", "pb200_last_error", "pb200_run", "pb200_upload", "pb200_upload_packed4", "pb200_upload_async", "pb200_prefetch_async", "pb200_get_calls24", "pb200_comm_gather_calls24", "pb200_pack4", "pb200_set_contig_base", "pb200_set_chunking", "pb200_set_trnas", "pb200_sizes", "pb200_stats",
            "pb200_get_orf_int_weights", "pb200_get_overlap_int_weights", "pb200_get_gap_int_weights", "pb200_get_calls",
            "pb200_get_contigs", "pb200_get_orfs", "pb200_get_orf_holds", "pb200_get_nodes", "pb200_build_edges", "pb200_get_edges",
            "pb200_bellman_ford", "pb200_connect", "pb200_stage_times", "pb200_stage_gaps", "pb200_launch_count", "pb200_last_run_ms",

@@ -21,6 +21,7 @@
 
 static_assert(sizeof(pb200_dec) == sizeof(Dec), "Dec layout");
 static_assert(sizeof(pb200_call) == sizeof(CallRec), "CallRec layout");
+static_assert(sizeof(pb200_call24) == sizeof(Call24), "Call24 layout");
 static_assert(sizeof(pb200_edge) == sizeof(EdgeRec), "EdgeRec layout");
 static_assert(sizeof(pb200_orf) == sizeof(OrfRec), "OrfRec layout");
 static_assert(sizeof(pb200_node) == sizeof(NodeRec), "NodeRec layout");
@@ -371,6 +372,10 @@ struct pb200_ctx {
     void* comm = nullptr;        // CommState (comm.inc) once pb200_comm_init ran
     cudaStream_t copy_stream = nullptr;   // pb200_upload_async: the stream several contexts queue their copies on, in order
     cudaEvent_t upload_ev = nullptr;      // ... this context's letters have arrived
+    cudaEvent_t unpack_ev = nullptr;      // the 4-bit letters of the current batch have been expanded: in_pack is free again
+    const uint8_t* pf_ptr = nullptr;      // pb200_prefetch_async: the host buffer whose 4-bit letters already sit in in_pack
+    size_t pf_bytes = 0;
+    int pf_skip = 0;
     cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 // wait for the context's stream.  PB200_BLOCKING_SYNC=1 (environment, read at pb200_create) makes the host thread sleep on
@@ -950,6 +955,7 @@ static int stage_packed4(pb200_ctx* ctx, const uint8_t* packed, int skip, const 
     if (buf_ensure(ctx, ctx->in_off, (size_t)(n_contigs + 1) * 8)) return -1;
     if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
 #ifndef PB_HOSTSIM
+    ctx->pf_ptr = nullptr;
     CK(cudaMemcpyAsync(ctx->in_pack.p, packed, pbytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     i64 g = (nb / 16 + 255) / 256;
@@ -1026,6 +1032,7 @@ void pb200_destroy(pb200_ctx* ctx) {
     if (ctx->run_b) cudaEventDestroy(ctx->run_b);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
+    if (ctx->unpack_ev) cudaEventDestroy(ctx->unpack_ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int k = 0; k < 4; k++)
         if (ctx->marks[k]) cudaEventDestroy(ctx->marks[k]);
@@ -1261,8 +1268,13 @@ int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int3
         CK(cudaMemcpyAsync(ctx->in_seq.p, data, (size_t)nb, cudaMemcpyHostToDevice, via->copy_stream));
     } else {
         const size_t pbytes = (size_t)((nb + skip + 1) >> 1);
-        if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
-        CK(cudaMemcpyAsync(ctx->in_pack.p, data, pbytes, cudaMemcpyHostToDevice, via->copy_stream));
+        // (letters that pb200_prefetch_async already brought in during the previous run are not copied again)
+        const bool have = ctx->pf_ptr == data && ctx->pf_bytes == pbytes && ctx->pf_skip == skip;
+        ctx->pf_ptr = nullptr;
+        if (!have) {
+            if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
+            CK(cudaMemcpyAsync(ctx->in_pack.p, data, pbytes, cudaMemcpyHostToDevice, via->copy_stream));
+        }
     }
     CK(cudaMemcpyAsync(ctx->in_off.p, offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, via->copy_stream));
     CK(cudaEventRecord(ctx->upload_ev, via->copy_stream));
@@ -1273,6 +1285,8 @@ int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int3
         if (g < 1) g = 1;
         k_unpack4<<<(int)g, 256, 0, ctx->stream>>>((const unsigned char*)ctx->in_pack.p, skip, (unsigned char*)ctx->in_seq.p, nb);
         CK(cudaGetLastError());
+        if (!ctx->unpack_ev) CK(cudaEventCreateWithFlags(&ctx->unpack_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->unpack_ev, ctx->stream));
     }
     return 0;
 #else
@@ -1280,6 +1294,32 @@ int pb200_upload_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int3
     if (skip < 0) return pb200_upload(ctx, data, offsets, n_contigs);
     return stage_packed4(ctx, data, skip, offsets, n_contigs);
 #endif
+}
+// Double buffering across batches: queue the copy of the NEXT batch's 4-bit letters (n_bases of them from nibble `skip` of
+// `data`) into the context's packed-letter buffer while the current run is still going -- that buffer is free as soon as
+// the current batch has been expanded (k_unpack4, the first kernel of the run), and the copy stream waits for exactly
+// that.  The next pb200_upload_async with the same `data`, `skip` and size then only sends the offsets.  Call it after
+// the pb200_upload_async of the current batch, with the same `via`; `data` must stay untouched until that next run.
+int pb200_prefetch_async(pb200_ctx* ctx, pb200_ctx* via, const uint8_t* data, int32_t skip, int64_t n_bases) {
+    if (!ctx || !via || !data || n_bases < 1 || skip < 0 || skip > 1) return -2;
+#ifndef PB_HOSTSIM
+    if (ctx->device != via->device) {
+        ctx->err = "pb200_prefetch_async: contexts on different devices";
+        return -2;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (!via->copy_stream) CK(cudaStreamCreateWithFlags(&via->copy_stream, cudaStreamNonBlocking));
+    const size_t pbytes = (size_t)((n_bases + skip + 1) >> 1);
+    if (buf_ensure(ctx, ctx->in_pack, pbytes + 64)) return -1;
+    if (ctx->unpack_ev) CK(cudaStreamWaitEvent(via->copy_stream, ctx->unpack_ev, 0));
+    CK(cudaMemcpyAsync(ctx->in_pack.p, data, pbytes, cudaMemcpyHostToDevice, via->copy_stream));
+    ctx->pf_ptr = data;
+    ctx->pf_bytes = pbytes;
+    ctx->pf_skip = skip;
+#else
+    (void)via;   // (host build: nothing to overlap; the next upload copies as usual)
+#endif
+    return 0;
 }
 
 int pb200_set_contig_base(pb200_ctx* ctx, int32_t base) {
@@ -1431,6 +1471,41 @@ int pb200_get_overlap_int_weights(pb200_ctx* ctx, int64_t* out) {
 int pb200_get_calls(pb200_ctx* ctx, pb200_call* out) {
     if (!ctx || !ctx->have) return -2;
     if (ctx->B.ncalls > 0) PB_TO_HOST(out, ctx->B.calls, (size_t)ctx->B.ncalls * sizeof(CallRec));
+    return 0;
+}
+// call rows without the Decimal weight (pb200_call24), n of them from src to dst (both on the device)
+PB_HD void call24_of(const CallRec* src, Call24* dst, i64 i) {
+    Call24 r;
+    r.contig = src[i].contig;
+    r.left = src[i].left;
+    r.right = src[i].right;
+    r.strand = src[i].strand;
+    r.score = src[i].score;
+    dst[i] = r;
+}
+#ifndef PB_HOSTSIM
+__global__ void __launch_bounds__(256) k_calls24(const CallRec* src, Call24* dst, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) call24_of(src, dst, i);
+}
+static int calls24_launch(pb200_ctx* ctx, const CallRec* src, Call24* dst, i64 n, cudaStream_t st) {
+    if (n < 1) return 0;
+    k_calls24<<<grid_for(ctx, n, 256), 256, 0, st>>>(src, dst, n);
+    CK(cudaGetLastError());
+    return 0;
+}
+#endif
+int pb200_get_calls24(pb200_ctx* ctx, pb200_call24* out) {
+    if (!ctx || !ctx->have) return -2;
+    Batch& B = ctx->B;
+    if (B.ncalls < 1) return 0;
+    PB_PHASE(13, (size_t)B.ncalls * sizeof(Call24) + 1024);
+    Call24* tmp = PB_ALLOC(13, Call24, B.ncalls);
+#ifndef PB_HOSTSIM
+    if (calls24_launch(ctx, B.calls, tmp, B.ncalls, ctx->stream)) return -1;
+#else
+    for (i64 i = 0; i < B.ncalls; i++) call24_of(B.calls, tmp, i);
+#endif
+    PB_TO_HOST(out, tmp, (size_t)B.ncalls * sizeof(Call24));
     return 0;
 }
 

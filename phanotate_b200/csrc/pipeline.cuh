@@ -92,6 +92,11 @@ struct CallRec {          // one CDS call (contig, left, right, stran
     double score;
 };
 
+struct Call24 {           // = pb200_call24: a call row without the Decimal weight (what crosses PCIe / NVLink when only the printed columns are wanted)
+    i32 contig, left, right, strand;
+    double score;
+};
+
 struct EdgeRec {          // = pb200_edge
     i32 contig, src, dst, kind;
     Dec weight;

@@ -97,15 +97,19 @@ class Comm:
         self.total = 0
         self._host = np.zeros(0, dtype=N.CALL)
         self._async = [np.zeros(0, dtype=N.CALL), np.zeros(0, dtype=N.CALL)]
+        self._dtype = N.CALL                                       # rows of the last gather: pb200_call or pb200_call24
         self._flip, self._pending = 0, None
 
-    def gather_calls(self, engines=None):
+    def gather_calls(self, engines=None, compact=False):
         """Call tables -> rank 0's device memory.  engines: the contexts whose tables make up this rank's rows, in order
-        (the lanes of a PipelinedEngine); default: the communicator's own engine.  -> (rows per rank, total rows)"""
+        (the lanes of a PipelinedEngine); default: the communicator's own engine.  compact: the rows travel and arrive as
+        pb200_call24 records (no Decimal weight column; half the bytes).  -> (rows per rank, total rows)"""
+        fn = self.lib.pb200_comm_gather_calls24 if compact else self.lib.pb200_comm_gather_calls
+        self._dtype = N.CALL24 if compact else N.CALL
         counts = np.zeros(self.world, dtype=np.int64)
         total = ctypes.c_int64(0)
         if engines is None:
-            rc = self.lib.pb200_comm_gather_calls(self.e.ctx, None, None, 0, counts.ctypes.data, None, ctypes.byref(total))
+            rc = fn(self.e.ctx, None, None, 0, counts.ctypes.data, None, ctypes.byref(total))
         else:
             ptrs, rows = [], []
             for e in engines:
@@ -117,8 +121,7 @@ class Comm:
                 ptrs, rows = [0], [0]
             p = (ctypes.c_void_p * len(ptrs))(*ptrs)
             r = np.asarray(rows, dtype=np.int64)
-            rc = self.lib.pb200_comm_gather_calls(self.e.ctx, p, r.ctypes.data, len(ptrs), counts.ctypes.data, None,
-                                                  ctypes.byref(total))
+            rc = fn(self.e.ctx, p, r.ctypes.data, len(ptrs), counts.ctypes.data, None, ctypes.byref(total))
         self.e._ck(rc)
         self.counts, self.total = [int(c) for c in counts], int(total.value)
         return self.counts, self.total
@@ -127,10 +130,10 @@ class Comm:
         """rank 0: rows [first, first+n) of the last gather as a numpy array of pb200_call records -- a view into a
         page-locked buffer the communicator keeps (valid until the next fetch; copy it to keep it)"""
         n = self.total - first if n is None else n
-        if n > len(self._host):
+        if n > len(self._host) or self._host.dtype != self._dtype:
             if len(self._host):
                 self.e.unpin(self._host)
-            self._host = np.zeros(n + n // 4 + 1024, dtype=N.CALL)
+            self._host = np.zeros(n + n // 4 + 1024, dtype=self._dtype)
             self.e.pin(self._host)                 # page-locked: the device->host copy is plain DMA
         out = self._host[:n]
         if n:
@@ -144,10 +147,10 @@ class Comm:
         n = self.total - first if n is None else n
         self._flip ^= 1
         buf = self._async[self._flip]
-        if n > len(buf):
+        if n > len(buf) or buf.dtype != self._dtype:
             if len(buf):
                 self.e.unpin(buf)
-            buf = np.zeros(n + n // 4 + 1024, dtype=N.CALL)
+            buf = np.zeros(n + n // 4 + 1024, dtype=self._dtype)
             self.e.pin(buf)
             self._async[self._flip] = buf
         self._pending = buf[:n]

@@ -359,13 +359,15 @@ class PipelinedEngine:
         self.pool = ThreadPoolExecutor(len(self.engines))
         self.device = device
         self._calls = np.zeros(0, dtype=N.CALL)
+        self._calls24 = np.zeros(0, dtype=N.CALL24)
         self._contigs = np.zeros(0, dtype=N.CONTIG)
 
     def close(self):
-        for buf in (self._calls, self._contigs):
+        for buf in (self._calls, self._calls24, self._contigs):
             if len(buf):
                 self.engines[0].unpin(buf)
         self._calls = np.zeros(0, dtype=N.CALL)
+        self._calls24 = np.zeros(0, dtype=N.CALL24)
         self._contigs = np.zeros(0, dtype=N.CONTIG)
         for e in self.engines:
             e.close()
@@ -390,18 +392,11 @@ class PipelinedEngine:
     def pack4(self, bases):
         return self.engines[0].pack4(bases)
 
-    def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0, resident=False,
-                   fetch=True, packed4=False):
-        """resident=True: every lane still holds its group of this same batch from the previous call (no copy-in).
-        fetch=False: leave the tables on the device (returns None).
-        packed4=True: `bases` holds the 4-bit codes of the batch (pack4): half the bytes over the host link."""
-        if params is None:
-            params = make_params()
-        bases = np.ascontiguousarray(bases, dtype=np.uint8)
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    def _groups(self, offsets):
+        """consecutive groups of contigs, one per lane; the first is half as large as the others so that kernels start
+        early -> (cut points, lanes that get contigs)"""
         n = len(offsets) - 1
         lanes = min(len(self.engines), max(n, 1))
-        # consecutive groups of contigs; the first is half as large as the others so that kernels start early
         weights = [1.0] + [2.0] * (lanes - 1)
         import os
         if os.environ.get("PB200_LANE_WEIGHTS"):                  # experiments: relative sizes of the groups, e.g. "1,3,4,4"
@@ -413,7 +408,24 @@ class PipelinedEngine:
             c = int(np.searchsorted(offsets, int(offsets[-1] * acc / total), side="left"))
             cuts.append(min(max(c, cuts[-1]), n))
         cuts.append(n)
-        live = [k for k in range(lanes) if cuts[k + 1] > cuts[k]]
+        return cuts, [k for k in range(lanes) if cuts[k + 1] > cuts[k]]
+
+    def run_packed(self, bases, offsets, params=None, literal=False, call_weights=False, flags=0, resident=False,
+                   fetch=True, packed4=False, prefetch=None, compact=False):
+        """resident=True: every lane still holds its group of this same batch from the previous call (no copy-in).
+        fetch=False: leave the tables on the device (returns None).
+        packed4=True: `bases` holds the 4-bit codes of the batch (pack4): half the bytes over the host link.
+        prefetch=(bases, offsets) of the NEXT batch (4-bit letters, pinned, untouched until its own run_packed): its
+        letters are copied in while this batch computes (pb200_prefetch_async), so that run starts without waiting for
+        the host link.
+        compact=True: the call rows come back as pb200_call24 records (no Decimal weight column: the columns
+        Locus.tabular prints) -- half the bytes from the device."""
+        if params is None:
+            params = make_params()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        cuts, live = self._groups(offsets)
         nlive = len(live)
         import threading
         sized = [threading.Event() for _ in range(nlive)]        # lane j knows its table sizes
@@ -422,7 +434,9 @@ class PipelinedEngine:
         ncont_total = sum(cuts[k + 1] - cuts[k] for k in live)
         contigs = self._grow("_contigs", ncont_total, N.CONTIG)[:ncont_total] if fetch else None
         cont_off = np.concatenate(([0], np.cumsum([cuts[k + 1] - cuts[k] for k in live]))).astype(np.int64)
-        capacity = len(self._calls)                              # fixed during the run: nothing is re-pinned under a copy
+        cname, cdtype = ("_calls24", N.CALL24) if compact else ("_calls", N.CALL)
+        getter = "pb200_get_calls24" if compact else "pb200_get_calls"
+        capacity = len(getattr(self, cname))                     # fixed during the run: nothing is re-pinned under a copy
 
         def copy_out(j):
             k = live[j]
@@ -430,10 +444,10 @@ class PipelinedEngine:
             call_off = sum(sizes[i][6] for i in range(j))
             node_off = sum(sizes[i][2] for i in range(j))
             orf_off = sum(sizes[i][3] for i in range(j))
-            cl = self._calls[call_off:call_off + sizes[j][6]]
+            cl = getattr(self, cname)[call_off:call_off + sizes[j][6]]
             ct = contigs[cont_off[j]:cont_off[j + 1]]
             if len(cl):
-                e._ck(e.lib.pb200_get_calls(e.ctx, cl.ctypes.data))    # (rows already numbered in the whole batch)
+                e._ck(getattr(e.lib, getter)(e.ctx, cl.ctypes.data))   # (rows already numbered in the whole batch)
             e._ck(e.lib.pb200_get_contigs(e.ctx, ct.ctypes.data))
             ct["call_off"] += call_off
             ct["node_off"] += node_off
@@ -454,6 +468,18 @@ class PipelinedEngine:
             if not resident:
                 e._ck(e.lib.pb200_upload_async(e.ctx, self.engines[live[0]].ctx, sub_b.ctypes.data,
                                                (int(offsets[a]) & 1) if packed4 else -1, sub_o.ctypes.data, len(sub_o) - 1))
+        if prefetch is not None and packed4 and not resident:
+            nb_, no_ = prefetch
+            nb_ = np.ascontiguousarray(nb_, dtype=np.uint8)
+            no_ = np.ascontiguousarray(no_, dtype=np.int64)
+            cuts2, live2 = self._groups(no_)
+            if live2 and live2[0] == live[0]:                       # (the same copy stream as this batch's uploads)
+                for k in live2:
+                    a, b = cuts2[k], cuts2[k + 1]
+                    sub = nb_[no_[a] // 2:(no_[b] + 1) // 2]
+                    e = self.engines[k]
+                    e._ck(e.lib.pb200_prefetch_async(e.ctx, self.engines[live[0]].ctx, sub.ctypes.data, int(no_[a]) & 1,
+                                                     int(no_[b] - no_[a])))
 
         def lane(j):
             k = live[j]
@@ -486,12 +512,12 @@ class PipelinedEngine:
             return None
         ncalls = sum(z[6] for z in sizes)
         if any(late):
-            old = self._calls[:min(capacity, ncalls)].copy()
-            self._grow("_calls", ncalls + ncalls // 4, N.CALL)
-            self._calls[:len(old)] = old
+            old = getattr(self, cname)[:min(capacity, ncalls)].copy()
+            self._grow(cname, ncalls + ncalls // 4, cdtype)
+            getattr(self, cname)[:len(old)] = old
             for j in range(nlive):
                 if late[j]:
                     copy_out(j)
-        calls = self._calls[:ncalls]
+        calls = getattr(self, cname)[:ncalls]
         done = [(sizes[j], stats[j], launches[j]) for j in range(nlive)]
         return MergedResult(calls, contigs, [cuts[k] for k in live], sizes, [d[1] for d in done], sum(d[2] for d in done))

@@ -119,6 +119,30 @@ def check_packed4_input(e, make_pipelined):
     try:
         c = p.run_packed(pk, offs, packed4=True)
         assert np.array_equal(a.calls, c.calls) and np.array_equal(a.contigs["err"], c.contigs["err"])
+        # double buffering across batches (pb200_prefetch_async): batch X's run brings batch Y's letters in; Y's run finds
+        # them there; a run of something else in between must not use them
+        seqs2 = seqs[5:] + seqs[:3]
+        offs2 = np.zeros(len(seqs2) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs2], out=offs2[1:])
+        bases2 = np.frombuffer(b"".join(seqs2), dtype=np.uint8)
+        pk2 = e.pack4(bases2)
+        want2 = e.run_packed(bases2, offs2).calls.copy()
+        p.pin(pk)
+        p.pin(pk2)
+        c = p.run_packed(pk, offs, packed4=True, prefetch=(pk2, offs2))
+        assert np.array_equal(a.calls, c.calls)
+        assert np.array_equal(p.run_packed(pk2, offs2, packed4=True, prefetch=(pk, offs)).calls, want2)
+        assert np.array_equal(p.run_packed(pk, offs, packed4=True, prefetch=(pk, offs)).calls, a.calls)
+        assert np.array_equal(p.run_packed(pk2, offs2, packed4=True).calls, want2)         # (prefetched: pk, run: pk2)
+        assert np.array_equal(p.run_packed(pk, offs, packed4=True).calls, a.calls)
+        p.unpin(pk)
+        p.unpin(pk2)
+        # compact rows (pb200_call24): the same columns without the Decimal weight
+        c24 = p.run_packed(pk, offs, packed4=True, compact=True)
+        assert c24.calls.dtype == N.CALL24 and c24.calls.itemsize == 24 and len(c24.calls) == len(a.calls)
+        for col in ("contig", "left", "right", "strand", "score"):
+            assert np.array_equal(c24.calls[col], a.calls[col]), col
+        assert [c24.call_rows(k) for k in range(len(seqs))] == [a.call_rows(k) for k in range(len(seqs))]
     finally:
         p.close()
     bad = seqs[0][:900] + b"x" + seqs[0][900:2000]

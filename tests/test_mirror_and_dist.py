@@ -380,11 +380,29 @@ for rep in range(3):                                  # (the gather buffer and t
         rows = np.array(comm.fetch(0, total), copy=True)
         comm.fetch_begin(0, total)
         assert np.array_equal(comm.fetch_wait(), rows)
+# the same gather with compact rows (pb200_call24: converted on the device on the way; several segments per rank)
+mine = e.run([seqs[i] for i in parts[rank]])
+counts24, total24 = comm.gather_calls([e, e], compact=True)
+assert total24 == 2 * total and counts24[rank] == 2 * mine.n_calls
+if rank == 0:
+    rows24 = np.array(comm.fetch(0, total24), copy=True)
+    assert rows24.dtype == N.CALL24
+    comm.fetch_begin(0, total24)
+    assert np.array_equal(comm.fetch_wait(), rows24)
 comm.barrier()
 if rank == 0:
     whole = e.run(seqs).calls
     got = pdist.unshard_calls(rows, counts, parts)
     assert len(got) == len(whole) and np.array_equal(got, whole)
+    at = 0
+    for r in range(world):                       # rank r's rows twice (its two segments), column by column
+        n = counts[r]
+        ref = rows[sum(counts[:r]):sum(counts[:r]) + n]
+        for rep in range(2):
+            blk = rows24[at:at + n]
+            for col in ("contig", "left", "right", "strand", "score"):
+                assert np.array_equal(blk[col], ref[col]), (r, rep, col)
+            at += n
     print("NCCL_GATHER_OK", world, counts, e.lib.pb200_comm_nccl_version())
 comm.close()
 e.close()
