@@ -499,10 +499,8 @@ def main():
                 comm.fetch_wait()
             counts, total = comm.gather_calls(peng.engines, compact=True)
             if rank == 0 and total > counts[0]:
-                n_f = int((total - counts[0]) * float(os.environ.get("PB200_FETCH_FRAC", "1")))     # (experiments only)
-                if n_f > 0:
-                    comm.fetch_begin(counts[0], n_f)
-                moved += n_f * N.CALL24.itemsize
+                comm.fetch_begin(counts[0], total - counts[0])
+                moved += (total - counts[0]) * N.CALL24.itemsize
             trace.append(["gather", time.perf_counter() - t_a])
         return res, moved
 
