@@ -155,6 +155,36 @@ def test_packed4_input_on_host(sim):
 
 
 @pytest.mark.gpu
+def test_prefetch_of_a_larger_batch_on_gpu():
+    """pb200_prefetch_async while a run is going, for a next batch that does not fit the packed-letter buffer yet (the
+    buffer grows under the running batch), and a prefetched batch that is never run"""
+    from phanotate_b200 import synth
+    small_b, small_o = synth.synth4_batch(8, 20000)
+    big_b, big_o = synth.synth4_batch(40, 50000, first=100)
+    e = engine.Engine(0)
+    p = engine.PipelinedEngine(0, lanes=4)
+    try:
+        want_small = e.run_packed(small_b, small_o).calls.copy()
+        want_big = e.run_packed(big_b, big_o).calls.copy()
+        pk_s, pk_b = p.pack4(small_b), p.pack4(big_b)
+        p.pin(pk_s)
+        p.pin(pk_b)
+        for rep in range(3):
+            a = p.run_packed(pk_s, small_o, packed4=True, prefetch=(pk_b, big_o))
+            assert np.array_equal(a.calls, want_small), rep
+            b = p.run_packed(pk_b, big_o, packed4=True, prefetch=(pk_s, small_o), compact=True)
+            for col in ("contig", "left", "right", "strand", "score"):
+                assert np.array_equal(b.calls[col], want_big[col]), (rep, col)
+        a = p.run_packed(pk_b, big_o, packed4=True)                 # (the small batch was prefetched and is dropped)
+        assert np.array_equal(a.calls, want_big)
+        p.unpin(pk_s)
+        p.unpin(pk_b)
+    finally:
+        p.close()
+        e.close()
+
+
+@pytest.mark.gpu
 def test_packed4_input_on_gpu():
     e = engine.Engine(0)
     try:

@@ -72,12 +72,13 @@ def test_word_parallel_marks_one_long_contig_on_host(sim):
     check(sim, contigs(12, 1, 60000, 60001) + contigs(13, 2, 20000, 30000), [30, 90, 132])
 
 
-def test_word_parallel_marks_against_the_oracle_on_host(sim):
+@pytest.mark.parametrize("minlen", [90, 30, 132])
+def test_word_parallel_marks_against_the_oracle_on_host(sim, minlen):
     from oracle import phanotate_oracle as O
-    seqs = contigs(14, 6, 3000, 9000)
-    res = sim.run(seqs)
+    seqs = contigs(14 + minlen, 6 if minlen == 90 else 3, 3000, 9000 if minlen == 90 else 6000)
+    res = sim.run(seqs, params=engine.make_params(min_orf_len=minlen))
     for k, s in enumerate(seqs):
-        want = [tuple(r[:4]) for r in O.call_contig(s.decode())[3]]
+        want = [tuple(r[:4]) for r in O.call_contig(s.decode(), min_orf_len=minlen)[3]]
         assert [tuple(r) for r in res.call_rows(k)] == want, k
 
 
