@@ -221,14 +221,50 @@ PB_HD bool bridge_interval(const Batch& B, i32 i, int L, int& mi, int& me) {
     }
     return false;
 }
+PB_HDNI WInt bridge_wint_long(const Batch& B, int c, int len) {
+    WInt wi;
+    if (!dec_to_wint(gap_score(B, c, len, false), wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
+    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
+    return wi;
+}
+// The bridging pairs of interval start i (position `base`, last covered base `last`, base - last > 500): counted, or
+// written from slot k on.  left: exits with last-500 < l <= last+1 ; right: entries with base-1 <= r < base+500
+PB_HDN u32 bridge_pairs(const Batch& B, i32 i, int c, int base, int last, bool fill, u32 k) {
+    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
+    u32 cnt = 0;
+    i32 r0 = i;
+    while (r0 > nb && B.n_pos[r0 - 1] >= base - 1) r0--;          // same-position twins sort before i
+    for (i32 r = r0; r < ne && B.n_pos[r] < base + 500; r++) {
+        if (B.n_pos[r] < base - 1 || !kind_is_entry(B.n_kind[r] & 3)) continue;
+        for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
+            if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
+            int len = B.n_pos[r] - B.n_pos[l] - 3;
+            if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
+            if (fill) {
+                B.n_brs[l] |= 1;
+                B.br_src[k] = l;
+                B.br_dst[k] = r;
+                // score_gap(len > 300) = g**100 + len (functions.py:40-41): its integer is len*1000 + a per-contig constant
+                // for 3- and 4-digit lengths; longer gaps take the Decimal route
+                B.br_wint[k] = (len <= 9999) ? wint_from_i64((i64)len * 1000 + (len <= 999 ? B.cs[c].gap_hi3 : B.cs[c].gap_hi4))
+                                             : bridge_wint_long(B, c, len);
+                k++;
+            }
+            cnt++;
+        }
+    }
+    return cnt;
+}
 // exclusive prefix maximum of the interval ends over nodes [nb, ne) starting from `run`; returns the total.
-// (write = false: only the total)
+// write = false: only the total.  write = true: n_reach, and with it the number of bridging pairs of every node (br_cnt:
+// non-zero only for the rare interval start that begins more than 500 bp after the last covered base)
 PB_HDN int reach_range(const Batch& B, int c, i32 nb, i32 ne, int run, bool write, int lane, int NL) {
-    const int L = B.cs[c].L;
+    const int L = (int)(B.coff[c + 1] - B.coff[c]);
     for (i32 base = nb; base < ne; base += NL) {
         const i32 i = base + lane;
-        int v = 0, mi, me;
-        if (i < ne && bridge_interval(B, i, L, mi, me)) v = me - 1;
+        int v = 0, mi = 0, me;
+        const bool iv = i < ne && bridge_interval(B, i, L, mi, me);
+        if (iv) v = me - 1;
         int incl = v;
 #ifdef __CUDA_ARCH__
         for (int o = 1; o < 32; o <<= 1) {
@@ -242,7 +278,10 @@ PB_HDN int reach_range(const Batch& B, int c, i32 nb, i32 ne, int run, bool writ
 #else
         int excl = run, tot = incl;
 #endif
-        if (write && i < ne) B.n_reach[i] = excl;
+        if (write && i < ne) {
+            B.n_reach[i] = excl;
+            B.br_cnt[i] = (iv && mi > excl && mi - excl > 500) ? bridge_pairs(B, i, c, mi, excl, false, 0) : 0u;
+        }
         if (tot > run) run = tot;
     }
     return run;
@@ -251,52 +290,13 @@ PB_HDN void reach_contig(const Batch& B, int c, int lane, int NL) {
     if (B.ch_cnt[c + 1] > B.ch_cnt[c]) return;    // a long contig: reach_chunk_* (chunk.cuh)
     reach_range(B, c, B.cnode[c], B.cnode[c + 1], 0, true, lane, NL);
 }
-PB_HDNI WInt bridge_wint_long(const Batch& B, int c, int len) {
-    WInt wi;
-    if (!dec_to_wint(gap_score(B, c, len, false), wi)) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_OVERFLOW);
-    if (!wint_is_narrow(wi)) B.cs[c].wide = 1;
-    return wi;
-}
-PB_HDN void bridges_of(const Batch& B, i32 i, bool fill) {
-    const int c = contig_of_node(B, i);
-    const i32 nb = B.cnode[c], ne = B.cnode[c + 1];
-    const int L = B.cs[c].L;
-    u32 cnt = 0;
-    u32 k = fill ? B.br_cnt[i] : 0;
-    int mi, me;
-    const int last = B.n_reach[i];
-    if (bridge_interval(B, i, L, mi, me) && mi > last && mi - last > 500) {
-        const int base = mi;
-        // left: exits with last-500 < l <= last+1 ; right: entries with base-1 <= r < base+500
-        i32 r0 = i;
-        while (r0 > nb && B.n_pos[r0 - 1] >= base - 1) r0--;          // same-position twins sort before i
-        for (i32 r = r0; r < ne && B.n_pos[r] < base + 500; r++) {
-            if (B.n_pos[r] < base - 1 || !kind_is_entry(B.n_kind[r] & 3)) continue;
-            for (i32 l = i - 1; l >= nb && B.n_pos[l] > last - 500; l--) {
-                if (B.n_pos[l] > last + 1 || kind_is_entry(B.n_kind[l] & 3)) continue;
-                int len = B.n_pos[r] - B.n_pos[l] - 3;
-                if (B.n_pos[r] - B.n_pos[l] < 500) PB_ATOMIC_OR(&B.cs[c].err, (u32)ERR_PARALLEL);
-                if (fill) {
-                    B.n_brs[l] |= 1;
-                    B.br_src[k] = l;
-                    B.br_dst[k] = r;
-                    // score_gap(len > 300) = g**100 + len (functions.py:40-41): its integer is len*1000 + a per-contig constant
-                    // for 3- and 4-digit lengths; longer gaps take the Decimal route
-                    B.br_wint[k] = (len <= 9999) ? wint_from_i64((i64)len * 1000 + (len <= 999 ? B.cs[c].gap_hi3 : B.cs[c].gap_hi4))
-                                                 : bridge_wint_long(B, c, len);
-                    k++;
-                }
-                cnt++;
-            }
-        }
-    }
-    if (!fill) B.br_cnt[i] = cnt;
-}
-PB_HDN void st_br_count(const Batch& B, i64 i) {
-    if (i < B.nn) bridges_of(B, (i32)i, false);
-}
+// the pairs written (after the exclusive scan of br_cnt).  item = node
 PB_HDN void st_br_fill(const Batch& B, i64 i) {
-    if (i < B.nn) bridges_of(B, (i32)i, true);
+    if (i >= B.nn) return;
+    const u32 k = B.br_cnt[i];
+    if (B.br_cnt[i + 1] == k) return;             // (all but a few thousand nodes of a batch)
+    const int c = contig_of_node(B, (i32)i);
+    bridge_pairs(B, (i32)i, c, B.n_pos[i], B.n_reach[i], true, k);
 }
 
 // ------------------------------------------------------------------------------------------------

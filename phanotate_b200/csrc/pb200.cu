@@ -79,7 +79,6 @@ PB_KERNEL(st_gap_lut)
 PB_KERNEL(st_node_attrs)
 PB_KERNEL(st_ov_count)
 PB_KERNEL(st_ov_fill)
-PB_KERNEL(st_br_count)
 PB_KERNEL(st_br_fill)
 PB_KERNEL(st_backtrack)
 PB_KERNEL(st_tie_fix)
