@@ -1218,9 +1218,12 @@ PB_HDN void st_backtrack(const Batch& B, i64 c64) {
             cs->err |= ERR_INTERNAL;
             break;
         }
-        i32 orf = ((B.n_kind[x] & 3) == K_RSTART) ? B.n_orf[x] : B.n_orf[e];
+        // (the next step's load goes out before this step's store, which the compiler must assume may alias it: two
+        // dependent round trips per call instead of three)
+        const i32 xn = B.parent[e];                // exit node of the connector into e, or -2 = source
+        const i32 orf = ((B.n_kind[x] & 3) == K_RSTART) ? B.n_orf[x] : B.n_orf[e];
         out[n++] = orf;
-        x = B.parent[e];                           // exit node of the connector into e, or -2 = source
+        x = xn;
     }
     for (i32 a = 0, b = n - 1; a < b; a++, b--) {
         i32 t = out[a];
