@@ -320,13 +320,36 @@ PB_HDN void st_len_scatter(const Batch& B, i64 sl) {
 
 // Stage 7b+c: the per-codon product of the ORF in slot sl.  S holds its six HoldFac as
 // 18 U4 words with stride BD (shared memory on the GPU: S[(k*3+v)*BD + t]).
+// GC-frame factor class (0..5) of the codon that starts at batch position g: which of the strand's five class masks has
+// the bit; none = class 5 (the scan leaves no per-base class byte: only these few literal ORFs ever ask).  The five mask
+// words of the current 64 positions stay in registers: a walk along an ORF reloads them every 21 codons.
+struct ClassWin {
+    i64 w;
+    u64 m[5];
+};
+PB_HD int factor_class_at(ClassWin& cw, u64* const* M, i64 g) {
+    const i64 w = g >> 6;
+    if (w != cw.w) {
+        cw.w = w;
+#pragma unroll
+        for (int q = 0; q < 5; q++) cw.m[q] = M[q][w];
+    }
+    const int b = (int)(g & 63);
+    int k = 5;
+#pragma unroll
+    for (int q = 4; q >= 0; q--)
+        if ((cw.m[q] >> b) & 1ull) k = q;
+    return k;
+}
 PB_HDN void hold_run(const Batch& B, i32 sl, const U4* S, int BD, int t) {
     const i64 oi = orf_of_slot(B, sl);
     const int c = contig_of_orf(B, oi);
-    const u8* meta = B.meta + B.coff[c];
+    u64* const* M = B.o_frame[oi] < 0 ? B.cR : B.cF;
+    const i64 gb = B.coff[c] - 1;                  // position b of the contig = batch position gb + b
+    ClassWin cw;
+    cw.w = -1;
     const int start = B.o_start[oi], stop = B.o_stop[oi];
     const bool rev = B.o_frame[oi] < 0;
-    const int sh = rev ? 3 : 0;
     const int step = rev ? -3 : 3;
     const int n = orf_steps(start, stop, rev);
     // the fast path needs all six factors to carry exactly 28 digits
@@ -338,7 +361,7 @@ PB_HDN void hold_run(const Batch& B, i32 sl, const U4* S, int BD, int t) {
     // generic steps until the product carries 28 digits (normally just the first: 1 * f == f exactly)
     const Wide<4> lo27 = w_pow10<4>(27);
     while (it < n && !(fastok && hold.c.w[3] == 0 && w_cmp(hold.c, lo27) >= 0)) {
-        const int k = (meta[b - 1] >> sh) & 7;
+        const int k = factor_class_at(cw, M, gb + b);
         hold = dec_mul(hold, B.o_fac[(i64)sl * 6 + k]);             // functions.py:293,298
         it++;
         b += step;
@@ -347,10 +370,10 @@ PB_HDN void hold_run(const Batch& B, i32 sl, const U4* S, int BD, int t) {
         u32 a0 = hold.c.w[0], a1 = hold.c.w[1], a2 = hold.c.w[2];
         i32 eh = hold.e;
         // software pipeline: class of step it+1 and operands of step it are fetched one step ahead
-        int k = (meta[b - 1] >> sh) & 7;
+        int k = factor_class_at(cw, M, gb + b);
         U4 c27 = S[(k * 3 + 0) * BD + t], c28 = S[(k * 3 + 1) * BD + t], misc = S[(k * 3 + 2) * BD + t];
         b += step;
-        int knext = (it + 1 < n) ? ((meta[b - 1] >> sh) & 7) : 0;
+        int knext = (it + 1 < n) ? factor_class_at(cw, M, gb + b) : 0;
         for (; it < n; it++) {
             const int kcur = k;
             const U4 d27 = c27, d28 = c28, dmisc = misc;
@@ -359,7 +382,7 @@ PB_HDN void hold_run(const Batch& B, i32 sl, const U4* S, int BD, int t) {
             c28 = S[(k * 3 + 1) * BD + t];
             misc = S[(k * 3 + 2) * BD + t];
             b += step;
-            if (it + 2 < n) knext = (meta[b - 1] >> sh) & 7;
+            if (it + 2 < n) knext = factor_class_at(cw, M, gb + b);
             if (hold_step_fast(a0, a1, a2, eh, d27, d28, dmisc)) continue;
             // undecidable from 32 fraction bits: exact multiplication, then back to the fast path
             Dec h;

@@ -8,7 +8,7 @@
 // into /root/reference.
 //
 // HBM layout (structure of arrays, contigs concatenated):
-//   per base   : seq (input, 1 B), meta (1 B: GC-frame factor index fwd | rev), RBS scores (2 B), 26 bit masks (3.25 B)
+//   per base   : seq (input, 1 B), RBS scores (2 B), 26 bit masks (3.25 B; the GC-frame factor class of every codon start is five of them per strand)
 //   per 64 bp  : rank_nodes / rank_orfs (exclusive prefix counts -> node / ORF index of a position)
 //   per node   : position, kind, mate, ORF id, trigger, other_end, pstop index (sorted by contig, position)
 //   per ORF    : start, stop, frame, rbs score, start-codon weight id, pstop, weight (Dec), integer weight
@@ -110,7 +110,6 @@ struct Batch {
     i64 nb;
     const u8* seq;
     const i64* coff;
-    u8* meta;
     u64* rank;            // per 64-base block: low 32 = nodes before, high 32 = ORFs before
     CStat* cs;
     Dec* gap_same;
@@ -448,7 +447,7 @@ PB_HD void gc_class(int code, bool rev, int& imax, int& imin) {
 // Stage 1: per-base scan (functions.py:158-171 + codon classes of :196-215 + gc_frame_plot.py)
 // item = strip of SCAN_STRIP consecutive bases of the concatenated batch
 #define SCAN_STRIP 32
-PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1, u8* meta, int bitoff, u32* mk) {
+PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1, i64 cb, int bitoff, u32* mk) {
     CStat* cs = B.cs + c;
     const int n = i1 - i0;
     // ---- window sums Tz(j) = sum_{k=-19..20} gc0(j+3k), j = i0 .. i1+1
@@ -516,7 +515,6 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
         // factor index of the codon starting here, forward strand in bits 0-2, reverse strand in bits 3-5
         const int kf = TBL(gc_fac_index)[0][tr], kr = TBL(gc_fac_index)[1][tr];
-        meta[i] = (u8)(kf | (kr << 3));
         const u32 bit = 1u << (bitoff + k);
         if (kf < 5) mk[8 + kf] |= bit;
         if (kr < 5) mk[13 + kr] |= bit;
@@ -548,8 +546,8 @@ PB_HDN void scan_range(const Batch& B, int c, const u8* s, int L, int i0, int i1
         }
         if (sf) PB_ATOMIC_ADD(&cs->hist_bg[sf], 1u);
         if (sr) PB_ATOMIC_ADD(&cs->hist_bg[sr], 1u);
-        B.rbsf[(meta - B.meta) + i] = (u8)sf;
-        B.rbsr[(meta - B.meta) + i] = (u8)sr;
+        B.rbsf[cb + i] = (u8)sf;
+        B.rbsr[cb + i] = (u8)sr;
     }
     PB_ATOMIC_ADD(&cs->nAT, nAT);
     PB_ATOMIC_ADD(&cs->nGC, nGC);
@@ -570,7 +568,7 @@ PB_HDN void st_scan(const Batch& B, i64 strip) {
         int i0 = (int)(g - cb);
         i64 e = gend - cb;
         int i1 = (e < L) ? (int)e : L;
-        scan_range(B, c, B.seq + cb, L, i0, i1, B.meta + cb, (int)(g - g0), mk);
+        scan_range(B, c, B.seq + cb, L, i0, i1, cb, (int)(g - g0), mk);
         g = cb + i1;
     }
     ((u32*)B.mS)[strip] = mk[0];

@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
         const i64 tg0 = tile * ST_T;
         const i64 tg1 = (tg0 + ST_T < B.nb) ? tg0 + ST_T : B.nb;
         const i64 gb = tg0 + 8 * tid;                // this thread's bases: gb .. gb+7
-        u32 meta_lo = 0, meta_hi = 0;
         u64 acc_cls = 0, acc_cd = 0, acc_kf = 0, acc_kr = 0, acc_sf = 0, acc_sr = 0;
         uint4 raw = raw_next;
         if (use_tma) {
@@ -296,8 +295,6 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                     const int tr = gc_trits(tz[k], tz[k + 1], tz[k + 2]);
                     const u32 mb = S.facm[tr];
                     const u32 kf = mb & 7u, kr = mb >> 3;
-                    if (k < 4) meta_lo |= mb << (8 * k);
-                    else meta_hi |= mb << (8 * (k - 4));
                     // one bit per base in byte `value` of a 64-bit word: byte v of accX = the 8-base mask of "X == v"
                     acc_cls |= 1ull << (cls * 8 + k);
                     acc_cd |= 1ull << (cd0 * 8 + k);
@@ -413,7 +410,6 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
         if (8 * tid >= ST_T) {
             // (a thread beyond the tile's last base: nothing to store)
         } else if (gb + 8 <= B.nb) {
-            *(u64*)(B.meta + gb) = ((u64)meta_hi << 32) | meta_lo;
             *(u64*)(B.rbsf + gb) = acc_sf;
             *(u64*)(B.rbsr + gb) = acc_sr;
         } else {
@@ -421,8 +417,6 @@ __global__ void __launch_bounds__(ST_NT, 4) k_scan_tiles(const Batch B, i64 ntil
                 B.rbsf[gb + k] = (u8)(acc_sf >> (8 * k));
                 B.rbsr[gb + k] = (u8)(acc_sr >> (8 * k));
             }
-            for (int k = 0; k < 8 && gb + k < B.nb; k++)
-                B.meta[gb + k] = (u8)((k < 4 ? (meta_lo >> (8 * k)) : (meta_hi >> (8 * (k - 4)))) & 0xFFu);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
