@@ -68,6 +68,18 @@ def test_word_parallel_marks_equal_the_statement_on_host(sim):
     check(sim, contigs(11, 40, 1, 5000), MINLENS)
 
 
+def test_word_parallel_marks_at_word_and_run_boundaries_on_host(sim):
+    """contig lengths around multiples of the 64-base word and of the 8-word runs the stop-key stage hands its carries
+    along (MARK_RUN), packed one behind the other so that contig ends fall on every phase of a run"""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for L in [63, 64, 65, 127, 128, 129, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 9, 10, 3, 700, 1536]:
+        s = np.frombuffer(b"acgt", dtype=np.uint8)[rng.integers(0, 4, size=L)]
+        seqs.append(s.tobytes())
+    check(sim, seqs, [9, 30, 90])
+    check(sim, seqs[::-1], [30, 90])
+
+
 def test_word_parallel_marks_one_long_contig_on_host(sim):
     check(sim, contigs(12, 1, 60000, 60001) + contigs(13, 2, 20000, 30000), [30, 90, 132])
 
