@@ -121,7 +121,8 @@ enum {
     PB200_SOLVE_PLAIN = 64,   /* testing: the plain statement of the 128-bit sweep (every operand fetched when needed) instead
                                  of the windowed kernel */
     PB200_SOLVE_NOCHUNK = 128, /* testing: long contigs are solved by one sweep like the others, not in chunks */
-    PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel */
+    PB200_SCAN_REFERENCE = 8, /* testing: run the per-strip statement of the scan stage instead of the tiled kernel, and the
+                                 per-candidate statement of the node marks instead of the 64-positions-at-a-time form */
     PB200_LITERAL = 4         /* replay the reference's Decimal arithmetic for EVERY ORF and overlap edge inside
                                  pb200_run.  Default: the solve uses certified integer weights (exactly
                                  trunc(weight*1000), edges.py:22) and the 28-digit Decimal weights are computed
